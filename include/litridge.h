@@ -1,0 +1,189 @@
+/* litridge.h -- C ABI of the B200 (sm_100a) hot path of LITcoder's encoding models.
+ *
+ * The reference (GT-LIT-Lab/litcoder_core) is pure Python and has no FFI of its own; its
+ * boundary for this path is three Python call signatures
+ *     NestedCVModel.fit_predict      encoding/models/nested_cv.py:18-42
+ *     Downsampler.downsample         encoding/downsample/downsampling.py:395-424
+ *     FIR.make_delayed               encoding/features/FIR_expander.py:24-43
+ * The Python package `litcoder_core_b200` mirrors those signatures and drives the entry
+ * points below through ctypes.  Each entry point replaces one (group of) torch / NumPy /
+ * SciPy call site(s) of the reference, cited next to it.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative errno-style code; the message is
+ *     available from lit_last_error() (thread-local);
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_h`;
+ *   - matrices are row-major fp32 with an explicit leading dimension (pitch, in elements);
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on that stream
+ *     unless stated otherwise; nothing here allocates device memory behind the caller's
+ *     back except lit_syevd's workspace query helper (sizes are reported, caller allocates);
+ *   - a "split pair" (hi, lo) is the 3xTF32 representation of an fp32 matrix:
+ *     hi = rna_tf32(x), lo = rna_tf32(x - hi); the two planes share one pitch.
+ */
+#ifndef LITRIDGE_H_
+#define LITRIDGE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LITRIDGE_ABI_VERSION 1
+
+const char* lit_last_error(void);
+int lit_abi_version(void);
+/* SM count, compute capability and memory of the current device. */
+int lit_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* free_bytes, size_t* total_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contractions: 3xTF32 tcgen05 GEMMs
+ * ---------------------------------------------------------------------------------------- */
+enum lit_gemm_variant {
+  LIT_GEMM_AUTO = 0,
+  LIT_GEMM_1CTA_N256 = 1, /* 128x256 tile per CTA, cta_group::1 */
+  LIT_GEMM_1CTA_N128 = 2, /* 128x128 tile per CTA, cta_group::1 */
+  LIT_GEMM_2CTA_N256 = 3  /* 256x256 tile per CTA pair, cta_group::2 */
+};
+
+/* D[M,N] = alpha * A[M,K] * B[N,K]^T + beta * Cin[M,N]   (Cin may be NULL).
+ * A and B are split pairs.  If D_lo is non-NULL the result is written as a split pair
+ * (D = hi, D_lo = lo) so it can feed the next GEMM directly.
+ * Replaces torch.matmul at ridge_regression.py:32,59-61,104,105 and nested_cv.py:151,251
+ * (after the Gram/eigen reformulation described in DESIGN.md). */
+int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,
+                       int M, int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D, float* D_lo,
+                       long ldd, int variant, void* stream);
+
+/* Prediction GEMM with the correlation reduction fused into the epilogue.
+ *   acc[v, g*R + t] = sum_k A[v,k] * B[g*R + t, k]       v < M (voxels), g < n_groups, t < R
+ *   dot_part[tile][v] = sum_{t in tile} acc * Yz[t][v]      ssq_part[tile][v] = sum_{t in tile} acc^2
+ * with R = rows_per_group (multiple of 256; pad rows of B and Yz must be zero) and
+ * tile = g*(R/256) + t/256.  Yz is [R][ldy] (time-major, voxel contiguous).
+ * Replaces the per-alpha loop body of ridge_corr_torch (ridge_regression.py:115-125) and the
+ * outer-test prediction + per-voxel Pearson loop (nested_cv.py:151,251,418-438). */
+int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo,
+                            long ldb, int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy,
+                            float* dot_part, float* ssq_part, long ld_part, int variant, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / conversion (bandwidth-bound streaming kernels)
+ * ---------------------------------------------------------------------------------------- */
+/* dst[i] = (float)src[i]   -- the torch.tensor(..., dtype=float32) of nested_cv.py:99-100. */
+int lit_convert_f64_to_f32(const double* src, float* dst, size_t n, void* stream);
+/* dst[i] = (double)src[i]. */
+int lit_convert_f32_to_f64(const float* src, double* dst, size_t n, void* stream);
+/* hi/lo TF32 split of a [rows][cols] matrix (hi or lo may alias src). */
+int lit_split_tf32(const float* src, long rows, long cols, long ld_src, float* hi, float* lo, long ld_dst,
+                   void* stream);
+/* dst[c][r] = src[r][c]; if dst_lo != NULL the result is written as a split pair. */
+int lit_transpose_f32(const float* src, long rows, long cols, long ld_src, float* dst, float* dst_lo, long ld_dst,
+                      void* stream);
+/* dst[i][:] = src[idx[i]][:] for i < n_idx, zero rows for n_idx <= i < n_rows_out.
+ * idx == NULL means the identity (a padded copy).  Optional split output.
+ * Replaces the fancy-index gathers at nested_cv.py:200-201,371-374. */
+int lit_gather_rows_f32(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, float* dst,
+                        float* dst_lo, long ld_dst, long n_rows_out, void* stream);
+/* dst[c][i] = src[idx[i]][c] for i < n_idx (zero for n_idx <= i < ld_dst): gather + transpose,
+ * written as a split pair; this is how the K-major (time-contiguous) operands X^T and Y^T of
+ * a fold's training rows are produced. */
+int lit_gather_rows_transpose_split(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                                    float* dst_hi, float* dst_lo, long ld_dst, void* stream);
+/* y[i] += a * (x_hi[i] (+ x_lo[i])) over a [rows][cols] matrix (x_lo may be NULL). */
+int lit_axpy_f32(float a, const float* x_hi, const float* x_lo, long ld_x, float* y, long ld_y, long rows, long cols,
+                 void* stream);
+int lit_fill_f32(float* dst, size_t n, float value, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Column statistics / normalisation  (ridge_utils.py:6-15 z_score, :70-180 DataNormalizer)
+ * ---------------------------------------------------------------------------------------- */
+/* Per-column mean and std over the gathered rows idx (NULL = all n rows).  ddof = 1 matches
+ * torch.std (unbiased), ddof = 0 NumPy.  Accumulation is in fp64; outputs fp32. */
+int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, int ddof, float* mean,
+                  float* std, void* stream);
+/* dst[i][c] = (src[idx[i]][c] - mean[c]) * scale(c), zero rows up to n_rows_out, where
+ *   mode 0: scale = 1 / (std[c] + eps)                  (z_score, eps = 1e-8)
+ *   mode 1: scale = 1 / (std[c] * sqrt(n_idx - 1))      (unit-norm centred column; 0 if std == 0)
+ *   mode 2: scale = 1                                   (centre only)
+ * Optional split output. */
+int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                              const float* mean, const float* std, int mode, float eps, float* dst, float* dst_lo,
+                              long ld_dst, long n_rows_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Eigen-decomposition of the p x p Gram (the only library call: cuSOLVER syevd)
+ * replaces torch.linalg.svd in svd_wrapper (ridge_utils.py:49-67).
+ * ---------------------------------------------------------------------------------------- */
+/* Workspace size in bytes (device and host) for lit_syevd at order n. */
+int lit_syevd_workspace(int n, size_t* device_bytes, size_t* host_bytes);
+/* In place: on exit row j of G (pitch ld == n required) is the j-th eigenvector, lam ascending.
+ * info is a device int (0 on success). work/work_h from lit_syevd_workspace. */
+int lit_syevd(float* G, int n, float* lam, void* work, size_t work_bytes, void* work_h, size_t work_h_bytes,
+              int* info, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ridge-specific elementwise kernels
+ * ---------------------------------------------------------------------------------------- */
+/* Stacked, column-centred, alpha-weighted validation design in the eigenbasis:
+ *   Lst[a*rows_pad + t][j] = (L[t][j] - mean_t L[:,j]) * keep_j / (lam_j + (alpha_a * s)^2)
+ * s = sqrt(max(lam)) if normalpha else 1;  keep_j = sqrt(max(lam_j,0)) > singcutoff;
+ * rows t >= n_rows are zero.  Output is a split pair of shape [n_alphas*rows_pad][k].
+ * (ridge_regression.py:97-101,117-120 with D = S/(S^2+a^2) folded into the Gram form.) */
+int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, long rows_pad, int k, const float* lam,
+                          const float* alphas, int n_alphas, int normalpha, float singcutoff, float* out_hi,
+                          float* out_lo, long ld_out, void* stream);
+/* Per-voxel shrinkage in the eigenbasis: out[v][j] = (Z_hi+Z_lo)[v][j] * keep_j / (lam_j + (alpha_v * s)^2)
+ * written as a split pair (ridge_regression.py:56-61 for every voxel at once). */
+int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, long n_vox, int k, const float* lam,
+                            const float* alpha_v, int normalpha, float singcutoff, float* out_hi, float* out_lo,
+                            long ld_out, void* stream);
+/* Inner-CV score from the fused partials (ridge_regression.py:122-133):
+ *   corr[a][v] = nan_to_num( (sum_tiles dot / n_rows) / (sqrt(sum_tiles ssq / (n_rows-1)) + eps) )
+ * accumulate != 0 adds into corr (fold sum for nested_cv.py:391-393). */
+int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group, int n_groups,
+                      long n_vox, long n_rows, float eps, int accumulate, float* corr, long ld_corr, void* stream);
+/* best[v] = first argmax_a mean[a][v], mean = corr_sum / n_folds (nested_cv.py:391-393,408-411);
+ * alpha_out[v] = (float)alphas[best[v]].  col_sums (n_alphas doubles, may be NULL) receives
+ * sum_v mean[a][v] for the single_alpha rule (nested_cv.py:396-400). */
+int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_vox, int n_folds, const float* alphas,
+                     int32_t* best, float* alpha_out, double* col_sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Test statistics (nested_cv.py:418-477, statsmodels fdrcorrection)
+ * ---------------------------------------------------------------------------------------- */
+/* r[v] = clip(sum_tiles dot / sqrt(sum_tiles ssq), -1, 1) (Yz must hold unit-norm centred columns),
+ * NaN -> r = 0, p = 1; p = two-sided Student-t / Beta(n/2-1, n/2-1) p-value of r with n samples,
+ * evaluated in fp64; if p_round_f32 != 0 it is rounded through fp32 (SciPy >= 1.14 keeps the
+ * input dtype, so the reference run in this image produces fp32 p-values). */
+int lit_pearson_finalize(const float* dot_part, const float* ssq_part, long ld_part, int n_tiles, long n_vox,
+                         long n_samples, int p_round_f32, float* r, double* p, void* stream);
+/* Benjamini-Hochberg: reject[v] (uint8), p_adj[v], *count_out (device int).  Scratch: see
+ * lit_bh_workspace.  Sorting is a hand-written bitonic network (keys padded to a power of two). */
+int lit_bh_workspace(long n, size_t* bytes);
+int lit_bh_fdr(const double* p, long n, double alpha_fdr, uint8_t* reject, double* p_adj, int* count_out, void* work,
+               size_t work_bytes, void* stream);
+/* Fisher's method across n_folds p-value vectors (p is [n_folds][ld_p]); all-ones -> 1.0;
+ * p_round_f32 as above. */
+int lit_fisher_combine(const double* p, long ld_p, int n_folds, long n_vox, int p_round_f32, double* p_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Feature construction
+ * ---------------------------------------------------------------------------------------- */
+/* FIR delay stacking (FIR_expander.py:24-43): out[t][i*ndim + c] = stim[t - delays[i]][c] or 0
+ * (circpad: index mod nt).  dtype_in: 0 = f32, 1 = f64.  out is [nt][ndelays*ndim] f64, pitch ld_out. */
+int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, long ndim, long ld_stim, const int32_t* delays,
+                         int ndelays, int circpad, double* out, long ld_out, void* stream);
+/* Lanczos resampling (interpdata.py:45-63,87-126): out = W * data, W[i][j] = lanczos((tr_i - t_j) * cutoff),
+ * cutoff = cutoff_mult / mean(diff(tr_times)) computed by the caller.  rectify -> out is [n_tr][2*ndim]
+ * (negative part | positive part).  lo/hi (n_tr + 1 int32, or NULL) bound the contributing samples of
+ * each TR when data_times is sorted: TR i only reads samples [lo[i], hi[i]). */
+int lit_lanczos_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                           const double* data_times, const double* tr_times, long n_tr, int window, double cutoff,
+                           int rectify, const int32_t* lo, const int32_t* hi, double* out, long ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITRIDGE_H_ */

@@ -1,0 +1,494 @@
+// 3xTF32 split-precision GEMM on the sm_100a tensor cores (tcgen05 + TMEM + TMA).
+//
+//   D[M,N] = alpha * A[M,K] * B[N,K]^T (+ beta * Cin)        ("NT": both operands K-major)
+//
+// Every dense contraction of the nested-CV ridge path is expressed in this one form
+// (see DESIGN.md): the Gram X^T X, the cross product Y^T X, the rotation into the
+// eigenbasis, the per-alpha validation predictions and the weight solve.  They replace
+// the torch.matmul / torch.linalg.svd call sites of the reference
+// (encoding/models/ridge_regression.py:32,59-61,104-105,120; nested_cv.py:151,251).
+//
+// Precision: operands arrive as two fp32 planes hi = rna_tf32(x), lo = rna_tf32(x - hi)
+// (both exactly representable in TF32), and each k-step issues three kind::tf32 MMAs
+//   lo*hi + hi*lo + hi*hi
+// into the same fp32 TMEM accumulator, which recovers ~fp32 accuracy (error ~2^-21).
+//
+// Kernel structure (persistent, warp-specialised, one CTA or one CTA pair per SM):
+//   warp 0   : TMA producer  (4 tiled loads per k-block: A_hi, A_lo, B_hi, B_lo; SWIZZLE_128B)
+//   warp 1   : MMA issuer    (one thread issues tcgen05.mma; commits free the smem stage)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld from a double-buffered accumulator)
+// Two epilogues:
+//   EPI_STORE : D = alpha*acc + beta*Cin, optionally written as a (hi, lo) TF32 split pair
+//   EPI_CORR  : fused column reduction for per-voxel correlation.  Accumulator rows are
+//               voxels, columns are (alpha group, time) pairs; each thread reduces its row
+//               against the z-scored responses Yz[t][v] and emits per-tile partial sums
+//               sum(pred*yz) and sum(pred^2).  Predictions never reach HBM
+//               (the reference materialises them per alpha: ridge_regression.py:120-125).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "../../include/litridge.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace lit {
+
+enum { EPI_STORE = 0, EPI_CORR = 1 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles;  // in units of BM*CG rows
+  int num_n_tiles;
+  int num_k_blocks;
+  int group_m;  // rasterisation group (tiles along M that share a B tile wave)
+  // EPI_STORE
+  float* D;
+  float* D_lo;  // optional: when non-null D receives hi and D_lo receives lo
+  long ldd;
+  const float* Cin;
+  long ldc;
+  float alpha, beta;
+  // EPI_CORR
+  const float* Yz;  // [tiles_per_group*BN rows][>= M cols], row pitch ldy
+  long ldy;
+  int tiles_per_group;
+  float* dot_part;  // [num_n_tiles][ld_part]
+  float* ssq_part;
+  long ld_part;
+};
+
+template <int BN_, int CG_>
+struct GemmShape {
+  static constexpr int BM = 128;  // accumulator rows per CTA (= TMEM lanes)
+  static constexpr int BN = BN_;  // accumulator columns
+  static constexpr int BK = 32;   // fp32 per k-block = one 128-byte swizzle span
+  static constexpr int CG = CG_;  // CTAs cooperating on one MMA (cta_group)
+  static constexpr int UMMA_K = 8;
+  static constexpr int B_ROWS = BN / CG;  // rows of B staged by each CTA
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = B_ROWS * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+  static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // tiles; barriers + alignment slack live in the rest
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols pow2");
+  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+};
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& mt, int& nt) {
+  const int gsz = p.group_m * p.num_n_tiles;
+  const int g = tile / gsz;
+  const int first_m = g * p.group_m;
+  const int gm = min(p.num_m_tiles - first_m, p.group_m);
+  const int r = tile - g * gsz;
+  mt = first_m + r % gm;
+  nt = r / gm;
+}
+
+template <int BN, int CG, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                   const GemmParams p) {
+  using S = GemmShape<BN, CG>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment (same offset in both CTAs of a pair).
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmAh);
+    ptx::prefetch_tensormap(&tmAl);
+    ptx::prefetch_tensormap(&tmBh);
+    ptx::prefetch_tensormap(&tmBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], CG * 4);  // one arrive per epilogue warp of every CTA
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<CG>(tmem_ptr_smem, S::TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / CG;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+        int mt, nt;
+        tile_coords(p, tile, mt, nt);
+        const int m_row = (mt * CG + (int)cta_rank) * S::BM;
+        const int n_row = nt * BN + (int)cta_rank * S::B_ROWS;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * S::STAGE_BYTES;
+          const int k0 = kb * S::BK;
+          if constexpr (CG == 1) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+            ptx::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m_row);
+            ptx::tma_load_2d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
+            ptx::tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
+            ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+          } else {
+            // Both CTAs load their halves; all bytes are accounted on the leader's barrier.
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            ptx::tma_load_2d_2sm(st, &tmAh, &full_bar[stage], k0, m_row);
+            ptx::tma_load_2d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
+            ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
+            ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+          }
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_tf32(S::BM * CG, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t st = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + S::A_BYTES;
+          const uint32_t b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < S::BK / S::UMMA_K; ++ks) {
+            const uint32_t koff = ks * S::UMMA_K * 4;  // bytes along K inside the swizzle span
+            const uint64_t dah = ptx::umma_desc_k_sw128(a_hi + koff);
+            const uint64_t dal = ptx::umma_desc_k_sw128(a_lo + koff);
+            const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + koff);
+            const uint64_t dbl = ptx::umma_desc_k_sw128(b_lo + koff);
+            ptx::umma_tf32<CG>(d_tmem, dal, dbh, idesc, (kb | ks) != 0);
+            ptx::umma_tf32<CG>(d_tmem, dah, dbl, idesc, 1u);
+            ptx::umma_tf32<CG>(d_tmem, dah, dbh, idesc, 1u);
+          }
+          if constexpr (CG == 1)
+            ptx::umma_commit(&empty_bar[stage]);
+          else
+            ptx::umma_commit_2sm_mc(&empty_bar[stage], 0b11);
+          if (++stage == S::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if constexpr (CG == 1)
+          ptx::umma_commit(&tmem_full_bar[as]);
+        else
+          ptx::umma_commit_2sm_mc(&tmem_full_bar[as], 0b11);
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+      int mt, nt;
+      tile_coords(p, tile, mt, nt);
+      const int as = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tc_fence_after();
+      const long row = (long)(mt * CG + (int)cta_rank) * S::BM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
+
+      if constexpr (EPI == EPI_STORE) {
+        for (int c = 0; c < BN / 32; ++c) {
+          const long n0 = (long)nt * BN + c * 32;
+          if (n0 >= p.N) break;  // warp-uniform
+          float v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+            float* drow = p.D + row * p.ldd + n0;
+            float* lrow = p.D_lo ? p.D_lo + row * p.ldd + n0 : nullptr;
+            const float* crow = p.Cin ? p.Cin + row * p.ldc + n0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float o[4];
+              if (n0 + j + 3 < p.N) {
+                if (crow) {
+                  const float4 cv = *reinterpret_cast<const float4*>(crow + j);
+                  o[0] = p.alpha * v[j] + p.beta * cv.x;
+                  o[1] = p.alpha * v[j + 1] + p.beta * cv.y;
+                  o[2] = p.alpha * v[j + 2] + p.beta * cv.z;
+                  o[3] = p.alpha * v[j + 3] + p.beta * cv.w;
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) o[q] = p.alpha * v[j + q];
+                }
+                if (lrow) {
+                  float h[4], l[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    h[q] = ptx::to_tf32(o[q]);
+                    l[q] = ptx::to_tf32(o[q] - h[q]);
+                  }
+                  *reinterpret_cast<float4*>(drow + j) = make_float4(h[0], h[1], h[2], h[3]);
+                  *reinterpret_cast<float4*>(lrow + j) = make_float4(l[0], l[1], l[2], l[3]);
+                } else {
+                  *reinterpret_cast<float4*>(drow + j) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+              } else {
+                for (int q = 0; q < 4; ++q) {
+                  if (n0 + j + q < p.N) {
+                    float x = p.alpha * v[j + q];
+                    if (crow) x += p.beta * crow[j + q];
+                    if (lrow) {
+                      const float h = ptx::to_tf32(x);
+                      drow[j + q] = h;
+                      lrow[j + q] = ptx::to_tf32(x - h);
+                    } else {
+                      drow[j + q] = x;
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else {
+        // Fused per-voxel reduction: rows = voxels, columns = time points of one alpha group.
+        float dot = 0.f, ssq = 0.f;
+        const long t_base = (long)(nt % p.tiles_per_group) * BN;
+        const float* ycol = p.Yz + (row_ok ? row : 0);
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          float y[32];
+          if (row_ok) {
+            const float* yp = ycol + (t_base + c * 32) * p.ldy;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = __ldg(yp + (long)j * p.ldy);
+          }
+          ptx::tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              dot = fmaf(v[j], y[j], dot);
+              ssq = fmaf(v[j], v[j], ssq);
+            }
+          }
+        }
+        if (row_ok) {
+          p.dot_part[(long)nt * p.ld_part + row] = dot;
+          p.ssq_part[(long)nt * p.ld_part + row] = ssq;
+        }
+      }
+      // Release this accumulator buffer back to the MMA issuer (leader CTA).
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1)
+          ptx::mbar_arrive(&tmem_empty_bar[as]);
+        else
+          ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+    }
+  }
+
+  // ======================= teardown =======================
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<CG>(tmem_base, S::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &ptr, 12000, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+// Tensor map of a row-major [rows][k] fp32 matrix (row pitch ld floats); box = box_rows x 32 floats.
+static int make_operand_map(CUtensorMap* tm, const float* base, long rows, long k, long ld, int box_rows) {
+  auto enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return LIT_ERR_CUDA;
+  }
+  LIT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base must be 16-byte aligned");
+  LIT_REQUIRE(ld % 4 == 0 && ld >= k, "GEMM operand pitch must be a multiple of 4 floats and >= K (ld=%ld K=%ld)", ld,
+              k);
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%ld k=%ld ld=%ld box_rows=%d)", (int)r, rows, k, ld,
+              box_rows);
+    return LIT_ERR_CUDA;
+  }
+  return LIT_OK;
+}
+
+template <int BN, int CG, int EPI>
+static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,
+                       GemmParams p, cudaStream_t stream) {
+  using S = GemmShape<BN, CG>;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  int rc;
+  if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM))) return rc;
+  if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM))) return rc;
+  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS))) return rc;
+  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS))) return rc;
+
+  p.num_m_tiles = (p.M + S::BM * CG - 1) / (S::BM * CG);
+  p.num_n_tiles = (p.N + BN - 1) / BN;
+  p.num_k_blocks = (p.K + S::BK - 1) / S::BK;
+  if (p.num_k_blocks < 1) p.num_k_blocks = 1;  // K == 0 still zero-initialises the accumulator via OOB fill
+  if (p.group_m <= 0) p.group_m = 16 / CG;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (tiles == 0) return LIT_OK;
+
+  auto kfn = gemm_tf32x3_kernel<BN, CG, EPI>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    LIT_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
+    attr_set = true;
+  }
+  int workers = sm_count() / CG;
+  if (workers > tiles) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(workers * CG);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = S::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LIT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kfn, tmAh, tmAl, tmBh, tmBl, p));
+  return LIT_OK;
+}
+
+}  // namespace lit
+
+using namespace lit;
+
+extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
+                                  const float* B_lo, long ldb, int M, int N, int K, float alpha, const float* Cin,
+                                  long ldc, float beta, float* D, float* D_lo, long ldd, int variant, void* stream) {
+  LIT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative GEMM extent");
+  LIT_REQUIRE(ldd % 4 == 0 && ldd >= N, "output pitch must be a multiple of 4 floats and >= N");
+  LIT_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "output must be 16-byte aligned");
+  LIT_REQUIRE(!Cin || (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0), "Cin alignment");
+  LIT_REQUIRE(!D_lo || (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0, "D_lo alignment");
+  if (M == 0 || N == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.D = D;
+  p.D_lo = D_lo;
+  p.ldd = ldd;
+  p.Cin = Cin;
+  p.ldc = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (variant) {
+    case LIT_GEMM_AUTO:
+    case LIT_GEMM_1CTA_N256:
+      return launch_gemm<256, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    case LIT_GEMM_1CTA_N128:
+      return launch_gemm<128, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    case LIT_GEMM_2CTA_N256:
+      return launch_gemm<256, 2, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    default:
+      set_error("unknown GEMM variant %d", variant);
+      return LIT_ERR_INVALID;
+  }
+}
+
+extern "C" int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
+                                       const float* B_lo, long ldb, int M, int n_groups, int rows_per_group, int K,
+                                       const float* Yz, long ldy, float* dot_part, float* ssq_part, long ld_part,
+                                       int variant, void* stream) {
+  LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0, "negative extent");
+  LIT_REQUIRE(rows_per_group % 256 == 0, "rows_per_group must be padded to a multiple of 256 (got %d)",
+              rows_per_group);
+  LIT_REQUIRE(ld_part >= M && ldy >= M, "partial / response pitch smaller than M");
+  if (M == 0 || n_groups == 0 || rows_per_group == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = n_groups * rows_per_group;
+  p.K = K;
+  p.Yz = Yz;
+  p.ldy = ldy;
+  p.tiles_per_group = rows_per_group / 256;
+  p.dot_part = dot_part;
+  p.ssq_part = ssq_part;
+  p.ld_part = ld_part;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (variant) {
+    case LIT_GEMM_AUTO:
+    case LIT_GEMM_1CTA_N256:
+      return launch_gemm<256, 1, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    case LIT_GEMM_2CTA_N256:
+      return launch_gemm<256, 2, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    default:
+      set_error("unknown corr-GEMM variant %d", variant);
+      return LIT_ERR_INVALID;
+  }
+}

@@ -1,0 +1,388 @@
+// Ridge-specific streaming kernels: column statistics and z-scoring of the responses,
+// construction of the alpha-stacked validation design in the eigenbasis, per-voxel
+// shrinkage, inner-CV score finalisation and the per-voxel argmax over alphas.
+// All are HBM-bound: threads map to the contiguous (voxel / feature) axis so every warp
+// access is a full 128-byte line; reductions over rows are per-thread serial (no atomics).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "../../include/litridge.h"
+
+#include <cfloat>
+
+namespace lit {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int blocks_for(long items, int block) { return (int)((items + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------
+// Column mean / std over a gathered row set.  One thread per column, row loop split over
+// blockIdx.y into ROW_SPLIT slices that are combined with fp64 atomics on (sum, sumsq) of
+// values shifted by the first row (avoids cancellation when |mean| >> std).
+// ---------------------------------------------------------------------------------------------
+__global__ void col_moments_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx,
+                                   long n_idx, long cols, double* __restrict__ acc /* [2][cols] */) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long r_begin = (long)blockIdx.y * ((n_idx + gridDim.y - 1) / gridDim.y);
+  long r_end = r_begin + (n_idx + gridDim.y - 1) / gridDim.y;
+  if (r_end > n_idx) r_end = n_idx;
+  const long r_first = idx ? (long)idx[0] : 0;
+  const float shift = src[r_first * ld_src + c];
+  double s = 0.0, q = 0.0;
+  long r = r_begin;
+  for (; r + 4 <= r_end; r += 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long sr = idx ? (long)idx[r + u] : r + u;
+      v[u] = src[sr * ld_src + c];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double d = (double)v[u] - (double)shift;
+      s += d;
+      q += d * d;
+    }
+  }
+  for (; r < r_end; ++r) {
+    const long sr = idx ? (long)idx[r] : r;
+    const double d = (double)src[sr * ld_src + c] - (double)shift;
+    s += d;
+    q += d * d;
+  }
+  if (gridDim.y == 1) {
+    acc[c] = s;
+    acc[cols + c] = q;
+  } else {
+    atomicAdd(&acc[c], s);
+    atomicAdd(&acc[cols + c], q);
+  }
+}
+
+__global__ void col_stats_finish_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx,
+                                        long n_idx, long cols, int ddof, const double* __restrict__ acc,
+                                        float* __restrict__ mean, float* __restrict__ stdv) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long r_first = idx ? (long)idx[0] : 0;
+  const double shift = (double)src[r_first * ld_src + c];
+  const double s = acc[c], q = acc[cols + c];
+  const double n = (double)n_idx;
+  const double m = s / n;
+  double var = (q - s * m) / (n - (double)ddof);
+  if (var < 0.0) var = 0.0;
+  if (mean) mean[c] = (float)(shift + m);
+  if (stdv) stdv[c] = (float)sqrt(var);
+}
+
+// dst[i][c] = (src[idx[i]][c] - mean[c]) * scale(c)
+template <bool VEC, bool SPLIT>
+__global__ void gather_normalize_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx,
+                                        long n_idx, long cols, const float* __restrict__ mean,
+                                        const float* __restrict__ stdv, int mode, float eps, float* __restrict__ dst,
+                                        float* __restrict__ dst_lo, long ld_dst, long n_rows_out) {
+  constexpr int CPT = VEC ? 4 : 1;
+  const long cols_t = (cols + CPT - 1) / CPT;
+  const long total = n_rows_out * cols_t;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const float rs = n_idx > 1 ? rsqrtf((float)(n_idx - 1)) : 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long r = i / cols_t;
+    const long c = (i - r * cols_t) * CPT;
+    float x[CPT];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) x[u] = 0.f;
+    if (r < n_idx) {
+      const long sr = idx ? (long)idx[r] : r;
+      if (VEC) {
+        const float4 v = *reinterpret_cast<const float4*>(src + sr * ld_src + c);
+        x[0] = v.x;
+        if (CPT > 1) {
+          x[1 % CPT] = v.y;
+          x[2 % CPT] = v.z;
+          x[3 % CPT] = v.w;
+        }
+      } else {
+        x[0] = src[sr * ld_src + c];
+      }
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        const float m = mean[c + u];
+        float sc = 1.f;
+        if (mode == 0) {
+          sc = 1.f / (stdv[c + u] + eps);
+        } else if (mode == 1) {
+          const float sd = stdv[c + u];
+          sc = sd > 0.f ? rs / sd : 0.f;
+        }
+        x[u] = (x[u] - m) * sc;
+      }
+    }
+    float h[CPT], l[CPT];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+      if (SPLIT) {
+        h[u] = ptx::to_tf32(x[u]);
+        l[u] = ptx::to_tf32(x[u] - h[u]);
+      } else {
+        h[u] = x[u];
+        l[u] = 0.f;
+      }
+    }
+    if (VEC) {
+      *reinterpret_cast<float4*>(dst + r * ld_dst + c) = make_float4(h[0], h[1 % CPT], h[2 % CPT], h[3 % CPT]);
+      if (SPLIT)
+        *reinterpret_cast<float4*>(dst_lo + r * ld_dst + c) = make_float4(l[0], l[1 % CPT], l[2 % CPT], l[3 % CPT]);
+    } else {
+      dst[r * ld_dst + c] = h[0];
+      if (SPLIT) dst_lo[r * ld_dst + c] = l[0];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Alpha stack: out[a*rows_pad + t][j] = (L[t][j] - mean_j) * keep_j / (lam_j + (alpha_a*s)^2)
+// grid: x over column tiles (128 columns), y over (alpha, row-chunk).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float norm_scale(const float* lam, int k, int normalpha) {
+  // lam ascending (cuSOLVER syevd) -> largest eigenvalue is the last one.
+  return normalpha ? sqrtf(fmaxf(lam[k - 1], 0.f)) : 1.f;
+}
+
+__global__ void alpha_stack_kernel(const float* __restrict__ L, long ld_l, long n_rows, long rows_pad, int k,
+                                   const float* __restrict__ lam, const float* __restrict__ alphas, int normalpha,
+                                   float singcutoff, const float* __restrict__ col_mean, float* __restrict__ out_hi,
+                                   float* __restrict__ out_lo, long ld_out, int row_chunk) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_chunks = (int)((rows_pad + row_chunk - 1) / row_chunk);
+  const int a = blockIdx.y / n_chunks;
+  const int ch = blockIdx.y - a * n_chunks;
+  if (j >= k) return;
+  const float s = norm_scale(lam, k, normalpha);
+  const double an = (double)alphas[a] * (double)s;
+  const float a2 = (float)(an * an);
+  const float lj = lam[j];
+  const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
+  const float d = keep ? 1.f / (lj + a2) : 0.f;
+  const float m = col_mean[j];
+  const long t0 = (long)ch * row_chunk;
+  long t1 = t0 + row_chunk;
+  if (t1 > rows_pad) t1 = rows_pad;
+  for (long t = t0; t < t1; ++t) {
+    float v = 0.f;
+    if (t < n_rows) v = (L[t * ld_l + j] - m) * d;
+    const float h = ptx::to_tf32(v);
+    const long o = ((long)a * rows_pad + t) * ld_out + j;
+    out_hi[o] = h;
+    out_lo[o] = ptx::to_tf32(v - h);
+  }
+}
+
+// out[v][j] = (Zhi+Zlo)[v][j] * keep_j / (lam_j + (alpha_v*s)^2)
+__global__ void scale_rows_kernel(const float* __restrict__ Z_hi, const float* __restrict__ Z_lo, long ld_z,
+                                  long n_vox, int k, const float* __restrict__ lam, const float* __restrict__ alpha_v,
+                                  int normalpha, float singcutoff, float* __restrict__ out_hi,
+                                  float* __restrict__ out_lo, long ld_out) {
+  const float s = norm_scale(lam, k, normalpha);
+  const long total = n_vox * (long)k;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long v = i / k;
+    const int j = (int)(i - v * k);
+    const float an = alpha_v[v] * s;  // fp32 product, as nalphas = alphas * norm in ridge_torch
+    const float a2 = an * an;
+    const float lj = lam[j];
+    const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
+    float z = Z_hi[v * ld_z + j];
+    if (Z_lo) z += Z_lo[v * ld_z + j];
+    const float o = keep ? z / (lj + a2) : 0.f;
+    const float h = ptx::to_tf32(o);
+    out_hi[v * ld_out + j] = h;
+    out_lo[v * ld_out + j] = ptx::to_tf32(o - h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nan_to_num(float x) {
+  if (isnan(x)) return 0.f;
+  if (isinf(x)) return x > 0.f ? FLT_MAX : -FLT_MAX;
+  return x;
+}
+
+__global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const float* __restrict__ ssq_part,
+                                     long ld_part, int tiles_per_group, int n_groups, long n_vox, long n_rows, float eps,
+                                     int accumulate, float* __restrict__ corr, long ld_corr) {
+  const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vox) return;
+  const float inv_n = 1.f / (float)n_rows;
+  const float inv_nm1 = 1.f / (float)(n_rows - 1);
+  for (int g = 0; g < n_groups; ++g) {
+    float d = 0.f, q = 0.f;
+    for (int t = 0; t < tiles_per_group; ++t) {
+      const long o = (long)(g * tiles_per_group + t) * ld_part + v;
+      d += dot_part[o];
+      q += ssq_part[o];
+    }
+    const float sd = sqrtf(q * inv_nm1);
+    float c = (d * inv_n) / (sd + eps);
+    c = nan_to_num(c);
+    float* dst = corr + (long)g * ld_corr + v;
+    *dst = accumulate ? *dst + c : c;
+  }
+}
+
+__global__ void argmax_alpha_kernel(const float* __restrict__ corr_sum, long ld_corr, int n_alphas, long n_vox,
+                                    int n_folds, const float* __restrict__ alphas, int32_t* __restrict__ best,
+                                    float* __restrict__ alpha_out, double* __restrict__ col_sums) {
+  extern __shared__ double sh[];  // [n_alphas] block partial sums
+  for (int a = threadIdx.x; a < n_alphas; a += blockDim.x) sh[a] = 0.0;
+  __syncthreads();
+  const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float nf = (float)n_folds;
+  int bi = 0;
+  float bv = -INFINITY;
+  for (int a = 0; a < n_alphas; ++a) {
+    float m = 0.f;
+    if (v < n_vox) {
+      m = corr_sum[(long)a * ld_corr + v] / nf;
+      if (m > bv) {  // strict: first maximum wins (torch.argmax)
+        bv = m;
+        bi = a;
+      }
+    }
+    if (col_sums) {
+      double x = (double)m;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sh[a], x);
+    }
+  }
+  if (v < n_vox) {
+    if (best) best[v] = bi;
+    if (alpha_out) alpha_out[v] = alphas[bi];
+  }
+  if (col_sums) {
+    __syncthreads();
+    for (int a = threadIdx.x; a < n_alphas; a += blockDim.x) atomicAdd(&col_sums[a], sh[a]);
+  }
+}
+
+}  // namespace lit
+
+using namespace lit;
+
+extern "C" int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, int ddof,
+                             float* mean, float* stdv, double* scratch, void* stream) {
+  LIT_REQUIRE(n_idx > 0 && cols >= 0, "col_stats: need at least one row");
+  LIT_REQUIRE(scratch != nullptr, "col_stats: scratch (2*cols doubles) required");
+  if (cols == 0) return LIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int block = 128;
+  const int gx = blocks_for(cols, block);
+  // enough row slices to fill the machine when there are few columns
+  int gy = 1;
+  const int target = sm_count() * 8;
+  if (gx < target) {
+    gy = (target + gx - 1) / gx;
+    const long max_gy = (n_idx + 63) / 64;
+    if (gy > max_gy) gy = (int)max_gy;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+  }
+  if (gy > 1) LIT_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * cols, s));
+  col_moments_kernel<<<dim3(gx, gy), block, 0, s>>>(src, ld_src, idx, n_idx, cols, scratch);
+  LIT_LAUNCH_CHECK();
+  col_stats_finish_kernel<<<gx, block, 0, s>>>(src, ld_src, idx, n_idx, cols, ddof, scratch, mean, stdv);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                                         const float* mean, const float* stdv, int mode, float eps, float* dst,
+                                         float* dst_lo, long ld_dst, long n_rows_out, void* stream) {
+  LIT_REQUIRE(ld_src >= cols && ld_dst >= cols && n_rows_out >= n_idx, "gather_normalize: bad extents");
+  LIT_REQUIRE(mode >= 0 && mode <= 2, "gather_normalize: mode must be 0, 1 or 2");
+  LIT_REQUIRE(mode == 2 || stdv != nullptr, "gather_normalize: std required");
+  if (n_rows_out == 0 || cols == 0) return LIT_OK;
+  const bool vec = cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && aligned16(src) && aligned16(dst) &&
+                   (!dst_lo || aligned16(dst_lo));
+  const long items = n_rows_out * (vec ? cols / 4 : cols);
+  long grid = (items + 255) / 256;
+  const long cap = (long)sm_count() * 64;
+  if (grid > cap) grid = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+#define LIT_GN(V, S)                                                                                              \
+  gather_normalize_kernel<V, S><<<(int)grid, 256, 0, s>>>(src, ld_src, idx, n_idx, cols, mean, stdv, mode, eps, dst, \
+                                                          dst_lo, ld_dst, n_rows_out)
+  if (vec) {
+    if (dst_lo)
+      LIT_GN(true, true);
+    else
+      LIT_GN(true, false);
+  } else {
+    if (dst_lo)
+      LIT_GN(false, true);
+    else
+      LIT_GN(false, false);
+  }
+#undef LIT_GN
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, long rows_pad, int k, const float* lam,
+                                     const float* alphas, int n_alphas, int normalpha, float singcutoff,
+                                     float* col_mean, double* scratch, float* out_hi, float* out_lo, long ld_out,
+                                     void* stream) {
+  LIT_REQUIRE(n_rows > 0 && rows_pad >= n_rows && k > 0 && n_alphas > 0, "alpha_stack: bad extents");
+  LIT_REQUIRE(ld_l >= k && ld_out >= k, "alpha_stack: pitch smaller than k");
+  int rc = lit_col_stats(L, ld_l, nullptr, n_rows, k, 0, col_mean, nullptr, scratch, stream);
+  if (rc) return rc;
+  const int block = 128;
+  const int row_chunk = 128;
+  const int n_chunks = (int)((rows_pad + row_chunk - 1) / row_chunk);
+  LIT_REQUIRE((long)n_alphas * n_chunks <= 65535, "alpha_stack: too many (alpha, row-chunk) pairs");
+  dim3 grid(blocks_for(k, block), n_alphas * n_chunks);
+  alpha_stack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(L, ld_l, n_rows, rows_pad, k, lam, alphas, normalpha,
+                                                               singcutoff, col_mean, out_hi, out_lo, ld_out, row_chunk);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, long n_vox, int k,
+                                       const float* lam, const float* alpha_v, int normalpha, float singcutoff,
+                                       float* out_hi, float* out_lo, long ld_out, void* stream) {
+  LIT_REQUIRE(ld_z >= k && ld_out >= k && k > 0, "scale_rows: bad extents");
+  if (n_vox == 0) return LIT_OK;
+  const long items = n_vox * (long)k;
+  long grid = (items + 255) / 256;
+  const long cap = (long)sm_count() * 64;
+  if (grid > cap) grid = cap;
+  scale_rows_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(Z_hi, Z_lo, ld_z, n_vox, k, lam, alpha_v, normalpha,
+                                                                 singcutoff, out_hi, out_lo, ld_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
+                                 int n_groups, long n_vox, long n_rows, float eps, int accumulate, float* corr,
+                                 long ld_corr, void* stream) {
+  LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
+  if (n_vox == 0 || n_groups == 0) return LIT_OK;
+  corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
+      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, corr, ld_corr);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_vox, int n_folds,
+                                const float* alphas, int32_t* best, float* alpha_out, double* col_sums, void* stream) {
+  LIT_REQUIRE(n_alphas > 0 && n_folds > 0 && ld_corr >= n_vox, "argmax_alpha: bad extents");
+  if (n_vox == 0) return LIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (col_sums) LIT_CUDA_CHECK(cudaMemsetAsync(col_sums, 0, sizeof(double) * n_alphas, s));
+  argmax_alpha_kernel<<<blocks_for(n_vox, 256), 256, sizeof(double) * n_alphas, s>>>(
+      corr_sum, ld_corr, n_alphas, n_vox, n_folds, alphas, best, alpha_out, col_sums);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
