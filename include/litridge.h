@@ -101,7 +101,7 @@ int lit_fill_f32(float* dst, size_t n, float value, void* stream);
 /* Per-column mean and std over the gathered rows idx (NULL = all n rows).  ddof = 1 matches
  * torch.std (unbiased), ddof = 0 NumPy.  Accumulation is in fp64; outputs fp32. */
 int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, int ddof, float* mean,
-                  float* std, void* stream);
+                  float* std, double* scratch /* 2*cols doubles */, void* stream);
 /* dst[i][c] = (src[idx[i]][c] - mean[c]) * scale(c), zero rows up to n_rows_out, where
  *   mode 0: scale = 1 / (std[c] + eps)                  (z_score, eps = 1e-8)
  *   mode 1: scale = 1 / (std[c] * sqrt(n_idx - 1))      (unit-norm centred column; 0 if std == 0)
@@ -115,12 +115,13 @@ int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx,
  * Eigen-decomposition of the p x p Gram (the only library call: cuSOLVER syevd)
  * replaces torch.linalg.svd in svd_wrapper (ridge_utils.py:49-67).
  * ---------------------------------------------------------------------------------------- */
-/* Workspace size in bytes (device and host) for lit_syevd at order n. */
-int lit_syevd_workspace(int n, size_t* device_bytes, size_t* host_bytes);
-/* In place: on exit row j of G (pitch ld == n required) is the j-th eigenvector, lam ascending.
- * info is a device int (0 on success). work/work_h from lit_syevd_workspace. */
-int lit_syevd(float* G, int n, float* lam, void* work, size_t work_bytes, void* work_h, size_t work_h_bytes,
-              int* info, void* stream);
+/* Workspace size in bytes (device and host) for lit_syevd at order n.
+ * dtype: 0 = f32, 1 = f64.  batch > 1 selects the batched solver (matrices n*n apart). */
+int lit_syevd_workspace(int n, int dtype, int batch, size_t* device_bytes, size_t* host_bytes);
+/* In place: on exit row j of G (pitch == n) is the j-th eigenvector, lam ascending.
+ * info is a device int per matrix (0 on success). work / work_h (host) from lit_syevd_workspace. */
+int lit_syevd(void* G, int n, int dtype, int batch, void* lam, void* work, size_t work_bytes, void* work_h,
+              size_t work_h_bytes, int* info, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Ridge-specific elementwise kernels
@@ -131,7 +132,8 @@ int lit_syevd(float* G, int n, float* lam, void* work, size_t work_bytes, void* 
  * rows t >= n_rows are zero.  Output is a split pair of shape [n_alphas*rows_pad][k].
  * (ridge_regression.py:97-101,117-120 with D = S/(S^2+a^2) folded into the Gram form.) */
 int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, long rows_pad, int k, const float* lam,
-                          const float* alphas, int n_alphas, int normalpha, float singcutoff, float* out_hi,
+                          const float* alphas, int n_alphas, int normalpha, float singcutoff,
+                          float* col_mean /* k floats, scratch */, double* scratch /* 2*k doubles */, float* out_hi,
                           float* out_lo, long ld_out, void* stream);
 /* Per-voxel shrinkage in the eigenbasis: out[v][j] = (Z_hi+Z_lo)[v][j] * keep_j / (lam_j + (alpha_v * s)^2)
  * written as a split pair (ridge_regression.py:56-61 for every voxel at once). */

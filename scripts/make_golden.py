@@ -1,0 +1,279 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python scripts/make_golden.py
+
+The reference package pulls in optional dependencies that are absent from this image
+(transformer_lens, gensim, h5py, statsmodels); they are stubbed in sys.modules before import.
+statsmodels' `fdrcorrection` is the only stubbed function that is actually executed; it is
+replaced by the restatement documented in SURVEY.md section 8c (parity for BH is therefore pinned by
+the known-answer tests in tests/test_oracle_golden.py instead).
+"""
+import contextlib
+import io
+import logging
+import os
+import random
+import sys
+import types
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+
+
+def _fdrcorrection(pvals, alpha=0.05, method="indep", is_sorted=False):
+    p = np.asarray(pvals)
+    m = len(p)
+    o = np.argsort(p)
+    ps = p[o]
+    c = np.arange(1, m + 1) / float(m)
+    rej = ps <= c * alpha
+    if rej.any():
+        rej[: np.max(np.nonzero(rej)[0])] = True
+    adj = np.minimum.accumulate((ps / c)[::-1])[::-1]
+    adj[adj > 1] = 1
+    r = np.empty_like(rej)
+    a = np.empty_like(adj)
+    r[o] = rej
+    a[o] = adj
+    return r, a
+
+
+def import_reference():
+    _stub("transformer_lens", HookedTransformer=object)
+    _stub("gensim")
+    _stub("gensim.models", KeyedVectors=object)
+    _stub("h5py")
+    _stub("statsmodels")
+    _stub("statsmodels.stats")
+    _stub("statsmodels.stats.multitest", fdrcorrection=_fdrcorrection)
+    sys.path.insert(0, REF)
+    from encoding.models.nested_cv import NestedCVModel
+    from encoding.models.ridge_regression import ridge_corr_torch, ridge_torch
+    from encoding.models.folding import create_folds
+    from encoding.features.FIR_expander import FIR
+    from encoding.downsample.downsampling import Downsampler
+    return NestedCVModel, ridge_corr_torch, ridge_torch, create_folds, FIR, Downsampler
+
+
+@contextlib.contextmanager
+def quiet():
+    logging.disable(logging.CRITICAL)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with contextlib.redirect_stdout(io.StringIO()):
+            yield
+    logging.disable(logging.NOTSET)
+
+
+def pack_folds(folds):
+    """list of (train, test) -> flat int32 array + offsets."""
+    flat, offs = [], [0]
+    for tr, te in folds:
+        for part in (tr, te):
+            flat.extend(int(i) for i in part)
+            offs.append(len(flat))
+    return np.asarray(flat, dtype=np.int32), np.asarray(offs, dtype=np.int64)
+
+
+def synth_ridge(rng, N, p, V, signal_frac=0.4, noise=2.0, const_vox=1, dup_vox=1, smooth=True):
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    if smooth:  # temporally smooth, correlated features as after Lanczos + FIR
+        for t in range(1, N):
+            X[t] = 0.6 * X[t - 1] + 0.8 * X[t]
+    W = rng.standard_normal((p, V)).astype(np.float32) / np.sqrt(p)
+    W[:, rng.random(V) > signal_frac] = 0
+    Y = X @ W + noise * rng.standard_normal((N, V)).astype(np.float32)
+    for i in range(const_vox):
+        Y[:, V - 1 - i] = 3.25
+    for i in range(dup_vox):
+        Y[:, V - 1 - const_vox - i] = Y[:, i]
+    return X, Y.astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    NestedCVModel, ridge_corr_torch, ridge_torch, create_folds, FIR, Downsampler = import_reference()
+    import torch
+
+    torch.set_num_threads(4)
+
+    # ------------------------------------------------------------------ FIR
+    fir = {}
+    base = np.arange(12, dtype=np.float32).reshape(6, 2)
+    cases = {
+        "a_d12": (base, [1, 2], False), "a_dm102": (base, [-1, 0, 2], False), "a_d1m2": (base, [1, -2], False),
+        "a_d0": (base, [0], False), "a_d01": (base, [0, 1], False), "a_circ2": (base, [2], True),
+        "a_circm2_1": (base, [-2, 1], True), "a_d7": (base, [7], False), "a_d6": (base, [6], False),
+        "a_d7circ": (base, [7], True), "a_dm9circ": (base, [-9], True), "a_d6circ": (base, [6], True),
+    }
+    rng = np.random.default_rng(11)
+    r32 = rng.standard_normal((50, 7)).astype(np.float32)
+    r64 = rng.standard_normal((33, 5))
+    cases["r32_d1234"] = (r32, [1, 2, 3, 4], False)
+    cases["r64_dm3_0_5_circ"] = (r64, [-3, 0, 5], True)
+    cases["r64_d1234"] = (r64, [1, 2, 3, 4], False)
+    for name, (stim, delays, circ) in cases.items():
+        fir[f"{name}__stim"] = stim
+        fir[f"{name}__delays"] = np.asarray(delays, dtype=np.int32)
+        fir[f"{name}__circpad"] = np.asarray(circ)
+        fir[f"{name}__out"] = FIR.make_delayed(stim, delays, circpad=circ)
+    np.savez_compressed(os.path.join(OUT, "fir.npz"), **fir)
+
+    # ------------------------------------------------------------------ Lanczos
+    lz = {}
+    ds = Downsampler()
+    rng = np.random.default_rng(5)
+    tr_times = np.arange(40) * 2.0 + 1.0
+    t_uniform = np.arange(0, 80, 0.5)  # hits t == 0 exactly at every TR
+    t_jitter = np.sort(np.cumsum(rng.exponential(0.33, size=260)))
+    t_unsorted = t_jitter.copy()
+    rng.shuffle(t_unsorted)
+    lcases = {
+        "uniform_w3": (rng.standard_normal((len(t_uniform), 6)).astype(np.float32), t_uniform, tr_times, 3, 1.0, False),
+        "jitter_w3": (rng.standard_normal((260, 9)).astype(np.float32), t_jitter, tr_times, 3, 1.0, False),
+        "jitter_w2_c05": (rng.standard_normal((260, 4)), t_jitter, tr_times, 2, 0.5, False),
+        "jitter_rect": (rng.standard_normal((260, 5)).astype(np.float32), t_jitter, tr_times, 3, 1.0, True),
+        "unsorted_w3": (rng.standard_normal((260, 3)).astype(np.float32), t_unsorted, tr_times, 3, 1.0, False),
+        "edge_w1": (rng.standard_normal((len(t_uniform), 2)), t_uniform, tr_times[:7], 1, 1.0, False),
+    }
+    with quiet():
+        for name, (data, dt, tt, w, cm, rect) in lcases.items():
+            lz[f"{name}__data"] = data
+            lz[f"{name}__data_times"] = dt
+            lz[f"{name}__tr_times"] = tt
+            lz[f"{name}__params"] = np.asarray([w, cm, float(rect)])
+            kw = dict(window=w, cutoff_mult=cm, split_indices=[1, 2, 3])  # split_indices must be dropped silently
+            if rect:
+                kw["rectify"] = True
+            lz[f"{name}__out"] = ds.downsample(data, dt, tt, method="lanczos", **kw)
+    np.savez_compressed(os.path.join(OUT, "lanczos.npz"), **lz)
+
+    # ------------------------------------------------------------------ folds
+    fo = {}
+    fcases = {
+        "chunked_9407": (9407, "chunked", 5, 20, None, None, 0),
+        "chunked_7520": (7520, "chunked", 5, 20, None, None, 1),
+        "chunked_403_c10_k4": (403, "chunked", 4, 10, None, None, 2),
+        "chunked_fallback_50": (50, "chunked", 5, 20, None, None, 3),
+        "chunked_trimmed_500": (500, "chunked_trimmed", 5, 20, None, None, 4),
+        "chunked_trimmed_500_t3": (500, "chunked_trimmed", 5, 20, 3, None, 4),
+        "chunked_trimmed_fallback": (60, "chunked_trimmed", 5, 20, None, None, 4),
+        "chunked_contiguous_407": (407, "chunked_contiguous", 5, 20, None, None, 5),
+        "kfold_103": (103, "kfold", 5, None, None, None, 6),
+        "kfold_trimmed_103": (103, "kfold_trimmed", 5, None, None, None, 6),
+        "kfold_trimmed_small": (38, "kfold_trimmed", 5, None, 4, None, 6),
+        "timeseries_103": (103, "timeseries", 5, None, None, None, 6),
+        "group_90": (90, "group", 4, None, None, np.repeat(np.arange(9), [4, 20, 7, 7, 12, 10, 10, 15, 5]), 7),
+    }
+    with quiet():
+        for name, (n, ftype, k, chunk, trim, groups, seed) in fcases.items():
+            random.seed(seed)
+            np.random.seed(seed)
+            folds = create_folds(n, ftype, k, chunk, trim, groups)
+            flat, offs = pack_folds(folds)
+            fo[f"{name}__flat"] = flat
+            fo[f"{name}__offs"] = offs
+            fo[f"{name}__args"] = np.asarray([n, k, -1 if chunk is None else chunk, -1 if trim is None else trim, seed])
+            fo[f"{name}__type"] = np.asarray(ftype)
+            if groups is not None:
+                fo[f"{name}__groups"] = groups
+    np.savez_compressed(os.path.join(OUT, "folds.npz"), **fo)
+
+    # ------------------------------------------------------------------ ridge kernels
+    rk = {}
+    rng = np.random.default_rng(21)
+    alphas = list(np.logspace(-1, 4, 8))
+    shapes = {"tall": (120, 40, 16, 30), "dupcol": (100, 30, 12, 20), "wide": (30, 20, 50, 10)}
+    with quiet():
+        for name, (n, m, p, V) in shapes.items():
+            X, Y = synth_ridge(rng, n + m, p, V)
+            if name == "dupcol":
+                X[:, 5] = X[:, 2]
+            Rs, Ps, Rr, Pr = X[:n], X[n:], Y[:n], Y[n:]
+            for normalpha in (True, False):
+                for use_corr in (True, False):
+                    tag = f"{name}_n{int(normalpha)}_c{int(use_corr)}"
+                    c = ridge_corr_torch(torch.tensor(Rs), torch.tensor(Ps), torch.tensor(Rr), torch.tensor(Pr),
+                                         alphas, singcutoff=1e-10, use_corr=use_corr, normalpha=normalpha).numpy()
+                    rk[f"{tag}__corr"] = c
+                va = torch.tensor(rng.choice(np.asarray(alphas, dtype=np.float32), size=V))
+                w = ridge_torch(torch.tensor(Rs), torch.tensor(Rr), va, singcutoff=1e-10, normalpha=normalpha).numpy()
+                rk[f"{name}_n{int(normalpha)}__valphas"] = va.numpy()
+                rk[f"{name}_n{int(normalpha)}__wt"] = w
+            rk[f"{name}__X"] = X
+            rk[f"{name}__Y"] = Y
+            rk[f"{name}__n_train"] = np.asarray(n)
+    rk["alphas"] = np.asarray(alphas)
+    np.savez_compressed(os.path.join(OUT, "ridge_kernels.npz"), **rk)
+
+    # ------------------------------------------------------------------ fit_predict end to end
+    fp = {}
+    rng = np.random.default_rng(33)
+    X, Y = synth_ridge(rng, 400 + 120, 24, 64, const_vox=1, dup_vox=2)
+    Xtr, Ytr, Xte, Yte = X[:400], Y[:400], X[400:], Y[400:]
+    fp["X"], fp["Y"] = X, Y
+    fp["alphas"] = np.asarray(alphas)
+    model = NestedCVModel("ridge_regression")
+    runs = {
+        "tt_default": dict(train_test=True),
+        "tt_single": dict(train_test=True, single_alpha=True),
+        "tt_norm": dict(train_test=True, normalize_features=True, normalize_targets=True),
+        "tt_nonormalpha": dict(train_test=True, normalpha=False),
+        "tt_rsq": dict(train_test=True, use_corr=False),
+        "cv_default": dict(train_test=False),
+        "cv_single": dict(train_test=False, single_alpha=True),
+        "cv_kfold": dict(train_test=False, folding_type="kfold"),
+        "cv_norm": dict(train_test=False, normalize_targets=True),
+    }
+    with quiet():
+        for name, kw in runs.items():
+            kw = dict(kw)
+            tt = kw.pop("train_test")
+            random.seed(7)
+            np.random.seed(7)
+            common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas,
+                          use_gpu=False)
+            common.update(kw)
+            if tt:
+                metrics, wt, va = model.fit_predict(Xtr, Ytr, X_test=Xte, y_test=Yte, **common)
+            else:
+                metrics, wt, va = model.fit_predict(X[:400], Y[:400], **common)
+            fp[f"{name}__weights"] = np.asarray(wt)
+            fp[f"{name}__best_alphas"] = np.asarray(va)
+            for key, val in metrics.items():
+                fp[f"{name}__m__{key}"] = np.asarray(val)
+    np.savez_compressed(os.path.join(OUT, "fit_predict.npz"), **fp)
+
+    # ------------------------------------------------------------------ Fisher (SciPy is the third-party pin)
+    from scipy.stats import combine_pvalues
+
+    rng = np.random.default_rng(9)
+    P = rng.random((5, 200)).astype(np.float32) ** 3
+    P[:, 0] = 1.0
+    P[2, 1] = 0.0
+    P[:, 2] = np.float32(1e-30)
+    comb = []
+    with quiet():
+        for i in range(P.shape[1]):
+            pv = [P[f, i] for f in range(5)]
+            comb.append(1.0 if all(x == 1.0 for x in pv) else combine_pvalues(pv, method="fisher")[1])
+    np.savez_compressed(os.path.join(OUT, "fisher.npz"), P=P, combined=np.asarray(comb, dtype=np.float64))
+    print("golden vectors written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print(f"  {f}: {os.path.getsize(os.path.join(OUT, f))} bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+"""Pins the CPU oracle (oracle/ridge_oracle.py) against outputs of the UNMODIFIED reference
+(tests/golden/*.npz, produced by scripts/make_golden.py) and against known-answer vectors."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, unpack_folds
+from oracle import ridge_oracle as O
+
+
+def _cases(npz, suffix):
+    return sorted({k.split("__")[0] for k in npz.files if k.endswith(suffix)})
+
+
+# ------------------------------------------------------------------------------------------ FIR
+def test_fir_matches_reference():
+    g = load_golden("fir.npz")
+    for name in _cases(g, "__out"):
+        out = O.fir_make_delayed(g[f"{name}__stim"], g[f"{name}__delays"].tolist(), bool(g[f"{name}__circpad"]))
+        ref = g[f"{name}__out"]
+        assert out.dtype == ref.dtype, name
+        assert out.shape == ref.shape, name
+        np.testing.assert_array_equal(out, ref, err_msg=name)
+
+
+def test_fir_known_answers():
+    stim = np.arange(12, dtype=np.float32).reshape(6, 2)
+    out = O.fir_make_delayed(stim, [1, -2])
+    assert out.dtype == np.float64 and out.shape == (6, 4)
+    np.testing.assert_array_equal(out[:, :2], np.vstack([np.zeros((1, 2)), stim[:-1]]))
+    np.testing.assert_array_equal(out[:, 2:], np.vstack([stim[2:], np.zeros((2, 2))]))
+    assert O.fir_make_delayed(stim, [0]).dtype == np.float32  # single zero delay keeps the dtype
+    np.testing.assert_array_equal(O.fir_make_delayed(stim, [2], circpad=True), stim[[4, 5, 0, 1, 2, 3]])
+    assert not O.fir_make_delayed(stim, [6]).any()  # shift >= nt -> all zeros
+
+
+# ------------------------------------------------------------------------------------------ Lanczos
+def test_lanczos_matches_reference():
+    g = load_golden("lanczos.npz")
+    for name in _cases(g, "__out"):
+        w, cm, rect = g[f"{name}__params"]
+        out = O.lanczos_interp2d(g[f"{name}__data"], g[f"{name}__data_times"], g[f"{name}__tr_times"],
+                                 window=int(w), cutoff_mult=float(cm), rectify=bool(rect))
+        ref = g[f"{name}__out"]
+        assert out.dtype == np.float64 and out.shape == ref.shape, name
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-13, err_msg=name)
+
+
+def test_lanczos_kernel_known_answers():
+    t = np.array([0.0, 2.0, 6.0, 6.0001, 3.0])
+    v = O.lanczos_kernel(0.5, t, 3)
+    assert v[0] == 1.0  # 0/0 overwritten
+    assert abs(v[1]) < 1e-15  # sinc zero at integer lobes
+    assert v[3] == 0.0  # |t*cutoff| > window
+    assert v[2] != 0.0 and abs(v[2]) < 1e-30  # == window is NOT forced to zero (strict >)
+    assert v[4] < 0 and abs(v[4] + 0.1350949) < 1e-6  # negative side lobe at 1.5 lobes
+
+
+# ------------------------------------------------------------------------------------------ folds
+def test_folds_match_reference():
+    g = load_golden("folds.npz")
+    for name in _cases(g, "__flat"):
+        n, k, chunk, trim, seed = (int(x) for x in g[f"{name}__args"])
+        ftype = str(g[f"{name}__type"])
+        groups = g[f"{name}__groups"] if f"{name}__groups" in g.files else None
+        random.seed(seed)
+        np.random.seed(seed)
+        folds = O.create_folds(n, ftype, k, None if chunk < 0 else chunk, None if trim < 0 else trim, groups)
+        ref = unpack_folds(g[f"{name}__flat"], g[f"{name}__offs"])
+        assert len(folds) == len(ref), name
+        for (tr, te), (rtr, rte) in zip(folds, ref):
+            np.testing.assert_array_equal(np.asarray(tr), rtr, err_msg=name)
+            np.testing.assert_array_equal(np.asarray(te), rte, err_msg=name)
+
+
+def test_chunked_fold_sizes():
+    random.seed(0)
+    folds = O.create_folds(9407, "chunked", 5, 20)
+    assert [(len(a), len(b)) for a, b in folds] == [(7520, 1880)] * 5
+    used = set()
+    for a, b in folds:
+        used |= set(a) | set(b)
+    assert max(used) == 9399  # the 7-row tail belongs to no fold
+    inner = O.create_folds(7520, "chunked", 5, 20)
+    assert [(len(a), len(b)) for a, b in inner] == [(6020, 1500)] * 4 + [(6000, 1520)]
+
+
+# ------------------------------------------------------------------------------------------ ridge kernels
+@pytest.mark.parametrize("name", ["tall", "dupcol", "wide"])
+def test_ridge_kernels_match_reference(name):
+    g = load_golden("ridge_kernels.npz")
+    alphas = g["alphas"].tolist()
+    X, Y, n = g[f"{name}__X"], g[f"{name}__Y"], int(g[f"{name}__n_train"])
+    for normalpha in (True, False):
+        for use_corr in (True, False):
+            ref = g[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corr"]
+            out = O.ridge_corr(X[:n], X[n:], Y[:n], Y[n:], alphas, singcutoff=1e-10, use_corr=use_corr,
+                               normalpha=normalpha)
+            assert out.dtype == np.float32
+            # LAPACK/BLAS rounding differs between torch's and NumPy's builds: compare at fp32 noise level
+            # (rank-deficient designs amplify it when alpha is not normalised)
+            tol = 2e-4 if (name != "tall" and not normalpha) else 2e-5
+            if not use_corr:  # sqrt(|Rsq|) amplifies fp32 noise near Rsq = 0: compare Rsq itself
+                out, ref = np.sign(out) * out ** 2, np.sign(ref) * ref ** 2
+            np.testing.assert_allclose(out, ref, rtol=0, atol=tol, err_msg=f"{name} {normalpha} {use_corr}")
+        w = O.ridge_weights(X[:n], Y[:n], g[f"{name}_n{int(normalpha)}__valphas"], singcutoff=1e-10,
+                            normalpha=normalpha)
+        ref = g[f"{name}_n{int(normalpha)}__wt"]
+        scale = np.abs(ref).max()
+        tol = 5e-3 if (name != "tall" and not normalpha) else 1e-4
+        assert np.abs(w - ref).max() <= tol * scale, (name, normalpha, np.abs(w - ref).max() / scale)
+
+
+# ------------------------------------------------------------------------------------------ statistics
+def test_bh_known_answer():
+    p = np.array([0.001, 0.008, 0.039, 0.041, 0.042, 0.06, 0.074, 0.205, 0.212, 0.216])
+    rej, adj = O.fdr_bh(p, alpha=0.05)
+    # hand computation: thresholds i/10*0.05 = .005,.01,...; largest i with p_(i) <= thr is i=2
+    assert rej.tolist() == [True, True] + [False] * 8
+    expect = np.array([0.01, 0.04, 0.084, 0.084, 0.084, 0.1, 0.10571428571428572, 0.216, 0.216, 0.216])
+    np.testing.assert_allclose(adj, expect, rtol=1e-12)
+    # order independence + cross-check of the adjusted p-values against SciPy's BH
+    from scipy.stats import false_discovery_control
+    rng = np.random.default_rng(0)
+    q = rng.random(5000) ** 2
+    q[:7] = [0.0, 1.0, 1.0, 0.5, 0.5, 1e-300, 0.05]
+    rej, adj = O.fdr_bh(q, alpha=0.05)
+    np.testing.assert_allclose(adj, false_discovery_control(q, method="bh"), rtol=1e-12, atol=0)
+    assert (rej == (adj <= 0.05)).all()
+    assert not O.fdr_bh(np.ones(10))[0].any()
+
+
+def test_fisher_matches_scipy_golden():
+    g = load_golden("fisher.npz")
+    P, ref = g["P"], g["combined"]
+    out = O.fisher_combine([list(P[f]) for f in range(P.shape[0])])
+    np.testing.assert_allclose(out, ref, rtol=1e-6, atol=0)
+    vec = O.fisher_combine_vectorised(P)
+    np.testing.assert_allclose(vec, ref, rtol=2e-5, atol=1e-38)  # reference sums float32 logs
+    assert ref[0] == 1.0 and ref[1] == 0.0
+
+
+def test_pearson_vectorised_matches_scipy_loop():
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((150, 40)).astype(np.float32)
+    b = (0.3 * a + rng.standard_normal((150, 40))).astype(np.float32)
+    b[:, 3] = 1.5  # constant prediction -> NaN -> (0, 1)
+    r0, p0 = O.correlations_pvalues(a, b)
+    r1, p1 = O.correlations_pvalues_vectorised(a, b)
+    np.testing.assert_allclose(np.asarray(r0, dtype=np.float64), r1, atol=2e-6)
+    np.testing.assert_allclose(np.asarray(p0, dtype=np.float64), p1, rtol=2e-4, atol=1e-30)
+    assert r1[3] == 0.0 and p1[3] == 1.0
+
+
+# ------------------------------------------------------------------------------------------ end to end
+RUNS = {
+    "tt_default": dict(train_test=True),
+    "tt_single": dict(train_test=True, single_alpha=True),
+    "tt_norm": dict(train_test=True, normalize_features=True, normalize_targets=True),
+    "tt_nonormalpha": dict(train_test=True, normalpha=False),
+    "tt_rsq": dict(train_test=True, use_corr=False),
+    "cv_default": dict(train_test=False),
+    "cv_single": dict(train_test=False, single_alpha=True),
+    "cv_kfold": dict(train_test=False, folding_type="kfold"),
+    "cv_norm": dict(train_test=False, normalize_targets=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_fit_predict_matches_reference(name):
+    g = load_golden("fit_predict.npz")
+    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    kw = dict(RUNS[name])
+    tt = kw.pop("train_test")
+    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
+    common.update(kw)
+    random.seed(7)
+    np.random.seed(7)
+    if tt:
+        m, w, va = O.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
+    else:
+        m, w, va = O.fit_predict(X[:400], Y[:400], **common)
+    ref_va = g[f"{name}__best_alphas"]
+    ref_r = g[f"{name}__m__correlations"]
+    # alpha selection: identical except where fp32 noise decides between near-tied alphas
+    agree = np.mean(np.isclose(va, ref_va, rtol=1e-6))
+    # (the R^2 metric takes sqrt(|Rsq|) of values that are pure rounding noise for null voxels,
+    #  so many more voxels are near-ties there)
+    assert agree >= (0.7 if name == "tt_rsq" else 0.9), (name, agree)
+    same = np.isclose(va, ref_va, rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(m["correlations"], dtype=np.float64)[same], ref_r[same], atol=2e-5)
+    np.testing.assert_allclose(np.asarray(m["correlations"], dtype=np.float64), ref_r, atol=5e-3)
+    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
+    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
+    wref = g[f"{name}__weights"]
+    assert w.shape == wref.shape and w.dtype == wref.dtype
+    err = np.abs(w[:, same] - wref[:, same]).max() / np.abs(wref).max()
+    assert err < 1e-4, (name, err)
