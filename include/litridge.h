@@ -94,6 +94,11 @@ int lit_gather_rows_transpose_split(const float* src, long ld_src, const int32_t
 int lit_axpy_f32(float a, const float* x_hi, const float* x_lo, long ld_x, float* y, long ld_y, long rows, long cols,
                  void* stream);
 int lit_fill_f32(float* dst, size_t n, float value, void* stream);
+/* Pitched copy between host and device (cudaMemcpy2DAsync): kind 1 = host->device, 2 = device->host,
+ * 3 = device->device.  Used to upload a column block (voxel shard) of a host matrix without a
+ * host-side repack.  The host side of the copy may be pageable or pinned. */
+int lit_memcpy_2d(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes,
+                  size_t height, int kind, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Column statistics / normalisation  (ridge_utils.py:6-15 z_score, :70-180 DataNormalizer)
@@ -104,7 +109,7 @@ int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx,
                   float* std, double* scratch /* 2*cols doubles */, void* stream);
 /* dst[i][c] = (src[idx[i]][c] - mean[c]) * scale(c), zero rows up to n_rows_out, where
  *   mode 0: scale = 1 / (std[c] + eps)                  (z_score, eps = 1e-8)
- *   mode 1: scale = 1 / (std[c] * sqrt(n_idx - 1))      (unit-norm centred column; 0 if std == 0)
+ *   mode 1: scale = 1 / (std[c] * sqrt(n_idx - 1))      (unit-norm centred column; NaN if std == 0)
  *   mode 2: scale = 1                                   (centre only)
  * Optional split output. */
 int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
@@ -118,9 +123,9 @@ int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx,
 /* Workspace size in bytes (device and host) for lit_syevd at order n.
  * dtype: 0 = f32, 1 = f64.  batch > 1 selects the batched solver (matrices n*n apart). */
 int lit_syevd_workspace(int n, int dtype, int batch, size_t* device_bytes, size_t* host_bytes);
-/* In place: on exit row j of G (pitch == n) is the j-th eigenvector, lam ascending.
+/* In place: on exit row j of G (pitch ld >= n) is the j-th eigenvector, lam ascending.
  * info is a device int per matrix (0 on success). work / work_h (host) from lit_syevd_workspace. */
-int lit_syevd(void* G, int n, int dtype, int batch, void* lam, void* work, size_t work_bytes, void* work_h,
+int lit_syevd(void* G, int n, long ld, int dtype, int batch, void* lam, void* work, size_t work_bytes, void* work_h,
               size_t work_h_bytes, int* info, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -132,7 +137,7 @@ int lit_syevd(void* G, int n, int dtype, int batch, void* lam, void* work, size_
  * rows t >= n_rows are zero.  Output is a split pair of shape [n_alphas*rows_pad][k].
  * (ridge_regression.py:97-101,117-120 with D = S/(S^2+a^2) folded into the Gram form.) */
 int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, long rows_pad, int k, const float* lam,
-                          const float* alphas, int n_alphas, int normalpha, float singcutoff,
+                          const double* alphas, int n_alphas, int normalpha, float singcutoff,
                           float* col_mean /* k floats, scratch */, double* scratch /* 2*k doubles */, float* out_hi,
                           float* out_lo, long ld_out, void* stream);
 /* Per-voxel shrinkage in the eigenbasis: out[v][j] = (Z_hi+Z_lo)[v][j] * keep_j / (lam_j + (alpha_v * s)^2)
@@ -141,10 +146,13 @@ int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, lon
                             const float* alpha_v, int normalpha, float singcutoff, float* out_hi, float* out_lo,
                             long ld_out, void* stream);
 /* Inner-CV score from the fused partials (ridge_regression.py:122-133):
- *   corr[a][v] = nan_to_num( (sum_tiles dot / n_rows) / (sqrt(sum_tiles ssq / (n_rows-1)) + eps) )
+ *   metric 0: corr[a][v] = nan_to_num( (sum_tiles dot / n_rows) / (sqrt(sum_tiles ssq / (n_rows-1)) + eps) )
+ *             (Yz z-scored with the unbiased std + eps)
+ *   metric 1: signed sqrt of R^2 = 1 - var(Q - pred)/var(Q) (Yz centred only; resp_std = unbiased std of Q)
  * accumulate != 0 adds into corr (fold sum for nested_cv.py:391-393). */
 int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group, int n_groups,
-                      long n_vox, long n_rows, float eps, int accumulate, float* corr, long ld_corr, void* stream);
+                      long n_vox, long n_rows, float eps, int accumulate, int metric, const float* resp_std,
+                      float* corr, long ld_corr, void* stream);
 /* best[v] = first argmax_a mean[a][v], mean = corr_sum / n_folds (nested_cv.py:391-393,408-411);
  * alpha_out[v] = (float)alphas[best[v]].  col_sums (n_alphas doubles, may be NULL) receives
  * sum_v mean[a][v] for the single_alpha rule (nested_cv.py:396-400). */
@@ -180,9 +188,11 @@ int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, long ndim, lon
 /* Lanczos resampling (interpdata.py:45-63,87-126): out = W * data, W[i][j] = lanczos((tr_i - t_j) * cutoff),
  * cutoff = cutoff_mult / mean(diff(tr_times)) computed by the caller.  rectify -> out is [n_tr][2*ndim]
  * (negative part | positive part).  lo/hi (n_tr + 1 int32, or NULL) bound the contributing samples of
- * each TR when data_times is sorted: TR i only reads samples [lo[i], hi[i]). */
+ * each TR when data_times is sorted: TR i only reads samples [lo[i], hi[i]).  Without them the kernel
+ * is the dense product (every sample is multiplied, zero weights included, so non-finite samples
+ * propagate as in np.dot). */
 int lit_lanczos_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
-                           const double* data_times, const double* tr_times, long n_tr, int window, double cutoff,
+                           const double* data_times, const double* tr_times, long n_tr, double window, double cutoff,
                            int rectify, const int32_t* lo, const int32_t* hi, double* out, long ld_out, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,19 @@
+"""litcoder_core_b200 -- the B200 (sm_100a) hot path of LITcoder's encoding models.
+
+Drop-in replacements for the three reference entry points on that path:
+
+    NestedCVModel / fit_nested_cv     encoding/models/nested_cv.py   (nested-CV ridge regression)
+    Downsampler                       encoding/downsample/downsampling.py   (Lanczos TR resampling)
+    FIR                               encoding/features/FIR_expander.py     (delay stacking)
+    create_folds                      encoding/models/folding.py
+
+All arithmetic runs in hand-written CUDA kernels behind the C ABI of `liblitridge.so`
+(include/litridge.h); importing this package does not need a GPU, calling it does.
+"""
+from .downsample import Downsampler
+from .fir import FIR
+from .folding import create_folds
+from .nested_cv import NestedCVModel, fit_nested_cv
+
+__all__ = ["NestedCVModel", "fit_nested_cv", "Downsampler", "FIR", "create_folds"]
+__version__ = "0.1.0"

@@ -59,3 +59,14 @@ extern "C" int lit_device_info(int* sm_count, int* cc_major, int* cc_minor, size
   }
   return LIT_OK;
 }
+
+extern "C" int lit_memcpy_2d(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes,
+                             size_t height, int kind, void* stream) {
+  LIT_REQUIRE(kind >= 1 && kind <= 3, "memcpy_2d: kind must be 1 (H2D), 2 (D2H) or 3 (D2D)");
+  if (width_bytes == 0 || height == 0) return LIT_OK;
+  const cudaMemcpyKind k =
+      kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  LIT_CUDA_CHECK(cudaMemcpy2DAsync(dst, dpitch_bytes, src, spitch_bytes, width_bytes, height, k,
+                                   static_cast<cudaStream_t>(stream)));
+  return LIT_OK;
+}

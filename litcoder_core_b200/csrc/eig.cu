@@ -61,9 +61,10 @@ extern "C" int lit_syevd_workspace(int n, int dtype, int batch, size_t* device_b
   return LIT_OK;
 }
 
-extern "C" int lit_syevd(void* G, int n, int dtype, int batch, void* lam, void* work, size_t work_bytes, void* work_h,
+extern "C" int lit_syevd(void* G, int n, long ld, int dtype, int batch, void* lam, void* work, size_t work_bytes, void* work_h,
                          size_t work_h_bytes, int* info, void* stream) {
   LIT_REQUIRE(n > 0 && batch > 0 && G && lam && info, "syevd: bad arguments");
+  LIT_REQUIRE(ld >= n && (batch == 1 || ld == n), "syevd: pitch must be >= n (== n for the batched solver)");
   LIT_REQUIRE(dtype == 0 || dtype == 1, "syevd: dtype must be 0 (f32) or 1 (f64)");
   SolverCtx* c;
   int rc = get_solver(&c);
@@ -77,7 +78,7 @@ extern "C" int lit_syevd(void* G, int n, int dtype, int batch, void* lam, void* 
   // The Gram is symmetric, so its row-major storage is also its column-major storage; cuSOLVER
   // returns eigenvector j in (column-major) column j == (row-major) row j, eigenvalues ascending.
   if (batch == 1)
-    st = cusolverDnXsyevd(c->handle, c->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dt, G, n, dt, lam,
+    st = cusolverDnXsyevd(c->handle, c->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dt, G, ld, dt, lam,
                           dt, work, work_bytes, work_h, work_h_bytes, info);
   else
     st = cusolverDnXsyevBatched(c->handle, c->params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, dt, G, n, dt,

@@ -48,20 +48,20 @@ __global__ void fir_kernel(const T* __restrict__ stim, long nt, long ndim, long 
 }
 
 // Lanczos kernel value exactly as interpdata.lanczosfun: t already multiplied by the cutoff.
-__device__ __forceinline__ double lanczos_weight(double t, int window) {
+__device__ __forceinline__ double lanczos_weight(double t, double window) {
   if (t == 0.0) return 1.0;
-  if (fabs(t) > (double)window) return 0.0;
+  if (fabs(t) > window) return 0.0;
   const double pi = 3.141592653589793;
   const double pit = pi * t;
-  return (double)window * sin(pit) * sin(pit / (double)window) / (pi * pi * (t * t));
+  return window * sin(pit) * sin(pit / window) / (pi * pi * (t * t));
 }
 
 // grid.x = TR index, grid.y = column tile.  The block first evaluates the weights of a chunk
 // of samples cooperatively into shared memory, then every thread accumulates its column(s).
 template <typename T, int CHUNK>
 __global__ void lanczos_kernel(const T* __restrict__ data, long n_samples, long ndim, long ld_data,
-                               const double* __restrict__ data_times, const double* __restrict__ tr_times, int window,
-                               double cutoff, int rectify, const int32_t* __restrict__ lo,
+                               const double* __restrict__ data_times, const double* __restrict__ tr_times,
+                               double window, double cutoff, int rectify, const int32_t* __restrict__ lo,
                                const int32_t* __restrict__ hi, double* __restrict__ out, long ld_out) {
   __shared__ double w_sh[CHUNK];
   const long i = blockIdx.x;
@@ -69,6 +69,9 @@ __global__ void lanczos_kernel(const T* __restrict__ data, long n_samples, long 
   const double tr = tr_times[i];
   const long j_begin = lo ? (long)lo[i] : 0;
   const long j_end = hi ? (long)hi[i] : n_samples;
+  // Without a band (lo == NULL) the kernel is the dense product of the reference: zero weights are
+  // multiplied too, so that non-finite samples poison the output exactly as np.dot(sincmat, data) does.
+  const bool dense = lo == nullptr;
   double acc = 0.0, acc_neg = 0.0;
   for (long j0 = j_begin; j0 < j_end; j0 += CHUNK) {
     const long cnt = (j_end - j0) < CHUNK ? (j_end - j0) : CHUNK;
@@ -79,11 +82,12 @@ __global__ void lanczos_kernel(const T* __restrict__ data, long n_samples, long 
     if (c < ndim) {
       for (long q = 0; q < cnt; ++q) {
         const double w = w_sh[q];
-        if (w != 0.0) {
+        if (w != 0.0 || dense) {
           const double x = (double)data[(j0 + q) * ld_data + c];
           if (rectify) {
-            acc_neg = fma(w, fmin(x, 0.0), acc_neg);
-            acc = fma(w, fmax(x, 0.0), acc);
+            // np.clip keeps NaN; CUDA's fmin / fmax would drop it
+            acc_neg = fma(w, x != x ? x : fmin(x, 0.0), acc_neg);
+            acc = fma(w, x != x ? x : fmax(x, 0.0), acc);
           } else {
             acc = fma(w, x, acc);
           }
@@ -129,7 +133,7 @@ extern "C" int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, lon
 }
 
 extern "C" int lit_lanczos_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
-                                      const double* data_times, const double* tr_times, long n_tr, int window,
+                                      const double* data_times, const double* tr_times, long n_tr, double window,
                                       double cutoff, int rectify, const int32_t* lo, const int32_t* hi, double* out,
                                       long ld_out, void* stream) {
   LIT_REQUIRE(n_samples >= 0 && ndim >= 0 && n_tr >= 0, "lanczos: negative extent");

@@ -112,8 +112,10 @@ __global__ void gather_normalize_kernel(const float* __restrict__ src, long ld_s
         if (mode == 0) {
           sc = 1.f / (stdv[c + u] + eps);
         } else if (mode == 1) {
+          // a constant response column has no correlation: NaN here propagates through the fused
+          // reduction and becomes (r, p) = (0, 1) in pearson_finalize, as SciPy's pearsonr -> NaN
           const float sd = stdv[c + u];
-          sc = sd > 0.f ? rs / sd : 0.f;
+          sc = sd > 0.f ? rs / sd : __int_as_float(0x7fc00000);
         }
         x[u] = (x[u] - m) * sc;
       }
@@ -150,7 +152,7 @@ __device__ __forceinline__ float norm_scale(const float* lam, int k, int normalp
 }
 
 __global__ void alpha_stack_kernel(const float* __restrict__ L, long ld_l, long n_rows, long rows_pad, int k,
-                                   const float* __restrict__ lam, const float* __restrict__ alphas, int normalpha,
+                                   const float* __restrict__ lam, const double* __restrict__ alphas, int normalpha,
                                    float singcutoff, const float* __restrict__ col_mean, float* __restrict__ out_hi,
                                    float* __restrict__ out_lo, long ld_out, int row_chunk) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +161,7 @@ __global__ void alpha_stack_kernel(const float* __restrict__ L, long ld_l, long 
   const int ch = blockIdx.y - a * n_chunks;
   if (j >= k) return;
   const float s = norm_scale(lam, k, normalpha);
-  const double an = (double)alphas[a] * (double)s;
+  const double an = alphas[a] * (double)s;  // alpha * S[0] in double, as the Python floats of the reference
   const float a2 = (float)(an * an);
   const float lj = lam[j];
   const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
@@ -209,13 +211,22 @@ __device__ __forceinline__ float nan_to_num(float x) {
   return x;
 }
 
+// metric 0: correlation (Yz z-scored).  metric 1: signed sqrt of R^2 (Yz centred only, resp_std = unbiased
+// std of the validation responses): Rsq = 1 - var(Q - pred)/var(Q) with
+// sum (q_c - p_c)^2 = (n-1) var(Q) - 2 dot + ssq   (ridge_regression.py:126-130).
 __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const float* __restrict__ ssq_part,
                                      long ld_part, int tiles_per_group, int n_groups, long n_vox, long n_rows, float eps,
-                                     int accumulate, float* __restrict__ corr, long ld_corr) {
+                                     int accumulate, int metric, const float* __restrict__ resp_std,
+                                     float* __restrict__ corr, long ld_corr) {
   const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vox) return;
   const float inv_n = 1.f / (float)n_rows;
   const float inv_nm1 = 1.f / (float)(n_rows - 1);
+  float qvar = 0.f;
+  if (metric == 1) {
+    const float sd = resp_std[v];
+    qvar = sd * sd;
+  }
   for (int g = 0; g < n_groups; ++g) {
     float d = 0.f, q = 0.f;
     for (int t = 0; t < tiles_per_group; ++t) {
@@ -223,8 +234,16 @@ __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const f
       d += dot_part[o];
       q += ssq_part[o];
     }
-    const float sd = sqrtf(q * inv_nm1);
-    float c = (d * inv_n) / (sd + eps);
+    float c;
+    if (metric == 0) {
+      const float sd = sqrtf(q * inv_nm1);
+      c = (d * inv_n) / (sd + eps);
+    } else {
+      const float resvar = (qvar * (float)(n_rows - 1) - 2.f * d + q) * inv_nm1;
+      const float rsq = 1.f - resvar / qvar;
+      c = sqrtf(fabsf(rsq)) * (rsq > 0.f ? 1.f : (rsq < 0.f ? -1.f : 0.f));
+      if (isnan(rsq)) c = rsq;
+    }
     c = nan_to_num(c);
     float* dst = corr + (long)g * ld_corr + v;
     *dst = accumulate ? *dst + c : c;
@@ -331,7 +350,7 @@ extern "C" int lit_gather_normalize_rows(const float* src, long ld_src, const in
 }
 
 extern "C" int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, long rows_pad, int k, const float* lam,
-                                     const float* alphas, int n_alphas, int normalpha, float singcutoff,
+                                     const double* alphas, int n_alphas, int normalpha, float singcutoff,
                                      float* col_mean, double* scratch, float* out_hi, float* out_lo, long ld_out,
                                      void* stream) {
   LIT_REQUIRE(n_rows > 0 && rows_pad >= n_rows && k > 0 && n_alphas > 0, "alpha_stack: bad extents");
@@ -365,12 +384,14 @@ extern "C" int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, lon
 }
 
 extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
-                                 int n_groups, long n_vox, long n_rows, float eps, int accumulate, float* corr,
-                                 long ld_corr, void* stream) {
+                                 int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                 const float* resp_std, float* corr, long ld_corr, void* stream) {
   LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
+  LIT_REQUIRE(metric == 0 || (metric == 1 && resp_std), "corr_finalize: metric 1 (R^2) needs the response std");
   if (n_vox == 0 || n_groups == 0) return LIT_OK;
   corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
-      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, corr, ld_corr);
+      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, corr,
+      ld_corr);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

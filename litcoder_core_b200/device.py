@@ -1,0 +1,530 @@
+"""Device layer: thin, typed wrappers around the C ABI (liblitridge.so).
+
+PyTorch is used for plumbing only -- it owns the device allocations (caching allocator), the
+current CUDA stream and the timing events.  Every arithmetic operation on the hot path is one
+of our own sm_100a kernels (or cuSOLVER syevd, the one library call, timed separately).  No torch
+compute op is used here, and there is no CPU fallback: constructing `DeviceOps` without a CUDA
+device or without the built library raises.
+
+The nested-CV engine (engine.py) talks only to this interface, which is what lets the host logic
+be tested on CPU against a NumPy stand-in that lives under tests/ (never shipped).
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+_vp = C.c_void_p
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Mat:
+    """Row-major fp32 device matrix [rows][cols] with pitch `ld`; `lo` is the optional second
+    plane of a 3xTF32 split pair (then `hi` holds rna_tf32(x) and hi + lo == x up to 2^-22)."""
+
+    __slots__ = ("hi", "lo", "rows", "cols", "_ld")
+
+    def __init__(self, hi, lo, rows: int, cols: int, ld: Optional[int] = None):
+        self.hi, self.lo, self.rows, self.cols, self._ld = hi, lo, rows, cols, ld
+
+    @property
+    def ld(self) -> int:
+        return self._ld if self._ld is not None else self.hi.shape[1]
+
+    @property
+    def is_split(self) -> bool:
+        return self.lo is not None
+
+    def __repr__(self):
+        return f"Mat({self.rows}x{self.cols}, ld={self.ld}, split={self.is_split})"
+
+
+class Partials:
+    """Per-tile partial sums written by the fused correlation epilogue."""
+
+    __slots__ = ("dot", "ssq", "n_tiles", "ld")
+
+    def __init__(self, dot, ssq, n_tiles: int, ld: int):
+        self.dot, self.ssq, self.n_tiles, self.ld = dot, ssq, n_tiles, ld
+
+
+class DeviceOps:
+    TILE_N = 256  # accumulator columns per tile of the fused-correlation GEMM
+
+    def __init__(self, device_index: Optional[int] = None, gemm_variant: int = _lib.GEMM_AUTO):
+        import torch
+
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("litcoder_core_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        self.device = torch.device("cuda", device_index)
+        torch.cuda.set_device(self.device)
+        cc = torch.cuda.get_device_capability(self.device)
+        if cc[0] != 10:
+            raise RuntimeError(f"litcoder_core_b200 kernels are built for sm_100a only; device has sm_{cc[0]}{cc[1]}")
+        self.gemm_variant = gemm_variant
+        self.reset_counters()
+        self._eig_ws: Dict[Tuple[int, int], tuple] = {}
+        self._bh_ws = None
+        self._side = None  # side stream for the eigendecompositions
+        self._eig_infos: List[object] = []
+
+    # ------------------------------------------------------------------ bookkeeping
+    def reset_counters(self):
+        self.launches = 0  # kernels of ours launched (cuSOLVER internals not counted)
+        self.gemm_flops = 0.0  # algorithmic 2*M*N*K of the executed GEMMs (x3 tensor-core MMAs each)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._timed: Dict[str, List[tuple]] = {}
+
+    @property
+    def stream(self) -> int:
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    @contextlib.contextmanager
+    def timed(self, name: str):
+        """Bracket a region with CUDA events on the current stream (resolved lazily by timings())."""
+        t = self.torch
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        e0.record()
+        try:
+            yield
+        finally:
+            e1.record()
+            self._timed.setdefault(name, []).append((e0, e1))
+
+    def timings(self) -> Dict[str, float]:
+        """Milliseconds per category (synchronises the device)."""
+        self.torch.cuda.synchronize(self.device)
+        return {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self._timed.items()}
+
+    def synchronize(self):
+        self.torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ memory
+    def _empty2d(self, rows: int, ld: int):
+        return self.torch.empty((max(rows, 1), ld), dtype=self.torch.float32, device=self.device)
+
+    def empty(self, rows: int, cols: int, split: bool = False, ld: Optional[int] = None) -> Mat:
+        ld = round_up(max(cols, 1), 32) if ld is None else ld
+        hi = self._empty2d(rows, ld)
+        lo = self._empty2d(rows, ld) if split else None
+        return Mat(hi, lo, rows, cols)
+
+    def zeros(self, rows: int, cols: int) -> Mat:
+        m = self.empty(rows, cols)
+        check(self.lib.lit_fill_f32(_vp(m.hi.data_ptr()), m.hi.numel(), 0.0, _vp(self.stream)), "fill")
+        self.launches += 1
+        return m
+
+    def vec(self, n: int, dtype: str = "f32"):
+        t = self.torch
+        dt = {"f32": t.float32, "f64": t.float64, "i32": t.int32, "u8": t.uint8}[dtype]
+        return t.empty((max(n, 1),), dtype=dt, device=self.device)
+
+    def upload_vector(self, arr, dtype: str):
+        t = self.torch
+        npdt = {"f32": np.float32, "f64": np.float64, "i32": np.int32}[dtype]
+        a = np.ascontiguousarray(np.asarray(arr, dtype=npdt))
+        out = self.vec(a.size, dtype)
+        if a.size:
+            out[: a.size].copy_(t.from_numpy(a), non_blocking=False)
+            self.h2d_bytes += a.nbytes
+        return out
+
+    def upload_index(self, idx) -> "object":
+        return self.upload_vector(np.asarray(idx, dtype=np.int64), "i32")
+
+    def upload_matrix(self, host: np.ndarray, col_start: int = 0, col_stop: Optional[int] = None,
+                      chunk_bytes: int = 1 << 29) -> Mat:
+        """H2D of host[:, col_start:col_stop] into an fp32 device matrix (fp64 input is converted on
+        the device, mirroring torch.tensor(..., dtype=float32) at nested_cv.py:99-100).  The column
+        block is copied with a pitched memcpy straight from the caller's array -- no host repack."""
+        host = np.asarray(host)
+        if host.ndim != 2:
+            raise ValueError("expected a 2-D array")
+        if host.dtype not in (np.float32, np.float64):
+            host = host.astype(np.float32)
+        if not host.flags.c_contiguous:
+            host = np.ascontiguousarray(host)
+        n, c_all = host.shape
+        col_stop = c_all if col_stop is None else col_stop
+        cols = col_stop - col_start
+        out = self.empty(n, cols)
+        if n == 0 or cols == 0:
+            return out
+        item = host.dtype.itemsize
+        self.h2d_bytes += n * cols * item
+        src0 = host.ctypes.data + col_start * item
+        s = _vp(self.stream)
+        if host.dtype == np.float32:
+            check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr()), out.ld * 4, _vp(src0), c_all * 4, cols * 4, n, 1, s),
+                  "memcpy_2d(H2D)")
+            return out
+        # float64: stage row chunks through a device buffer and convert
+        rows_per = max(1, min(n, chunk_bytes // max(cols * 8, 1)))
+        stage = self.torch.empty((rows_per * cols,), dtype=self.torch.float64, device=self.device)
+        tmp32 = self.torch.empty((rows_per * cols,), dtype=self.torch.float32, device=self.device)
+        for r0 in range(0, n, rows_per):
+            nr = min(rows_per, n - r0)
+            check(self.lib.lit_memcpy_2d(_vp(stage.data_ptr()), cols * 8, _vp(src0 + r0 * c_all * 8), c_all * 8,
+                                         cols * 8, nr, 1, s), "memcpy_2d(H2D)")
+            check(self.lib.lit_convert_f64_to_f32(_vp(stage.data_ptr()), _vp(tmp32.data_ptr()), nr * cols, s), "convert")
+            check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr() + r0 * out.ld * 4), out.ld * 4, _vp(tmp32.data_ptr()),
+                                         cols * 4, cols * 4, nr, 3, s), "memcpy_2d(D2D)")
+            self.launches += 1
+        return out
+
+    def wrap(self, tensor) -> Mat:
+        """Adopt a resident torch CUDA float32 matrix (no copy) -- inputs already in HBM."""
+        t = self.torch
+        if tensor.dtype != t.float32 or tensor.dim() != 2 or tensor.device != self.device:
+            raise ValueError("wrap() expects a 2-D float32 CUDA tensor on this device")
+        if tensor.stride(1) != 1:
+            raise ValueError("wrap() expects a row-major tensor")
+        rows, cols = tensor.shape
+        ld = tensor.stride(0) if rows > 1 else max(cols, 1)
+        if ld % 4 or tensor.data_ptr() % 16:
+            raise ValueError("row pitch must be a multiple of 4 floats and the base 16-byte aligned")
+        view = tensor.as_strided((rows, ld), (ld, 1)) if ld != cols else tensor
+        return Mat(view, None, rows, cols)
+
+    def wrap_view(self, tensor, c0: int, c1: int) -> Mat:
+        """Columns [c0, c1) of a resident row-major float32 CUDA matrix as a Mat (no copy)."""
+        full = self.wrap(tensor)
+        if c0 % 4:
+            raise ValueError("column block must start on a multiple of 4 columns (16-byte alignment)")
+        return Mat(tensor[:, c0:c1], None, full.rows, c1 - c0, ld=full.ld)
+
+    def download(self, t) -> np.ndarray:
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.detach().cpu().numpy()
+
+    def download_matrix(self, m: Mat) -> np.ndarray:
+        """D2H of the logical [rows][cols] block (hi + lo for split pairs is NOT applied here)."""
+        out = np.empty((m.rows, m.cols), dtype=np.float32)
+        if m.rows and m.cols:
+            check(self.lib.lit_memcpy_2d(_vp(out.ctypes.data), m.cols * 4, _vp(m.hi.data_ptr()), m.ld * 4, m.cols * 4,
+                                         m.rows, 2, _vp(self.stream)), "memcpy_2d(D2H)")
+            self.torch.cuda.current_stream(self.device).synchronize()
+            self.d2h_bytes += out.nbytes
+        return out
+
+    # ------------------------------------------------------------------ layout kernels
+    def gather_rows_T_split(self, src: Mat, idx, n: int) -> Mat:
+        out = self.empty(src.cols, n, split=True)
+        check(self.lib.lit_gather_rows_transpose_split(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr()), n, src.cols,
+                                                       _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld,
+                                                       _vp(self.stream)), "gather_rows_transpose_split")
+        self.launches += 1
+        return out
+
+    def gather_rows(self, src: Mat, idx, n: int, rows_out: Optional[int] = None, split: bool = False) -> Mat:
+        rows_out = n if rows_out is None else rows_out
+        out = self.empty(rows_out, src.cols, split=split)
+        check(self.lib.lit_gather_rows_f32(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr() if idx is not None else 0),
+                                           n, src.cols, _vp(out.hi.data_ptr()),
+                                           _vp(out.lo.data_ptr() if split else 0), out.ld, rows_out, _vp(self.stream)),
+              "gather_rows")
+        self.launches += 1
+        return out
+
+    def transpose(self, src: Mat, split: bool = False) -> Mat:
+        out = self.empty(src.cols, src.rows, split=split)
+        check(self.lib.lit_transpose_f32(_vp(src.hi.data_ptr()), src.rows, src.cols, src.ld, _vp(out.hi.data_ptr()),
+                                         _vp(out.lo.data_ptr() if split else 0), out.ld, _vp(self.stream)), "transpose")
+        self.launches += 1
+        return out
+
+    def split(self, src: Mat) -> Mat:
+        """Split pair of an fp32 matrix (new planes; src is left untouched)."""
+        out = self.empty(src.rows, src.cols, split=True, ld=src.ld)
+        check(self.lib.lit_split_tf32(_vp(src.hi.data_ptr()), src.rows, src.cols, src.ld, _vp(out.hi.data_ptr()),
+                                      _vp(out.lo.data_ptr()), out.ld, _vp(self.stream)), "split_tf32")
+        self.launches += 1
+        return out
+
+    def copy(self, src: Mat) -> Mat:
+        """Device-to-device copy of an fp32 matrix (same pitch)."""
+        out = self.empty(src.rows, src.cols, ld=src.ld)
+        check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr()), out.ld * 4, _vp(src.hi.data_ptr()), src.ld * 4,
+                                     src.cols * 4, src.rows, 3, _vp(self.stream)), "memcpy_2d(D2D)")
+        return out
+
+    def axpy(self, a: float, x: Mat, y: Mat) -> None:
+        check(self.lib.lit_axpy_f32(a, _vp(x.hi.data_ptr()), _vp(x.lo.data_ptr() if x.is_split else 0), x.ld,
+                                    _vp(y.hi.data_ptr()), y.ld, x.rows, x.cols, _vp(self.stream)), "axpy")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ statistics
+    def col_stats(self, src: Mat, idx, n: int, ddof: int):
+        mean, std = self.vec(src.cols), self.vec(src.cols)
+        scratch = self.vec(2 * src.cols, "f64")
+        check(self.lib.lit_col_stats(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr() if idx is not None else 0), n,
+                                     src.cols, ddof, _vp(mean.data_ptr()), _vp(std.data_ptr()),
+                                     _vp(scratch.data_ptr()), _vp(self.stream)), "col_stats")
+        self.launches += 2
+        return mean, std
+
+    def gather_normalize(self, src: Mat, idx, n: int, mean, std, mode: int, eps: float,
+                         rows_out: Optional[int] = None, split: bool = False) -> Mat:
+        rows_out = n if rows_out is None else rows_out
+        out = self.empty(rows_out, src.cols, split=split)
+        check(self.lib.lit_gather_normalize_rows(
+            _vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr() if idx is not None else 0), n, src.cols,
+            _vp(mean.data_ptr()), _vp(std.data_ptr() if std is not None else 0), mode, eps, _vp(out.hi.data_ptr()),
+            _vp(out.lo.data_ptr() if split else 0), out.ld, rows_out, _vp(self.stream)), "gather_normalize_rows")
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------ GEMMs
+    def gemm(self, A: Mat, B: Mat, alpha: float = 1.0, Cin: Optional[Mat] = None, beta: float = 0.0,
+             split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None) -> Mat:
+        """out[M,N] = alpha * A[M,K] @ B[N,K]^T + beta * Cin (A, B split pairs)."""
+        if not (A.is_split and B.is_split):
+            raise ValueError("GEMM operands must be 3xTF32 split pairs")
+        if A.cols != B.cols:
+            raise ValueError(f"GEMM K mismatch: {A} x {B}")
+        M, N, K = A.rows, B.rows, A.cols
+        if out is None:
+            out = self.empty(M, N, split=split_out, ld=ld_out)
+        check(self.lib.lit_gemm_tf32x3_nt(
+            _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M, N, K,
+            alpha, _vp(Cin.hi.data_ptr() if Cin is not None else 0), Cin.ld if Cin is not None else 0, beta,
+            _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr() if out.is_split else 0), out.ld, self.gemm_variant,
+            _vp(self.stream)), "gemm_tf32x3_nt")
+        self.launches += 1
+        self.gemm_flops += 2.0 * M * N * K
+        return out
+
+    def gemm_corr(self, A: Mat, B: Mat, n_groups: int, rows_per_group: int, Yz: Mat) -> Partials:
+        """Fused prediction + per-voxel reduction (see lit_gemm_tf32x3_nt_corr)."""
+        if rows_per_group % self.TILE_N or B.rows != n_groups * rows_per_group or Yz.rows != rows_per_group:
+            raise ValueError("gemm_corr: stacked design / response rows must be padded to the tile size")
+        if Yz.cols != A.rows or A.cols != B.cols:
+            raise ValueError("gemm_corr: shape mismatch")
+        M, K = A.rows, A.cols
+        n_tiles = n_groups * rows_per_group // self.TILE_N
+        ld = round_up(M, 32)
+        t = self.torch
+        dot = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
+        ssq = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
+        variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256, _lib.GEMM_2CTA_N256) \
+            else _lib.GEMM_AUTO
+        check(self.lib.lit_gemm_tf32x3_nt_corr(
+            _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
+            n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
+            variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
+        self.launches += 1
+        self.gemm_flops += 2.0 * M * (n_groups * rows_per_group) * K
+        return Partials(dot, ssq, n_tiles, ld)
+
+    # ------------------------------------------------------------------ eigendecomposition
+    def syevd(self, G: Mat, lam=None):
+        """In place: rows of G become the eigenvectors; returns ascending eigenvalues (device f32)."""
+        n = G.rows
+        if G.cols != n:
+            raise ValueError("syevd needs a square matrix")
+        key = (n, 0)
+        if key not in self._eig_ws:
+            dev_b, host_b = C.c_size_t(0), C.c_size_t(0)
+            check(self.lib.lit_syevd_workspace(n, 0, 1, C.byref(dev_b), C.byref(host_b)), "syevd_workspace")
+            work = self.torch.empty((max(dev_b.value, 16),), dtype=self.torch.uint8, device=self.device)
+            work_h = (C.c_uint8 * max(host_b.value, 16))()
+            self._eig_ws = {key: (work, dev_b.value, work_h, host_b.value)}  # keep only the latest size
+        work, dev_b, work_h, host_b = self._eig_ws[key]
+        info = self.vec(1, "i32")
+        self._eig_infos.append(info)
+        lam = self.vec(n) if lam is None else lam
+        with self.timed("eig"):
+            check(self.lib.lit_syevd(_vp(G.hi.data_ptr()), n, G.ld, 0, 1, _vp(lam.data_ptr()), _vp(work.data_ptr()),
+                                     dev_b, C.cast(work_h, _vp), host_b, _vp(info.data_ptr()), _vp(self.stream)),
+                  "syevd")
+        return lam
+
+    def check_eig(self) -> None:
+        """Raise if any syevd since the last check reported failure (synchronises)."""
+        infos, self._eig_infos = self._eig_infos, []
+        self.torch.cuda.synchronize(self.device)
+        bad = [int(i.item()) for i in infos if int(i.item()) != 0]
+        if bad:
+            raise _lib.LitRidgeError(f"cuSOLVER syevd did not converge (info = {bad})")
+
+    def syevd_async(self, G: Mat):
+        """Queue syevd(G) on the side stream behind everything already queued on the current stream.
+        Returns (lam, ticket); G and lam may be read on the current stream after wait(ticket)."""
+        t = self.torch
+        if self._side is None:
+            self._side = t.cuda.Stream(device=self.device)
+        lam = self.vec(G.rows)
+        ready = t.cuda.Event()
+        ready.record()
+        self._side.wait_event(ready)
+        with t.cuda.stream(self._side):
+            self.syevd(G, lam=lam)
+            done = t.cuda.Event()
+            done.record()
+        return lam, done
+
+    def wait(self, ticket) -> None:
+        self.torch.cuda.current_stream(self.device).wait_event(ticket)
+
+    # ------------------------------------------------------------------ ridge kernels
+    def build_alpha_stack(self, L: Mat, n_rows: int, rows_pad: int, lam, alphas_dev, n_alphas: int, normalpha: bool,
+                          singcutoff: float) -> Mat:
+        k = L.cols
+        out = self.empty(n_alphas * rows_pad, k, split=True)
+        col_mean = self.vec(k)
+        scratch = self.vec(2 * k, "f64")
+        check(self.lib.lit_build_alpha_stack(
+            _vp(L.hi.data_ptr()), L.ld, n_rows, rows_pad, k, _vp(lam.data_ptr()), _vp(alphas_dev.data_ptr()), n_alphas,
+            int(normalpha), singcutoff, _vp(col_mean.data_ptr()), _vp(scratch.data_ptr()), _vp(out.hi.data_ptr()),
+            _vp(out.lo.data_ptr()), out.ld, _vp(self.stream)), "build_alpha_stack")
+        self.launches += 3
+        return out
+
+    def scale_rows_by_alpha(self, Z: Mat, lam, alpha_v, normalpha: bool, singcutoff: float) -> Mat:
+        out = self.empty(Z.rows, Z.cols, split=True, ld=Z.ld)
+        check(self.lib.lit_scale_rows_by_alpha(
+            _vp(Z.hi.data_ptr()), _vp(Z.lo.data_ptr() if Z.is_split else 0), Z.ld, Z.rows, Z.cols, _vp(lam.data_ptr()),
+            _vp(alpha_v.data_ptr()), int(normalpha), singcutoff, _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld,
+            _vp(self.stream)), "scale_rows_by_alpha")
+        self.launches += 1
+        return out
+
+    def corr_finalize(self, parts: Partials, tiles_per_group: int, n_groups: int, n_vox: int, n_rows: int, eps: float,
+                      corr: Mat, accumulate: bool, metric: int = 0, resp_std=None) -> None:
+        check(self.lib.lit_corr_finalize(_vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld,
+                                         tiles_per_group, n_groups, n_vox, n_rows, eps, int(accumulate), metric,
+                                         _vp(resp_std.data_ptr() if resp_std is not None else 0),
+                                         _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize")
+        self.launches += 1
+
+    def argmax_alpha(self, corr_sum: Mat, n_folds: int, alphas_dev, want_sums: bool):
+        n_alphas, n_vox = corr_sum.rows, corr_sum.cols
+        best, alpha_v = self.vec(n_vox, "i32"), self.vec(n_vox)
+        sums = self.vec(n_alphas, "f64") if want_sums else None
+        check(self.lib.lit_argmax_alpha(_vp(corr_sum.hi.data_ptr()), corr_sum.ld, n_alphas, n_vox, n_folds,
+                                        _vp(alphas_dev.data_ptr()), _vp(best.data_ptr()), _vp(alpha_v.data_ptr()),
+                                        _vp(sums.data_ptr() if want_sums else 0), _vp(self.stream)), "argmax_alpha")
+        self.launches += 1
+        return best, alpha_v, sums
+
+    # ------------------------------------------------------------------ test statistics
+    def pearson_finalize(self, parts: Partials, n_vox: int, n_samples: int, p_round_f32: bool):
+        r, p = self.vec(n_vox), self.vec(n_vox, "f64")
+        check(self.lib.lit_pearson_finalize(_vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld,
+                                            parts.n_tiles, n_vox, n_samples, int(p_round_f32), _vp(r.data_ptr()),
+                                            _vp(p.data_ptr()), _vp(self.stream)), "pearson_finalize")
+        self.launches += 1
+        return r, p
+
+    def bh_fdr(self, p, n: int, alpha: float):
+        need = C.c_size_t(0)
+        check(self.lib.lit_bh_workspace(n, C.byref(need)), "bh_workspace")
+        if self._bh_ws is None or self._bh_ws.numel() < need.value:
+            self._bh_ws = self.torch.empty((need.value,), dtype=self.torch.uint8, device=self.device)
+        reject, padj, count = self.vec(n, "u8"), self.vec(n, "f64"), self.vec(1, "i32")
+        check(self.lib.lit_bh_fdr(_vp(p.data_ptr()), n, alpha, _vp(reject.data_ptr()), _vp(padj.data_ptr()),
+                                  _vp(count.data_ptr()), _vp(self._bh_ws.data_ptr()), self._bh_ws.numel(),
+                                  _vp(self.stream)), "bh_fdr")
+        n_pad = max(2048, 1 << (n - 1).bit_length())
+        stages = sum(1 + max(0, (k.bit_length() - 1) - 11) for k in
+                     (1 << s for s in range(12, n_pad.bit_length())))
+        self.launches += 3 + stages
+        return reject, padj, count
+
+    def fisher(self, p_stack, n_folds: int, n_vox: int, p_round_f32: bool):
+        out = self.vec(n_vox, "f64")
+        check(self.lib.lit_fisher_combine(_vp(p_stack.data_ptr()), p_stack.shape[1], n_folds, n_vox, int(p_round_f32),
+                                          _vp(out.data_ptr()), _vp(self.stream)), "fisher_combine")
+        self.launches += 1
+        return out
+
+    def stack_vectors(self, vecs, n: int, dtype: str = "f64"):
+        """[len(vecs)][n] device array from device vectors (D2D copies; plumbing)."""
+        t = self.torch
+        dt = {"f32": t.float32, "f64": t.float64}[dtype]
+        out = t.empty((len(vecs), max(n, 1)), dtype=dt, device=self.device)
+        item = 8 if dtype == "f64" else 4
+        for i, v in enumerate(vecs):
+            check(self.lib.lit_memcpy_2d(_vp(out.data_ptr() + i * out.shape[1] * item), n * item, _vp(v.data_ptr()),
+                                         n * item, n * item, 1, 3, _vp(self.stream)), "memcpy_2d(D2D)")
+        return out
+
+    # ------------------------------------------------------------------ feature construction
+    def fir_make_delayed(self, stim: np.ndarray, delays, circpad: bool) -> np.ndarray:
+        """Host array in, host float64 array out (FIR_expander.py:24-43 on the device)."""
+        t = self.torch
+        stim = np.ascontiguousarray(stim)
+        if stim.dtype not in (np.float32, np.float64):
+            stim = stim.astype(np.float64)
+        nt, ndim = stim.shape
+        nd = len(delays)
+        out_h = np.empty((nt, nd * ndim), dtype=np.float64)
+        if out_h.size == 0:
+            return out_h
+        d_stim = t.from_numpy(stim).to(self.device)
+        d_del = self.upload_vector(np.asarray(delays, dtype=np.int64), "i32")
+        d_out = t.empty((nt, nd * ndim), dtype=t.float64, device=self.device)
+        check(self.lib.lit_fir_make_delayed(_vp(d_stim.data_ptr()), 0 if stim.dtype == np.float32 else 1, nt, ndim,
+                                            ndim, _vp(d_del.data_ptr()), nd, int(bool(circpad)),
+                                            _vp(d_out.data_ptr()), nd * ndim, _vp(self.stream)), "fir_make_delayed")
+        self.launches += 1
+        t.from_numpy(out_h).copy_(d_out)
+        return out_h
+
+    def lanczos_downsample(self, data: np.ndarray, data_times: np.ndarray, tr_times: np.ndarray, window: float,
+                           cutoff: float, rectify: bool, lo: Optional[np.ndarray], hi: Optional[np.ndarray]) -> np.ndarray:
+        t = self.torch
+        data = np.ascontiguousarray(data)
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        n_s, ndim = data.shape
+        n_tr = len(tr_times)
+        width = (2 if rectify else 1) * ndim
+        out_h = np.empty((n_tr, width), dtype=np.float64)
+        if out_h.size == 0:
+            return out_h
+        if n_s == 0:
+            out_h[:] = 0.0
+            return out_h
+        d_data = t.from_numpy(data).to(self.device)
+        d_dt = self.upload_vector(data_times, "f64")
+        d_tr = self.upload_vector(tr_times, "f64")
+        d_lo = self.upload_vector(lo, "i32") if lo is not None else None
+        d_hi = self.upload_vector(hi, "i32") if hi is not None else None
+        d_out = t.empty((n_tr, width), dtype=t.float64, device=self.device)
+        check(self.lib.lit_lanczos_downsample(
+            _vp(d_data.data_ptr()), 0 if data.dtype == np.float32 else 1, n_s, ndim, ndim, _vp(d_dt.data_ptr()),
+            _vp(d_tr.data_ptr()), n_tr, float(window), float(cutoff), int(bool(rectify)),
+            _vp(d_lo.data_ptr() if d_lo is not None else 0), _vp(d_hi.data_ptr() if d_hi is not None else 0),
+            _vp(d_out.data_ptr()), width, _vp(self.stream)), "lanczos_downsample")
+        self.launches += 1
+        t.from_numpy(out_h).copy_(d_out)
+        return out_h
+
+
+_default_ops: Optional[DeviceOps] = None
+
+
+def default_ops() -> DeviceOps:
+    """Process-wide DeviceOps on the current CUDA device (LOCAL_RANK-aware callers set the device first)."""
+    global _default_ops
+    import torch
+
+    if _default_ops is None or _default_ops.device.index != torch.cuda.current_device():
+        _default_ops = DeviceOps()
+    return _default_ops

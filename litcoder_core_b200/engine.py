@@ -1,0 +1,314 @@
+"""Nested-CV ridge engine: the reference's fit_predict algebra re-planned for B200.
+
+Reference formulation (encoding/models/ridge_regression.py, nested_cv.py): a thin SVD of every
+training design, predictions materialised per alpha (n_val x V fp32 each), several elementwise
+passes for the z-scored correlation, and per-voxel SciPy loops for the test statistics.
+
+This engine computes the same quantities from the Gram side, with every matrix kept in the layout
+the tensor cores want (K-major operands, voxels on the accumulator rows):
+
+    G   = X_tr^T X_tr                    (p x p)     tcgen05 3xTF32 GEMM
+    G   = V diag(lam) V^T                            cuSOLVER syevd  (lam = S^2, rows of Vt = Vh)
+    C^T = Y_tr^T X_tr                    (V x p)     GEMM, K = training TRs
+    Z^T = C^T V                          (V x k)     GEMM           (= (S U^T Y)^T)
+    L   = P_val V, column-centred        (n_v x k)   GEMM + streaming kernel
+    pred_a = L diag(1/(lam + a'^2)) Z    never materialised: ONE GEMM over the alpha-stacked L with the
+                                         per-voxel reduction (sum pred*zY, sum pred^2) in its epilogue
+    W^T = (Z^T * 1/(lam + a_v'^2)) V^T   (V x p)     per-voxel shrinkage + GEMM
+    r   = corr(P_test W, Y_test)                     same fused GEMM, then p-values / BH / Fisher kernels
+
+With X = U S V^T:  U^T Y = S^-1 V^T X^T Y, so (PVh * D) @ UR with D = S/(S^2+a^2) equals
+P V diag(1/(lam+a^2)) V^T X^T Y -- identical algebra, no SVD of the tall matrix, no n_v x V buffer.
+
+Two further savings inside one outer fold (both exact up to fp32 rounding of a sum):
+
+  * the Gram and the cross product of an inner fold are DOWNDATES of the outer fold's:
+        G_i = G_o - X_R^T X_R,   C_i^T = C_o^T - Y_R^T X_R,   R = outer-train rows not in inner-train
+    (|R| ~ n/5), so Y is streamed once per outer fold plus once per removed block instead of once
+    per inner fold, and the K extent of those GEMMs drops by 4x;
+  * all eigendecompositions of an outer fold depend only on X, so they are queued up front on a
+    side stream and overlap the response-side GEMMs on the main stream.
+
+The engine is written against the small `ops` interface of device.DeviceOps so that its control
+flow can be unit-tested on CPU with a NumPy stand-in (tests/fake_ops.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+EPS = 1e-8  # ridge_utils.z_score / DataNormalizer eps
+
+
+@dataclass
+class RidgeConfig:
+    alphas: Sequence[float]
+    alpha_fdr: float = 0.05
+    single_alpha: bool = False
+    normalpha: bool = True
+    use_corr: bool = True
+    normalize_features: bool = False
+    normalize_targets: bool = False
+    singcutoff: float = 1e-10
+    n_outer_folds: int = 5
+    p_round_f32: bool = True  # SciPy >= 1.14 keeps float32 inputs' dtype for p-values
+    downdate: bool = True  # inner-fold Gram / cross product by subtraction from the outer fold's
+    overlap_eig: bool = True  # eigendecompositions on a side stream
+
+
+@dataclass
+class FoldPlan:
+    """Host-side description of one outer fold; all indices are absolute rows of the source arrays."""
+    train_rows: np.ndarray
+    test_rows: np.ndarray
+    inner: List[Tuple[np.ndarray, np.ndarray]]  # (train rows, validation rows)
+
+
+@dataclass
+class ShardResult:
+    """Per-voxel-shard outputs of the fit (device handles)."""
+    r: list = field(default_factory=list)  # per outer fold: (V_r,) f32
+    p: list = field(default_factory=list)  # per outer fold: (V_r,) f64
+    alpha: list = field(default_factory=list)  # per outer fold: (V_r,) f32
+    Wt_mean: object = None  # Mat (V_r x p): fold-mean of the weights, voxel-major
+    n_test: list = field(default_factory=list)
+
+
+class SingleProcess:
+    """Degenerate communicator (one voxel shard)."""
+    rank, world = 0, 1
+
+    def all_reduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        return arr
+
+    def all_gather_concat(self, arr: np.ndarray, counts=None) -> np.ndarray:
+        return arr
+
+
+def removed_rows(outer_rows: np.ndarray, inner_rows: np.ndarray) -> Optional[np.ndarray]:
+    """Rows of the outer training set that are absent from the inner one, or None when the inner set
+    is not a duplicate-free subset of the outer set (then the downdate identity does not hold)."""
+    outer_rows = np.asarray(outer_rows, dtype=np.int64)
+    inner_rows = np.asarray(inner_rows, dtype=np.int64)
+    if len(np.unique(inner_rows)) != len(inner_rows) or len(np.unique(outer_rows)) != len(outer_rows):
+        return None
+    keep = np.isin(outer_rows, inner_rows, assume_unique=True)
+    if int(keep.sum()) != len(inner_rows):
+        return None
+    return outer_rows[~keep]
+
+
+class RidgeCVEngine:
+    def __init__(self, ops, comm=None):
+        self.ops = ops
+        self.comm = comm if comm is not None else SingleProcess()
+
+    # ------------------------------------------------------------------------------------------
+    # design side: Grams and their eigendecompositions (depend on X only)
+    # ------------------------------------------------------------------------------------------
+    def _design_side(self, X, plan: FoldPlan, cfg: RidgeConfig):
+        """Gram + syevd for the outer training set and for every inner fold.
+
+        Returns (outer, inners): dicts with XtT (p x n split, or None when downdated), XRt (p x |R| split)
+        / R for downdated folds, G (holds Vt after the eig), lam and the eig ticket."""
+        ops = self.ops
+        tr_o = np.asarray(plan.train_rows, dtype=np.int64)
+        XoT = ops.gather_rows_T_split(X, ops.upload_index(tr_o), len(tr_o))  # (p x n_o)
+        G_o = ops.gemm(XoT, XoT)  # outer Gram, p x p
+        inners = []
+        for tr_i, va_i in plan.inner:
+            R = removed_rows(tr_o, tr_i) if cfg.downdate else None
+            d = {"train": np.asarray(tr_i, dtype=np.int64), "val": np.asarray(va_i, dtype=np.int64), "R": None}
+            if R is not None and 0 < len(R) <= len(tr_i) // 2:
+                XRt = ops.gather_rows_T_split(X, ops.upload_index(R), len(R))  # (p x |R|)
+                d.update(R=R, XRt=XRt, XtT=None, G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0))
+            else:
+                XtT = ops.gather_rows_T_split(X, ops.upload_index(d["train"]), len(d["train"]))
+                d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT))
+            inners.append(d)
+        outer = {"XtT": XoT, "G": ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o, "G_keep": G_o}
+        # queue every eigendecomposition (inner folds first: they are needed first)
+        for d in inners + [outer]:
+            d["lam"], d["ticket"] = ops.syevd_async(d["G"]) if cfg.overlap_eig else (ops.syevd(d["G"]), None)
+        return outer, inners
+
+    def _eig_ready(self, d):
+        """Wait (on the main stream) for d's eigendecomposition; returns (Vt split, Vt fp32, lam)."""
+        ops = self.ops
+        if d["ticket"] is not None:
+            ops.wait(d["ticket"])
+            d["ticket"] = None
+        return ops.split(d["G"]), d["G"], d["lam"]
+
+    # ------------------------------------------------------------------------------------------
+    # inner CV
+    # ------------------------------------------------------------------------------------------
+    def _inner_scores(self, X, Y, plan: FoldPlan, outer, inners, alphas_dev, n_alphas: int, cfg: RidgeConfig):
+        """Sum over inner folds of the (n_alphas x V_r) validation scores (ridge_corr_torch per fold).
+        Also returns C_o^T (V_r x p fp32) for the outer fit."""
+        ops = self.ops
+        tr_o = np.asarray(plan.train_rows, dtype=np.int64)
+        YoT = ops.gather_rows_T_split(Y, ops.upload_index(tr_o), len(tr_o))  # (V_r x n_o)
+        Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
+        del YoT
+        corr_sum = ops.empty(n_alphas, Y.cols)
+        metric = 0 if cfg.use_corr else 1
+        for i, d in enumerate(inners):
+            tr, va = d["train"], d["val"]
+            n_tr, n_va = len(tr), len(va)
+            if n_va < 2 or n_tr < 1:
+                raise ValueError("inner fold needs >= 1 training and >= 2 validation samples")
+            # cross product of the inner training rows
+            if d["R"] is not None:
+                YRt = ops.gather_rows_T_split(Y, ops.upload_index(d["R"]), len(d["R"]))  # (V_r x |R|)
+                Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True)
+                del YRt
+            else:
+                YtT = ops.gather_rows_T_split(Y, ops.upload_index(tr), n_tr)
+                Ct = ops.gemm(YtT, d["XtT"], split_out=True)
+                del YtT
+            Vt, _, lam = self._eig_ready(d)
+            Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
+            del Ct
+            # validation design in the eigenbasis, centred and stacked over alphas
+            va_dev = ops.upload_index(va)
+            rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
+            Pv = ops.gather_rows(X, va_dev, n_va, split=True)  # (n_v x p)
+            L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
+            Lst = ops.build_alpha_stack(L, n_va, rows_pad, lam, alphas_dev, n_alphas, cfg.normalpha, cfg.singcutoff)
+            del Pv, L, Vt
+            mean, std = ops.col_stats(Y, va_dev, n_va, ddof=1)
+            Yz = ops.gather_normalize(Y, va_dev, n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
+            parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz)
+            ops.corr_finalize(parts, rows_pad // ops.TILE_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
+                              accumulate=(i > 0), metric=metric, resp_std=std)
+            del Zt, Lst, Yz, parts
+            d["G"] = d["XRt"] = d["XtT"] = None
+        return corr_sum, Ct_o
+
+    def _select_alphas(self, corr_sum, n_folds: int, alphas_dev, cfg: RidgeConfig, n_vox_total: int):
+        """nested_cv._find_best_alphas :391-413 -> device vector of per-voxel alpha values."""
+        ops = self.ops
+        _, alpha_v, sums = ops.argmax_alpha(corr_sum, n_folds, alphas_dev, want_sums=cfg.single_alpha)
+        if cfg.single_alpha:
+            tot = self.comm.all_reduce_sum(np.asarray(ops.download(sums), dtype=np.float64)[: len(cfg.alphas)])
+            j = int(np.argmax((tot / float(n_vox_total)).astype(np.float32)))
+            alpha_v = ops.upload_vector(np.full(corr_sum.cols, np.float32(cfg.alphas[j]), dtype=np.float32), "f32")
+        return alpha_v
+
+    # ------------------------------------------------------------------------------------------
+    # outer fit + test scoring
+    # ------------------------------------------------------------------------------------------
+    def _outer_fit_and_score(self, Xte_src, Yte_src, plan: FoldPlan, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+        """ridge_torch on the outer training set with the selected alphas, then test r / p."""
+        ops = self.ops
+        n_te = len(plan.test_rows)
+        te_dev = ops.upload_index(plan.test_rows)
+        Vt, G, lam = self._eig_ready(outer)
+        Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
+        del Vt
+        ZS = ops.scale_rows_by_alpha(Zt, lam, alpha_v, cfg.normalpha, cfg.singcutoff)  # (V_r x k)
+        del Zt
+        Vmat = ops.transpose(G, split=True)  # (p x k): rows = features
+        Wt = ops.gemm(ZS, Vmat, split_out=True)  # (V_r x p) voxel-major weights
+        del ZS, Vmat
+        # test predictions, centred so that the fused epilogue yields Pearson's r directly
+        rows_pad = -(-n_te // ops.TILE_N) * ops.TILE_N
+        pm, _ = ops.col_stats(Xte_src, te_dev, n_te, ddof=0)
+        Pt = ops.gather_normalize(Xte_src, te_dev, n_te, pm, None, 2, EPS, rows_out=rows_pad, split=True)
+        ym, ys = ops.col_stats(Yte_src, te_dev, n_te, ddof=1)
+        Ytz = ops.gather_normalize(Yte_src, te_dev, n_te, ym, ys, 1, EPS, rows_out=rows_pad)
+        parts = ops.gemm_corr(Wt, Pt, 1, rows_pad, Ytz)
+        r, p = ops.pearson_finalize(parts, Wt.rows, n_te, cfg.p_round_f32)
+        return Wt, r, p
+
+    def _normalised(self, X, Y, Xte_src, Yte_src, train_rows, cfg: RidgeConfig, same_source: bool):
+        """DataNormalizer (ridge_utils.py:70-180): z-score with the training rows' statistics."""
+        ops = self.ops
+        if not (cfg.normalize_features or cfg.normalize_targets):
+            return X, Y, Xte_src, Yte_src
+        tr_dev = ops.upload_index(train_rows)
+        n = len(train_rows)
+        Xn, Yn, Xtn, Ytn = X, Y, Xte_src, Yte_src
+        if cfg.normalize_features:
+            m, s = ops.col_stats(X, tr_dev, n, ddof=1)
+            Xn = ops.gather_normalize(X, None, X.rows, m, s, 0, EPS)
+            Xtn = Xn if same_source else ops.gather_normalize(Xte_src, None, Xte_src.rows, m, s, 0, EPS)
+        if cfg.normalize_targets:
+            m, s = ops.col_stats(Y, tr_dev, n, ddof=1)
+            Yn = ops.gather_normalize(Y, None, Y.rows, m, s, 0, EPS)
+            Ytn = Yn if same_source else ops.gather_normalize(Yte_src, None, Yte_src.rows, m, s, 0, EPS)
+        return Xn, Yn, Xtn, Ytn
+
+    # ------------------------------------------------------------------------------------------
+    # drivers
+    # ------------------------------------------------------------------------------------------
+    def fit_shard(self, X, Y, plans: List[FoldPlan], cfg: RidgeConfig, X_test=None, Y_test=None,
+                  n_vox_total: Optional[int] = None) -> ShardResult:
+        """Run every outer fold on this rank's voxel shard.
+
+        X (N x p) and Y (N x V_r) are device matrices.  In train/test mode there is one plan whose
+        test_rows index X_test / Y_test; in nested mode test rows index X / Y themselves."""
+        ops = self.ops
+        alphas = np.asarray(cfg.alphas, dtype=np.float64)
+        alphas_f32 = ops.upload_vector(alphas.astype(np.float32), "f32")
+        alphas_f64 = ops.upload_vector(alphas, "f64")
+        n_vox_total = Y.cols if n_vox_total is None else n_vox_total
+        res = ShardResult()
+        same_source = X_test is None
+        inv = 1.0 / len(plans)
+        for plan in plans:
+            Xs, Ys, Xts, Yts = self._normalised(X, Y, X if same_source else X_test, Y if same_source else Y_test,
+                                                plan.train_rows, cfg, same_source)
+            outer, inners = self._design_side(Xs, plan, cfg)
+            corr_sum, Ct_o = self._inner_scores(Xs, Ys, plan, outer, inners, alphas_f64, len(alphas), cfg)
+            alpha_v = self._select_alphas(corr_sum, len(plan.inner), alphas_f32, cfg, n_vox_total)
+            del corr_sum, inners
+            Wt, r, p = self._outer_fit_and_score(Xts, Yts, plan, outer, Ct_o, alpha_v, cfg)
+            del outer, Ct_o
+            if len(plans) == 1:
+                res.Wt_mean = Wt
+            else:
+                if res.Wt_mean is None:
+                    res.Wt_mean = ops.zeros(Wt.rows, Wt.cols)
+                ops.axpy(inv, Wt, res.Wt_mean)  # np.mean(fold_weights, axis=0), nested_cv.py:296
+            del Wt
+            res.r.append(r)
+            res.p.append(p)
+            res.alpha.append(alpha_v)
+            res.n_test.append(len(plan.test_rows))
+        return res
+
+    def weights_matrix(self, res: ShardResult):
+        """(p x V_r) fp32 device matrix of this shard's (fold-mean) weights."""
+        ops = self.ops
+        W = res.Wt_mean
+        if W.is_split:  # single fold: the GEMM wrote a split pair -> recombine hi + lo
+            full = ops.zeros(W.rows, W.cols)
+            ops.axpy(1.0, W, full)
+            W = full
+        return ops.transpose(W)
+
+    def significance(self, p_folds: np.ndarray, cfg: RidgeConfig):
+        """BH per fold, Fisher across folds, BH on the combined p (nested_cv.py:263-290) on device.
+
+        p_folds: (n_folds x V) float64 host array holding ALL voxels (gathered across shards).
+        Returns per-fold masks, combined p, its BH mask and adjusted p (host arrays)."""
+        ops = self.ops
+        K, V = p_folds.shape
+        masks = []
+        p_dev = [ops.upload_vector(p_folds[f], "f64") for f in range(K)]
+        padj0 = None
+        for f in range(K):
+            rej, padj, _ = ops.bh_fdr(p_dev[f], V, cfg.alpha_fdr)
+            masks.append(ops.download(rej)[:V].astype(bool))
+            if K == 1:
+                padj0 = ops.download(padj)[:V]
+        if K == 1:
+            return masks, None, masks[0], padj0
+        stack = ops.stack_vectors(p_dev, V, "f64")
+        comb = ops.fisher(stack, K, V, cfg.p_round_f32)
+        rej, padj, _ = ops.bh_fdr(comb, V, cfg.alpha_fdr)
+        return masks, ops.download(comb)[:V], ops.download(rej)[:V].astype(bool), ops.download(padj)[:V]

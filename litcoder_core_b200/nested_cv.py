@@ -1,0 +1,291 @@
+"""Drop-in for the reference's nested-CV ridge model (encoding/models/nested_cv.py).
+
+    NestedCVModel(model_name="ridge_regression").fit_predict(features, targets, ...)   nested_cv.py:14-331
+    fit_nested_cv(features=X, targets=Y, ...)                                          README.md:137,212-226
+
+Same keyword arguments, same return triple ``(metrics, weights, best_alphas)``, same metrics keys
+(nested_cv.py:501-528, 558-614), same fold semantics (folding.py) -- but the arithmetic runs on
+a B200 through the C ABI of liblitridge.so (engine.py / device.py).  Host code here only builds
+fold index lists, moves arrays across the PCIe boundary and assembles the metrics dictionary.
+
+Multi-GPU: when ``torch.distributed`` is initialised (one process per GPU, NCCL), the voxels
+(columns of ``targets``) are split into contiguous blocks, one per rank; ranks exchange only
+(i) the per-alpha score sums for ``single_alpha=True`` (all-reduce of A doubles per outer fold)
+and (ii) the per-voxel r / p / alpha vectors and, optionally, the weight blocks (all-gather at
+the end).  Every rank returns the full result.
+
+There is no CPU fallback: ``use_gpu=False`` is accepted for signature compatibility and ignored
+(with a log line); without a CUDA device or the built library the call raises.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from .engine import FoldPlan, RidgeConfig, RidgeCVEngine, SingleProcess
+from .folding import create_folds
+
+logger = logging.getLogger(__name__)
+
+
+# ----------------------------------------------------------------------------------------------
+# communicator over torch.distributed (NCCL on GPUs, gloo in the CPU tests)
+# ----------------------------------------------------------------------------------------------
+class TorchDistComm:
+    """Host-array collectives for the engine.  NCCL needs device tensors, gloo host tensors."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self._torch, self._dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        self._dev = device if (backend == "nccl" and device is not None) else (
+            torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+
+    def all_reduce_sum(self, arr: np.ndarray) -> np.ndarray:
+        t = self._torch.from_numpy(np.ascontiguousarray(arr)).to(self._dev)
+        self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def all_gather_concat(self, arr: np.ndarray, counts: Optional[Sequence[int]] = None) -> np.ndarray:
+        """Concatenate the ranks' arrays along the LAST axis; counts[r] = last-axis length on rank r."""
+        arr = np.ascontiguousarray(arr)
+        if counts is None:
+            counts = [arr.shape[-1]] * self.world
+        width = max(counts)
+        pad = np.zeros(arr.shape[:-1] + (width,), dtype=arr.dtype)
+        pad[..., : arr.shape[-1]] = arr
+        t = self._torch.from_numpy(pad).to(self._dev)
+        outs = [self._torch.empty_like(t) for _ in range(self.world)]
+        self._dist.all_gather(outs, t, group=self.group)
+        return np.concatenate([o.cpu().numpy()[..., : counts[r]] for r, o in enumerate(outs)], axis=-1)
+
+
+def default_comm():
+    """TorchDistComm when a process group with more than one rank is initialised, else single-process."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return SingleProcess()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return TorchDistComm()
+    return SingleProcess()
+
+
+def shard_bounds(n_vox: int, world: int) -> List[int]:
+    """Contiguous voxel blocks: boundaries b[0..world]; block sizes are multiples of 128 (one GEMM
+    M tile) except the last, so that every rank's shard starts on a tile boundary."""
+    per = -(-n_vox // world)
+    per = -(-per // 128) * 128
+    return [min(r * per, n_vox) for r in range(world + 1)]
+
+
+# ----------------------------------------------------------------------------------------------
+# metrics dictionaries (nested_cv.py:480-616)
+# ----------------------------------------------------------------------------------------------
+def _summary(values: np.ndarray, infix: str = "") -> Dict[str, float]:
+    return {
+        f"median_{infix}score": float(np.median(values)),
+        f"mean_{infix}score": float(np.mean(values)),
+        f"min_{infix}score": float(np.min(values)),
+        f"max_{infix}score": float(np.max(values)),
+    }
+
+
+def _metrics(corr: np.ndarray, pvals: np.ndarray, padj: np.ndarray, sig: np.ndarray, best_alphas: np.ndarray,
+             majority: Optional[np.ndarray] = None) -> Dict[str, Any]:
+    n = len(corr)
+    n_sig = int(np.sum(sig))
+    m: Dict[str, Any] = {
+        "median_score": float(np.median(corr)),
+        "mean_score": float(np.mean(corr)),
+        "std_score": float(np.std(corr)),
+        "min_score": float(np.min(corr)),
+        "max_score": float(np.max(corr)),
+        "best_alphas": best_alphas.tolist(),
+        "correlations": corr.tolist(),
+        "p_values": pvals.tolist(),
+        "corrected_p_values": padj.tolist(),
+        "significant_mask": sig.tolist(),
+    }
+    if majority is not None:
+        m["majority_significant_mask"] = majority.tolist()
+    m["n_significant"] = n_sig
+    if majority is not None:
+        m["n_majority_significant"] = int(np.sum(majority))
+    m["percent_significant"] = float(n_sig / n * 100)
+    if majority is not None:
+        m["percent_majority_significant"] = float(m["n_majority_significant"] / n * 100)
+    if n_sig > 0:
+        m.update(_summary(corr[sig], "significant_"))
+    if majority is not None and m["n_majority_significant"] > 0:
+        m.update(_summary(corr[majority], "majority_significant_"))
+    return m
+
+
+# ----------------------------------------------------------------------------------------------
+class NestedCVModel:
+    """Nested cross-validated ridge regression from (delayed) stimulus features to voxels."""
+
+    def __init__(self, model_name: str = "ridge_regression", ops=None, comm=None):
+        self.model_name = model_name
+        self._ops = ops
+        self._comm = comm
+        self.last_timings: Dict[str, float] = {}  # per-phase milliseconds of the most recent fit
+        self.last_stats: Dict[str, Any] = {}
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _get_ops(self):
+        if self._ops is None:
+            from .device import default_ops
+
+            self._ops = default_ops()
+        return self._ops
+
+    @staticmethod
+    def _is_torch(x) -> bool:
+        return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+    def _to_device(self, ops, arr, c0: int = 0, c1: Optional[int] = None):
+        """Host ndarray (any float dtype) or resident CUDA float32 tensor -> device Mat of columns [c0, c1)."""
+        if self._is_torch(arr):
+            if arr.is_cuda:
+                c1 = arr.shape[1] if c1 is None else c1
+                if c0 == 0 and c1 == arr.shape[1]:
+                    return ops.wrap(arr)
+                return ops.wrap_view(arr, c0, c1)
+            arr = arr.detach().numpy()
+        return ops.upload_matrix(np.asarray(arr), c0, c1)
+
+    # -- public API --------------------------------------------------------------------------------
+    def fit_predict(
+        self,
+        features: np.ndarray,
+        targets: np.ndarray,
+        X_test: Optional[np.ndarray] = None,
+        y_test: Optional[np.ndarray] = None,
+        groups: Optional[np.ndarray] = None,
+        folding_type: str = "chunked",
+        n_outer_folds: int = 5,
+        n_inner_folds: int = 5,
+        chunk_length: int = 20,
+        alphas: Optional[List[float]] = None,
+        alpha_fdr: float = 0.05,
+        use_gpu: bool = True,
+        single_alpha: bool = False,
+        normalpha: bool = True,
+        use_corr: bool = True,
+        normalize_features: bool = False,
+        normalize_targets: bool = False,
+        singcutoff: float = 1e-10,
+        gather_weights: bool = True,
+    ) -> Tuple[Dict[str, Union[float, List[float], List[bool]]], np.ndarray, np.ndarray]:
+        """Fit with nested CV (or inner CV + a given test set), per-voxel or single alpha, FDR correction.
+
+        Arguments and return value as the reference (nested_cv.py:18-70).  ``gather_weights`` (extension,
+        multi-GPU only): False returns this rank's (p x V_rank) weight block instead of the full matrix.
+        """
+        t_start = time.perf_counter()
+        if alphas is None:
+            alphas = np.logspace(-1, 8, 10)  # nested_cv.py:80-81
+        alphas = [float(a) for a in alphas]
+        if not use_gpu:
+            logger.info("use_gpu=False ignored: litcoder_core_b200 always runs on the B200 (no CPU path)")
+        n_samples, n_vox = features.shape[0], targets.shape[1]
+        if targets.shape[0] != n_samples:
+            raise ValueError("features and targets must have the same number of rows")
+        train_test_mode = X_test is not None and y_test is not None  # nested_cv.py:103
+        logger.info("Folding type: %s", folding_type)
+
+        # ---- fold index lists (host; reference semantics incl. the positional `groups` -> trim_size slot) ----
+        plans: List[FoldPlan] = []
+        if train_test_mode:
+            inner = create_folds(n_samples, folding_type, n_inner_folds, chunk_length, groups)  # nested_cv.py:130-132
+            plans.append(FoldPlan(np.arange(n_samples, dtype=np.int64), np.arange(X_test.shape[0], dtype=np.int64),
+                                  [(np.asarray(a, dtype=np.int64), np.asarray(b, dtype=np.int64)) for a, b in inner]))
+        else:
+            if groups is not None and folding_type == "group":
+                outer = create_folds(n_samples, "group", n_outer_folds, groups=groups)
+            else:
+                outer = create_folds(n_samples, folding_type, n_outer_folds, chunk_length, groups)
+            for tr, te in outer:
+                tr = np.asarray(tr, dtype=np.int64)
+                te = np.asarray(te, dtype=np.int64)
+                if groups is not None and folding_type == "group":
+                    inner = create_folds(len(tr), "group", n_inner_folds, groups=[groups[i] for i in tr])
+                else:
+                    inner = create_folds(len(tr), folding_type, n_inner_folds, chunk_length)
+                # inner indices are positions within the outer training rows (nested_cv.py:200-201,371-374)
+                plans.append(FoldPlan(tr, te, [(tr[np.asarray(a, dtype=np.int64)], tr[np.asarray(b, dtype=np.int64)])
+                                               for a, b in inner]))
+
+        cfg = RidgeConfig(alphas=alphas, alpha_fdr=alpha_fdr, single_alpha=single_alpha, normalpha=normalpha,
+                          use_corr=use_corr, normalize_features=normalize_features,
+                          normalize_targets=normalize_targets, singcutoff=singcutoff, n_outer_folds=n_outer_folds)
+
+        # ---- H2D: X replicated, this rank's voxel block of Y (nested_cv.py:99-100) ----
+        ops = self._get_ops()
+        comm = self._comm if self._comm is not None else default_comm()
+        bounds = shard_bounds(n_vox, comm.world)
+        c0, c1 = bounds[comm.rank], bounds[comm.rank + 1]
+        counts = [bounds[r + 1] - bounds[r] for r in range(comm.world)]
+        ops.reset_counters()
+        with ops.timed("h2d"):
+            X = self._to_device(ops, features)
+            Y = self._to_device(ops, targets, c0, c1)
+            Xt = self._to_device(ops, X_test) if train_test_mode else None
+            Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
+
+        engine = RidgeCVEngine(ops, comm)
+        with ops.timed("fit"):
+            res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox)
+        ops.check_eig()
+
+        # ---- per-voxel vectors back to the host, gathered over ranks ----
+        with ops.timed("d2h"):
+            r_f = np.stack([ops.download(v)[: c1 - c0] for v in res.r]).astype(np.float32)
+            p_f = np.stack([ops.download(v)[: c1 - c0] for v in res.p]).astype(np.float64)
+            a_f = np.stack([ops.download(v)[: c1 - c0] for v in res.alpha]).astype(np.float32)
+            if comm.world > 1:
+                r_f = comm.all_gather_concat(r_f, counts)
+                p_f = comm.all_gather_concat(p_f, counts)
+                a_f = comm.all_gather_concat(a_f, counts)
+            W = ops.download_matrix(engine.weights_matrix(res))  # (p x V_rank) float32
+            if comm.world > 1 and gather_weights:
+                W = comm.all_gather_concat(W, counts)
+        del res
+
+        with ops.timed("stats"):
+            masks, comb_p, sig, padj = engine.significance(p_f, cfg)
+
+        if train_test_mode:
+            best = a_f[0].astype(np.float64) if single_alpha else a_f[0]  # reference dtype quirk (:396-405)
+            metrics = _metrics(r_f[0].astype(np.float64), p_f[0], padj, sig, best)
+        else:
+            if comb_p is None:  # a single outer fold: Fisher's method on one p-value is the identity
+                comb_p = p_f[0]
+            corr = np.mean(r_f, axis=0)  # nested_cv.py:276
+            majority = np.sum(np.stack(masks), axis=0) >= (n_outer_folds // 2 + 1)  # nested_cv.py:288-290
+            best = np.mean(a_f.astype(np.float64) if single_alpha else a_f, axis=0)  # nested_cv.py:293
+            metrics = _metrics(corr.astype(np.float64), comb_p, padj, sig, best, majority)
+
+        self.last_timings = ops.timings()
+        self.last_timings["wall_ms"] = (time.perf_counter() - t_start) * 1e3
+        self.last_stats = {"launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
+                           "world": comm.world, "voxels_this_rank": c1 - c0,
+                           "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0)}
+        logger.info("Median correlation: %.3f", metrics["median_score"])
+        logger.info("Significant voxels: %d/%d (%.1f%%)", metrics["n_significant"], n_vox,
+                    metrics["percent_significant"])
+        return metrics, W, best
+
+
+def fit_nested_cv(features: np.ndarray, targets: np.ndarray, **kwargs):
+    """Function form documented by the reference (README.md:137,212-226); same kwargs as fit_predict."""
+    return NestedCVModel(model_name="ridge_regression").fit_predict(features=features, targets=targets, **kwargs)

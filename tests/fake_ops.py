@@ -1,0 +1,324 @@
+"""NumPy stand-in for litcoder_core_b200.device.DeviceOps -- TEST INFRASTRUCTURE ONLY.
+
+It restates, operation by operation, what the C-ABI entry points of include/litridge.h compute
+(in float32, GEMMs accumulated in float64 to play the role of 3xTF32), so that the host logic of
+the engine (fold plans, downdates, stream tickets, accumulation over folds, sharding, metrics) can
+be exercised by `pytest -m "not gpu"` on a machine without a GPU.  It is never imported by the
+product package; the GPU tests run the same engine code against the real DeviceOps.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+
+import numpy as np
+
+F32 = np.float32
+
+
+class FMat:
+    def __init__(self, a: np.ndarray, split: bool = False):
+        self.a = np.ascontiguousarray(a, dtype=F32)
+        self.is_split = split
+
+    @property
+    def rows(self):
+        return self.a.shape[0]
+
+    @property
+    def cols(self):
+        return self.a.shape[1]
+
+    @property
+    def ld(self):
+        return self.a.shape[1]
+
+
+class FakeOps:
+    TILE_N = 256
+
+    def __init__(self):
+        self.reset_counters()
+        self.eig_calls = 0
+        self.pending = 0
+
+    def reset_counters(self):
+        self.launches = 0
+        self.gemm_flops = 0.0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    @contextlib.contextmanager
+    def timed(self, name):
+        yield
+
+    def timings(self):
+        return {}
+
+    def synchronize(self):
+        pass
+
+    def check_eig(self):
+        assert self.pending == 0, "an eigendecomposition ticket was never waited on"
+
+    # ------------------------------------------------------------------ memory
+    def empty(self, rows, cols, split=False, ld=None):
+        return FMat(np.full((rows, cols), np.nan, dtype=F32), split)
+
+    def zeros(self, rows, cols):
+        return FMat(np.zeros((rows, cols), dtype=F32))
+
+    def upload_vector(self, arr, dtype):
+        dt = {"f32": np.float32, "f64": np.float64, "i32": np.int32}[dtype]
+        return np.array(arr, dtype=dt).reshape(-1)
+
+    def upload_index(self, idx):
+        return np.asarray(idx, dtype=np.int64).astype(np.int32)
+
+    def upload_matrix(self, host, col_start=0, col_stop=None, **kw):
+        host = np.asarray(host)
+        assert host.ndim == 2
+        self.h2d_bytes += host[:, col_start:col_stop].nbytes
+        return FMat(host[:, col_start:col_stop].astype(F32))
+
+    def download(self, t):
+        return np.array(t)
+
+    def download_matrix(self, m):
+        self.d2h_bytes += m.a.nbytes
+        return m.a.copy()
+
+    # ------------------------------------------------------------------ layout
+    def gather_rows_T_split(self, src, idx, n):
+        return FMat(src.a[np.asarray(idx[:n], dtype=np.int64)].T, split=True)
+
+    def gather_rows(self, src, idx, n, rows_out=None, split=False):
+        rows_out = n if rows_out is None else rows_out
+        out = np.zeros((rows_out, src.cols), dtype=F32)
+        out[:n] = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
+        return FMat(out, split)
+
+    def transpose(self, src, split=False):
+        return FMat(src.a.T, split)
+
+    def split(self, src):
+        return FMat(src.a.copy(), split=True)
+
+    def copy(self, src):
+        return FMat(src.a.copy(), src.is_split)
+
+    def axpy(self, a, x, y):
+        y.a += F32(a) * x.a
+
+    # ------------------------------------------------------------------ statistics
+    def col_stats(self, src, idx, n, ddof):
+        rows = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
+        r64 = rows.astype(np.float64)
+        mean = r64.mean(0)
+        var = ((r64 - mean) ** 2).sum(0) / (n - ddof) if n - ddof > 0 else np.full(src.cols, np.nan)
+        return mean.astype(F32), np.sqrt(var).astype(F32)
+
+    def gather_normalize(self, src, idx, n, mean, std, mode, eps, rows_out=None, split=False):
+        rows_out = n if rows_out is None else rows_out
+        rows = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
+        x = rows - mean[None, :].astype(F32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if mode == 0:
+                x = x * (F32(1) / (std + F32(eps)))[None, :]
+            elif mode == 1:
+                sc = np.where(std > 0, F32(1.0 / math.sqrt(n - 1)) / std, np.nan).astype(F32)
+                x = x * sc[None, :]
+        out = np.zeros((rows_out, src.cols), dtype=F32)
+        out[:n] = x
+        return FMat(out, split)
+
+    # ------------------------------------------------------------------ GEMMs
+    def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None):
+        assert A.is_split and B.is_split, "GEMM operands must be split pairs"
+        assert A.cols == B.cols
+        d = alpha * (A.a.astype(np.float64) @ B.a.astype(np.float64).T)
+        if Cin is not None:
+            d = d + beta * Cin.a.astype(np.float64)
+        self.launches += 1
+        self.gemm_flops += 2.0 * A.rows * B.rows * A.cols
+        return FMat(d.astype(F32), split_out)
+
+    def gemm_corr(self, A, B, n_groups, rows_per_group, Yz):
+        assert A.is_split and B.is_split
+        assert rows_per_group % self.TILE_N == 0 and B.rows == n_groups * rows_per_group
+        assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
+        acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][group*R + t]
+        tpg = rows_per_group // self.TILE_N
+        dot = np.zeros((n_groups * tpg, A.rows), dtype=F32)
+        ssq = np.zeros_like(dot)
+        for g in range(n_groups):
+            for t in range(tpg):
+                c0 = g * rows_per_group + t * self.TILE_N
+                blk = acc[:, c0:c0 + self.TILE_N].astype(np.float64)
+                yz = Yz.a[t * self.TILE_N:(t + 1) * self.TILE_N].astype(np.float64).T
+                dot[g * tpg + t] = (blk * yz).sum(1)
+                ssq[g * tpg + t] = (blk * blk).sum(1)
+        self.launches += 1
+        self.gemm_flops += 2.0 * A.rows * B.rows * A.cols
+        return {"dot": dot, "ssq": ssq, "n_tiles": n_groups * tpg}
+
+    # ------------------------------------------------------------------ eig
+    def syevd(self, G, lam=None):
+        a = G.a.astype(np.float64)
+        a = np.tril(a) + np.tril(a, -1).T  # cuSOLVER reads the lower triangle
+        w, v = np.linalg.eigh(a)
+        G.a[...] = v.T.astype(F32)
+        self.eig_calls += 1
+        return w.astype(F32)
+
+    def syevd_async(self, G):
+        self.pending += 1
+        snapshot = G.a.copy()
+        lam = self.syevd(G)
+        # emulate asynchrony: results become visible only after wait()
+        result = (G.a.copy(), lam.copy())
+        G.a[...] = np.nan
+        lam_out = np.full_like(lam, np.nan)
+        return lam_out, (G, lam_out, result, snapshot)
+
+    def wait(self, ticket):
+        G, lam_out, (vt, lam), _ = ticket
+        G.a[...] = vt
+        lam_out[...] = lam
+        self.pending -= 1
+
+    # ------------------------------------------------------------------ ridge kernels
+    @staticmethod
+    def _shrink(lam, alpha_scaled_sq, singcutoff):
+        keep = np.sqrt(np.maximum(lam, 0)) > singcutoff
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(keep, F32(1) / (lam + alpha_scaled_sq), F32(0)).astype(F32)
+
+    def build_alpha_stack(self, L, n_rows, rows_pad, lam, alphas_dev, n_alphas, normalpha, singcutoff):
+        s = math.sqrt(max(float(lam[-1]), 0.0)) if normalpha else 1.0
+        Lc = L.a[:n_rows] - L.a[:n_rows].astype(np.float64).mean(0).astype(F32)[None, :]
+        out = np.zeros((n_alphas * rows_pad, L.cols), dtype=F32)
+        for a in range(n_alphas):
+            an = float(alphas_dev[a]) * float(F32(s))
+            d = self._shrink(lam, F32(an * an), singcutoff)
+            out[a * rows_pad:a * rows_pad + n_rows] = Lc * d[None, :]
+        return FMat(out, split=True)
+
+    def scale_rows_by_alpha(self, Z, lam, alpha_v, normalpha, singcutoff):
+        s = F32(math.sqrt(max(float(lam[-1]), 0.0))) if normalpha else F32(1)
+        an = (alpha_v[:Z.rows].astype(F32) * s).astype(F32)
+        a2 = (an * an).astype(F32)
+        keep = np.sqrt(np.maximum(lam, 0)) > singcutoff
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = np.where(keep[None, :], Z.a / (lam[None, :] + a2[:, None]), F32(0))
+        return FMat(out.astype(F32), split=True)
+
+    def corr_finalize(self, parts, tiles_per_group, n_groups, n_vox, n_rows, eps, corr, accumulate, metric=0,
+                      resp_std=None):
+        for g in range(n_groups):
+            d = parts["dot"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
+            q = parts["ssq"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if metric == 0:
+                    c = (d / F32(n_rows)) / (np.sqrt(q / F32(n_rows - 1)) + F32(eps))
+                else:
+                    qvar = (resp_std * resp_std).astype(F32)
+                    resvar = (qvar * F32(n_rows - 1) - 2 * d + q) / F32(n_rows - 1)
+                    rsq = 1 - resvar / qvar
+                    c = np.sqrt(np.abs(rsq)) * np.sign(rsq)
+            c = np.nan_to_num(c.astype(F32))
+            corr.a[g] = corr.a[g] + c if accumulate else c
+
+    def argmax_alpha(self, corr_sum, n_folds, alphas_dev, want_sums):
+        mean = (corr_sum.a / F32(n_folds)).astype(F32)
+        best = np.argmax(mean, axis=0).astype(np.int32)
+        alpha_v = np.asarray(alphas_dev, dtype=F32)[best]
+        sums = mean.astype(np.float64).sum(1) if want_sums else None
+        return best, alpha_v, sums
+
+    # ------------------------------------------------------------------ test statistics
+    def pearson_finalize(self, parts, n_vox, n_samples, p_round_f32):
+        from scipy.special import betainc
+
+        d = parts["dot"].sum(0, dtype=F32)
+        q = parts["ssq"].sum(0, dtype=F32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            r = d / np.sqrt(q)
+        bad = np.isnan(r)
+        r = np.clip(np.where(bad, F32(0), r), -1, 1).astype(F32)
+        ab = n_samples / 2.0 - 1.0
+        p = np.minimum(2.0 * betainc(ab, ab, 0.5 * (1.0 - np.abs(r.astype(np.float64)))), 1.0) if n_samples >= 3 \
+            else np.ones(len(r))
+        p[np.abs(r) >= 1.0] = 0.0
+        if p_round_f32:
+            p = p.astype(F32).astype(np.float64)
+        p[bad] = 1.0
+        return r, p
+
+    def bh_fdr(self, p, n, alpha):
+        p = np.asarray(p[:n], dtype=np.float64)
+        key = np.where(np.isnan(p), np.inf, p)
+        order = np.lexsort((np.arange(n), key))
+        ps = key[order]
+        ecdf = np.arange(1, n + 1) / float(n)
+        rej_sorted = ps <= ecdf * alpha
+        kmax = np.max(np.nonzero(rej_sorted)[0]) if rej_sorted.any() else -1
+        adj_sorted = np.minimum(np.minimum.accumulate((ps / ecdf)[::-1])[::-1], 1.0)
+        reject = np.zeros(n, dtype=np.uint8)
+        padj = np.empty(n)
+        reject[order] = (np.arange(n) <= kmax).astype(np.uint8)
+        padj[order] = adj_sorted
+        return reject, padj, np.array([kmax + 1], dtype=np.int32)
+
+    def stack_vectors(self, vecs, n, dtype="f64"):
+        return np.stack([np.asarray(v[:n]) for v in vecs])
+
+    def fisher(self, p_stack, n_folds, n_vox, p_round_f32):
+        P = np.asarray(p_stack, dtype=np.float64)[:n_folds, :n_vox]
+        with np.errstate(divide="ignore"):
+            x = -np.log(P).sum(0)
+        term = np.ones_like(x)
+        s = np.ones_like(x)
+        with np.errstate(invalid="ignore", over="ignore"):
+            for j in range(1, n_folds):
+                term = term * x / j
+                s = s + term
+            out = np.minimum(np.exp(-x) * s, 1.0)
+        if p_round_f32:
+            out = out.astype(F32).astype(np.float64)
+        out[(P <= 0).any(0)] = 0.0
+        out[(P == 1.0).all(0)] = 1.0
+        return out
+
+    # ------------------------------------------------------------------ feature construction
+    def fir_make_delayed(self, stim, delays, circpad):
+        stim = np.asarray(stim)
+        nt, ndim = stim.shape
+        out = np.zeros((nt, ndim * len(delays)))
+        for i, d in enumerate(delays):
+            for t in range(nt):
+                ts = t - d
+                if 0 <= ts < nt:
+                    out[t, i * ndim:(i + 1) * ndim] = stim[ts]
+                elif circpad:
+                    src = ts % nt if abs(d) < nt else t
+                    out[t, i * ndim:(i + 1) * ndim] = stim[src]
+        return out
+
+    def lanczos_downsample(self, data, data_times, tr_times, window, cutoff, rectify, lo, hi):
+        data = np.asarray(data, dtype=np.float64)
+        n_tr = len(tr_times)
+        outs = []
+        parts = [np.clip(data, -np.inf, 0), np.clip(data, 0, np.inf)] if rectify else [data]
+        for part in parts:
+            out = np.zeros((n_tr, data.shape[1]))
+            for i in range(n_tr):
+                j0, j1 = (0, len(data_times)) if lo is None else (int(lo[i]), int(hi[i]))
+                t = (tr_times[i] - data_times[j0:j1]) * cutoff
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    w = window * np.sin(np.pi * t) * np.sin(np.pi * t / window) / (np.pi ** 2 * t ** 2)
+                w[t == 0] = 1.0
+                w[np.abs(t) > window] = 0.0
+                out[i] = w @ part[j0:j1]
+            outs.append(out)
+        return np.hstack(outs)
