@@ -47,9 +47,16 @@ enum lit_gemm_variant {
   LIT_GEMM_2CTA_N256 = 3  /* 256x256 tile per CTA pair, cta_group::2 */
 };
 
+/* The GEMMs are persistent kernels with one CTA per SM.  n_sms > 0 restricts their grids to that many
+ * SMs so that other work (the cuSOLVER eigendecompositions on a side stream) can run beside them;
+ * 0 restores the default (every SM).  Process-wide setting. */
+int lit_gemm_set_sm_limit(int n_sms);
+
 /* D[M,N] = alpha * A[M,K] * B[N,K]^T + beta * Cin[M,N]   (Cin may be NULL).
  * A and B are split pairs.  If D_lo is non-NULL the result is written as a split pair
- * (D = hi, D_lo = lo) so it can feed the next GEMM directly.
+ * (D = hi, D_lo = lo) so it can feed the next GEMM directly.  K is accumulated in chunks of 128
+ * inside the tensor core (whose fp32 accumulator truncates) and across chunks with round-to-nearest
+ * fp32 adds in registers, which keeps the result at fp32-FMA accuracy for any K.
  * Replaces torch.matmul at ridge_regression.py:32,59-61,104,105 and nested_cv.py:151,251
  * (after the Gram/eigen reformulation described in DESIGN.md). */
 int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,
@@ -58,9 +65,10 @@ int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const flo
 
 /* Prediction GEMM with the correlation reduction fused into the epilogue.
  *   acc[v, g*R + t] = sum_k A[v,k] * B[g*R + t, k]       v < M (voxels), g < n_groups, t < R
- *   dot_part[tile][v] = sum_{t in tile} acc * Yz[t][v]      ssq_part[tile][v] = sum_{t in tile} acc^2
+ *   dot_part[part][v] = sum_{t in part} acc * Yz[t][v]      ssq_part[part][v] = sum_{t in part} acc^2
  * with R = rows_per_group (multiple of 256; pad rows of B and Yz must be zero) and
- * tile = g*(R/256) + t/256.  Yz is [R][ldy] (time-major, voxel contiguous).
+ * part = g*(R/128) + t/128 (each epilogue thread reduces 128 consecutive time points, so the part
+ * arrays have n_groups * R / 128 rows of pitch ld_part).  Yz is [R][ldy] (time-major, voxel contiguous).
  * Replaces the per-alpha loop body of ridge_corr_torch (ridge_regression.py:115-125) and the
  * outer-test prediction + per-voxel Pearson loop (nested_cv.py:151,251,418-438). */
 int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo,
@@ -150,7 +158,7 @@ int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, lon
  *             (Yz z-scored with the unbiased std + eps)
  *   metric 1: signed sqrt of R^2 = 1 - var(Q - pred)/var(Q) (Yz centred only; resp_std = unbiased std of Q)
  * accumulate != 0 adds into corr (fold sum for nested_cv.py:391-393). */
-int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group, int n_groups,
+int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group, int n_groups,
                       long n_vox, long n_rows, float eps, int accumulate, int metric, const float* resp_std,
                       float* corr, long ld_corr, void* stream);
 /* best[v] = first argmax_a mean[a][v], mean = corr_sum / n_folds (nested_cv.py:391-393,408-411);
@@ -166,7 +174,7 @@ int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_v
  * NaN -> r = 0, p = 1; p = two-sided Student-t / Beta(n/2-1, n/2-1) p-value of r with n samples,
  * evaluated in fp64; if p_round_f32 != 0 it is rounded through fp32 (SciPy >= 1.14 keeps the
  * input dtype, so the reference run in this image produces fp32 p-values). */
-int lit_pearson_finalize(const float* dot_part, const float* ssq_part, long ld_part, int n_tiles, long n_vox,
+int lit_pearson_finalize(const float* dot_part, const float* ssq_part, long ld_part, int n_parts, long n_vox,
                          long n_samples, int p_round_f32, float* r, double* p, void* stream);
 /* Benjamini-Hochberg: reject[v] (uint8), p_adj[v], *count_out (device int).  Scratch: see
  * lit_bh_workspace.  Sorting is a hand-written bitonic network (keys padded to a power of two). */

@@ -21,6 +21,7 @@ PROTOTYPES = {
     "lit_last_error": [],
     "lit_abi_version": [],
     "lit_device_info": [_pi, _pi, _pi, _psz, _psz],
+    "lit_gemm_set_sm_limit": [_i],
     "lit_gemm_tf32x3_nt": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _f, _vp, _l, _f, _vp, _vp, _l, _i, _vp],
     "lit_gemm_tf32x3_nt_corr": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _vp, _l, _vp, _vp, _l, _i, _vp],
     "lit_convert_f64_to_f32": [_vp, _vp, _sz, _vp],

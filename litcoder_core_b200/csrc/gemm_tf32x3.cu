@@ -8,21 +8,31 @@
 // the torch.matmul / torch.linalg.svd call sites of the reference
 // (encoding/models/ridge_regression.py:32,59-61,104-105,120; nested_cv.py:151,251).
 //
-// Precision: operands arrive as two fp32 planes hi = rna_tf32(x), lo = rna_tf32(x - hi)
+// Precision.  Operands arrive as two fp32 planes hi = rna_tf32(x), lo = rna_tf32(x - hi)
 // (both exactly representable in TF32), and each k-step issues three kind::tf32 MMAs
 //   lo*hi + hi*lo + hi*hi
-// into the same fp32 TMEM accumulator, which recovers ~fp32 accuracy (error ~2^-21).
+// into the same fp32 TMEM accumulator.  The products are then exact to ~2^-22, but the
+// tensor core's fp32 accumulator TRUNCATES on every accumulation (measured on B200:
+// relative bias -6e-9 * K, i.e. -2e-5 at K = 3072, 20x the error of an fp32 FMA chain;
+// profiles/r1_gemm_accuracy.md).  The kernel therefore accumulates only a short K chunk
+// (kc_blocks * 32 values of K, 128 by default) inside TMEM and sums the chunks in
+// registers with round-to-nearest fp32 adds -- the accumulate-outside-the-tensor-core
+// scheme of Ootomo & Yokota, mapped onto TMEM double buffering: while the tensor core
+// fills one 128 x BN accumulator buffer, the epilogue warps drain the other one.
 //
-// Kernel structure (persistent, warp-specialised, one CTA or one CTA pair per SM):
-//   warp 0   : TMA producer  (4 tiled loads per k-block: A_hi, A_lo, B_hi, B_lo; SWIZZLE_128B)
-//   warp 1   : MMA issuer    (one thread issues tcgen05.mma; commits free the smem stage)
-//   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      (tcgen05.ld from a double-buffered accumulator)
+// Kernel structure (persistent, warp-specialised, one CTA or one CTA pair per SM, 384 threads):
+//   warp 0    : TMA producer  (4 tiled loads per k-block: A_hi, A_lo, B_hi, B_lo; SWIZZLE_128B)
+//   warp 1    : MMA issuer    (one thread issues tcgen05.mma; commits free the smem stage and
+//                              publish a finished K chunk)
+//   warp 2    : TMEM allocator
+//   warps 4-11: accumulate + epilogue.  Warp w owns TMEM lanes 32*(w%4).. and the column half
+//               (w-4)/4 of the tile: 128 x BN fp32 running sums live in registers
+//               (BN/2 per thread; setmaxnreg moves registers from warps 0-3 to these warps).
 // Two epilogues:
 //   EPI_STORE : D = alpha*acc + beta*Cin, optionally written as a (hi, lo) TF32 split pair
 //   EPI_CORR  : fused column reduction for per-voxel correlation.  Accumulator rows are
 //               voxels, columns are (alpha group, time) pairs; each thread reduces its row
-//               against the z-scored responses Yz[t][v] and emits per-tile partial sums
+//               against the z-scored responses Yz[t][v] and emits per-half-tile partial sums
 //               sum(pred*yz) and sum(pred^2).  Predictions never reach HBM
 //               (the reference materialises them per alpha: ridge_regression.py:120-125).
 #include "common.cuh"
@@ -30,6 +40,7 @@
 #include "../../include/litridge.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace lit {
@@ -41,7 +52,8 @@ struct GemmParams {
   int num_m_tiles;  // in units of BM*CG rows
   int num_n_tiles;
   int num_k_blocks;
-  int group_m;  // rasterisation group (tiles along M that share a B tile wave)
+  int kc_blocks;  // k-blocks accumulated inside TMEM before the chunk is drained into registers
+  int group_m;    // rasterisation group (tiles along M that share a B tile wave)
   // EPI_STORE
   float* D;
   float* D_lo;  // optional: when non-null D receives hi and D_lo receives lo
@@ -50,10 +62,10 @@ struct GemmParams {
   long ldc;
   float alpha, beta;
   // EPI_CORR
-  const float* Yz;  // [tiles_per_group*BN rows][>= M cols], row pitch ldy
+  const float* Yz;  // [parts_per_group*BN/2 rows][>= M cols], row pitch ldy
   long ldy;
-  int tiles_per_group;
-  float* dot_part;  // [num_n_tiles][ld_part]
+  int tiles_per_group;  // N tiles (of BN columns) per alpha group
+  float* dot_part;      // [2*num_n_tiles][ld_part]
   float* ssq_part;
   long ld_part;
 };
@@ -72,11 +84,14 @@ struct GemmShape {
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // tiles; barriers + alignment slack live in the rest
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered chunk accumulator
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 128 + EPI_WARPS * 32;
+  static constexpr int COLS = BN / 2;  // accumulator columns owned by one epilogue thread
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM cols pow2");
-  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+  static_assert(BN % 64 == 0 && BN <= 256, "BN");
 };
 
 __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& mt, int& nt) {
@@ -90,7 +105,7 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
 }
 
 template <int BN, int CG, int EPI>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(GemmShape<BN, CG>::THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const GemmParams p) {
@@ -122,7 +137,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], CG * 4);  // one arrive per epilogue warp of every CTA
+      ptx::mbar_init(&tmem_empty_bar[a], CG * S::EPI_WARPS);  // one arrive per epilogue warp of every CTA
     }
     ptx::fence_mbar_init();
   }
@@ -136,151 +151,183 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
+  const int num_chunks = (p.num_k_blocks + p.kc_blocks - 1) / p.kc_blocks;
 
-  if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
-        int mt, nt;
-        tile_coords(p, tile, mt, nt);
-        const int m_row = (mt * CG + (int)cta_rank) * S::BM;
-        const int n_row = nt * BN + (int)cta_rank * S::B_ROWS;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * S::STAGE_BYTES;
-          const int k0 = kb * S::BK;
-          if constexpr (CG == 1) {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-            ptx::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m_row);
-            ptx::tma_load_2d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
-            ptx::tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
-            ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
-          } else {
-            // Both CTAs load their halves; all bytes are accounted on the leader's barrier.
-            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
-            ptx::tma_load_2d_2sm(st, &tmAh, &full_bar[stage], k0, m_row);
-            ptx::tma_load_2d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
-            ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
-            ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
-          }
-          if (++stage == S::STAGES) {
-            stage = 0;
-            phase ^= 1;
+  if (warp < 4) {
+    // The data-movement / issue warps need few registers; hand the rest to the accumulating warps.
+    ptx::setmaxnreg_dec<40>();
+    if (warp == 0) {
+      // ======================= TMA producer =======================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+          int mt, nt;
+          tile_coords(p, tile, mt, nt);
+          const int m_row = (mt * CG + (int)cta_rank) * S::BM;
+          const int n_row = nt * BN + (int)cta_rank * S::B_ROWS;
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * S::STAGE_BYTES;
+            const int k0 = kb * S::BK;
+            if constexpr (CG == 1) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+              ptx::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m_row);
+              ptx::tma_load_2d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
+              ptx::tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
+              ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+            } else {
+              // Both CTAs load their halves; all bytes are accounted on the leader's barrier.
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+              ptx::tma_load_2d_2sm(st, &tmAh, &full_bar[stage], k0, m_row);
+              ptx::tma_load_2d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
+              ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
+              ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+            }
+            if (++stage == S::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_tf32(S::BM * CG, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t st = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t a_hi = st, a_lo = st + S::A_BYTES;
-          const uint32_t b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
+    } else if (warp == 1) {
+      // ======================= MMA issuer =======================
+      if (lane == 0 && cta_rank == 0) {
+        constexpr uint32_t idesc = ptx::umma_idesc_tf32(S::BM * CG, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t cc = 0;  // running chunk counter: TMEM buffer = cc & 1
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+          for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += p.kc_blocks, ++cc) {
+            const uint32_t buf = cc & 1u;
+            ptx::mbar_wait(&tmem_empty_bar[buf], ((cc >> 1) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BN;
+            const int kb1 = min(kb0 + p.kc_blocks, p.num_k_blocks);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              const uint32_t st = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
+              const uint32_t a_hi = st, a_lo = st + S::A_BYTES;
+              const uint32_t b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < S::BK / S::UMMA_K; ++ks) {
-            const uint32_t koff = ks * S::UMMA_K * 4;  // bytes along K inside the swizzle span
-            const uint64_t dah = ptx::umma_desc_k_sw128(a_hi + koff);
-            const uint64_t dal = ptx::umma_desc_k_sw128(a_lo + koff);
-            const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + koff);
-            const uint64_t dbl = ptx::umma_desc_k_sw128(b_lo + koff);
-            ptx::umma_tf32<CG>(d_tmem, dal, dbh, idesc, (kb | ks) != 0);
-            ptx::umma_tf32<CG>(d_tmem, dah, dbl, idesc, 1u);
-            ptx::umma_tf32<CG>(d_tmem, dah, dbh, idesc, 1u);
-          }
-          if constexpr (CG == 1)
-            ptx::umma_commit(&empty_bar[stage]);
-          else
-            ptx::umma_commit_2sm_mc(&empty_bar[stage], 0b11);
-          if (++stage == S::STAGES) {
-            stage = 0;
-            phase ^= 1;
+              for (int ks = 0; ks < S::BK / S::UMMA_K; ++ks) {
+                const uint32_t koff = ks * S::UMMA_K * 4;  // bytes along K inside the swizzle span
+                const uint64_t dah = ptx::umma_desc_k_sw128(a_hi + koff);
+                const uint64_t dal = ptx::umma_desc_k_sw128(a_lo + koff);
+                const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + koff);
+                const uint64_t dbl = ptx::umma_desc_k_sw128(b_lo + koff);
+                ptx::umma_tf32<CG>(d_tmem, dal, dbh, idesc, (uint32_t)((kb != kb0) | (ks != 0)));
+                ptx::umma_tf32<CG>(d_tmem, dah, dbl, idesc, 1u);
+                ptx::umma_tf32<CG>(d_tmem, dah, dbh, idesc, 1u);
+              }
+              if constexpr (CG == 1)
+                ptx::umma_commit(&empty_bar[stage]);
+              else
+                ptx::umma_commit_2sm_mc(&empty_bar[stage], 0b11);
+              if (++stage == S::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+            if constexpr (CG == 1)
+              ptx::umma_commit(&tmem_full_bar[buf]);
+            else
+              ptx::umma_commit_2sm_mc(&tmem_full_bar[buf], 0b11);
           }
         }
-        if constexpr (CG == 1)
-          ptx::umma_commit(&tmem_full_bar[as]);
-        else
-          ptx::umma_commit_2sm_mc(&tmem_full_bar[as], 0b11);
       }
     }
-  } else if (warp >= 4) {
-    // ======================= epilogue =======================
-    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may access
-    int it = 0;
-    for (int tile = worker; tile < num_tiles; tile += num_workers, ++it) {
+  } else {
+    // ======================= accumulate + epilogue =======================
+    ptx::setmaxnreg_inc<216>();
+    const int ew = warp - 4;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = ew >> 2;   // column half of the tile owned by this warp
+    constexpr int COLS = S::COLS;
+    uint32_t cc = 0;
+    float acc[COLS];
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int mt, nt;
       tile_coords(p, tile, mt, nt);
-      const int as = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      ptx::mbar_wait(&tmem_full_bar[as], aph);
-      ptx::tc_fence_after();
-      const long row = (long)(mt * CG + (int)cta_rank) * S::BM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN;
-
-      if constexpr (EPI == EPI_STORE) {
-        for (int c = 0; c < BN / 32; ++c) {
-          const long n0 = (long)nt * BN + c * 32;
-          if (n0 >= p.N) break;  // warp-uniform
-          float v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
+      for (int c = 0; c < num_chunks; ++c, ++cc) {
+        const uint32_t buf = cc & 1u;
+        ptx::mbar_wait(&tmem_full_bar[buf], (cc >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + half * COLS;
+#pragma unroll
+        for (int j = 0; j < COLS / 64; ++j) {
+          float v0[32], v1[32];
+          ptx::tmem_ld_32x32(taddr + j * 64, v0);
+          ptx::tmem_ld_32x32(taddr + j * 64 + 32, v1);
           ptx::tmem_ld_wait();
-          if (row_ok) {
-            float* drow = p.D + row * p.ldd + n0;
-            float* lrow = p.D_lo ? p.D_lo + row * p.ldd + n0 : nullptr;
-            const float* crow = p.Cin ? p.Cin + row * p.ldc + n0 : nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float o[4];
-              if (n0 + j + 3 < p.N) {
-                if (crow) {
-                  const float4 cv = *reinterpret_cast<const float4*>(crow + j);
-                  o[0] = p.alpha * v[j] + p.beta * cv.x;
-                  o[1] = p.alpha * v[j + 1] + p.beta * cv.y;
-                  o[2] = p.alpha * v[j + 2] + p.beta * cv.z;
-                  o[3] = p.alpha * v[j + 3] + p.beta * cv.w;
-                } else {
+          for (int i = 0; i < 32; ++i) {
+            acc[j * 64 + i] += v0[i];  // round-to-nearest fp32 adds across K chunks
+            acc[j * 64 + 32 + i] += v1[i];
+          }
+        }
+        // Release this chunk buffer back to the MMA issuer (leader CTA).
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 1)
+            ptx::mbar_arrive(&tmem_empty_bar[buf]);
+          else
+            ptx::mbar_arrive_cluster(&tmem_empty_bar[buf], 0);
+        }
+      }
+
+      const long row = (long)(mt * CG + (int)cta_rank) * S::BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      if constexpr (EPI == EPI_STORE) {
+        const long n_base = (long)nt * BN + half * COLS;
+        if (row_ok) {
+          float* drow = p.D + row * p.ldd + n_base;
+          float* lrow = p.D_lo ? p.D_lo + row * p.ldd + n_base : nullptr;
+          const float* crow = p.Cin ? p.Cin + row * p.ldc + n_base : nullptr;
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) o[q] = p.alpha * v[j + q];
-                }
-                if (lrow) {
-                  float h[4], l[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    h[q] = ptx::to_tf32(o[q]);
-                    l[q] = ptx::to_tf32(o[q] - h[q]);
-                  }
-                  *reinterpret_cast<float4*>(drow + j) = make_float4(h[0], h[1], h[2], h[3]);
-                  *reinterpret_cast<float4*>(lrow + j) = make_float4(l[0], l[1], l[2], l[3]);
-                } else {
-                  *reinterpret_cast<float4*>(drow + j) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+          for (int j = 0; j < COLS; j += 4) {
+            if (n_base + j >= p.N) break;
+            float o[4];
+            if (n_base + j + 3 < p.N) {
+              if (crow) {
+                const float4 cv = *reinterpret_cast<const float4*>(crow + j);
+                o[0] = p.alpha * acc[j] + p.beta * cv.x;
+                o[1] = p.alpha * acc[j + 1] + p.beta * cv.y;
+                o[2] = p.alpha * acc[j + 2] + p.beta * cv.z;
+                o[3] = p.alpha * acc[j + 3] + p.beta * cv.w;
               } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o[q] = p.alpha * acc[j + q];
+              }
+              if (lrow) {
+                float h[4], l[4];
+#pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  if (n0 + j + q < p.N) {
-                    float x = p.alpha * v[j + q];
-                    if (crow) x += p.beta * crow[j + q];
-                    if (lrow) {
-                      const float h = ptx::to_tf32(x);
-                      drow[j + q] = h;
-                      lrow[j + q] = ptx::to_tf32(x - h);
-                    } else {
-                      drow[j + q] = x;
-                    }
+                  h[q] = ptx::to_tf32(o[q]);
+                  l[q] = ptx::to_tf32(o[q] - h[q]);
+                }
+                *reinterpret_cast<float4*>(drow + j) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(lrow + j) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
+                *reinterpret_cast<float4*>(drow + j) = make_float4(o[0], o[1], o[2], o[3]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (n_base + j + q < p.N) {
+                  float x = p.alpha * acc[j + q];
+                  if (crow) x += p.beta * crow[j + q];
+                  if (lrow) {
+                    const float h = ptx::to_tf32(x);
+                    drow[j + q] = h;
+                    lrow[j + q] = ptx::to_tf32(x - h);
+                  } else {
+                    drow[j + q] = x;
                   }
                 }
               }
@@ -289,40 +336,25 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
       } else {
         // Fused per-voxel reduction: rows = voxels, columns = time points of one alpha group.
-        float dot = 0.f, ssq = 0.f;
-        const long t_base = (long)(nt % p.tiles_per_group) * BN;
-        const float* ycol = p.Yz + (row_ok ? row : 0);
-        for (int c = 0; c < BN / 32; ++c) {
-          float v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
-          float y[32];
-          if (row_ok) {
-            const float* yp = ycol + (t_base + c * 32) * p.ldy;
+        if (row_ok) {
+          float dot = 0.f, ssq = 0.f;
+          const long t_base = (long)(nt % p.tiles_per_group) * BN + half * COLS;
+          const float* ycol = p.Yz + row + t_base * p.ldy;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = __ldg(yp + (long)j * p.ldy);
-          }
-          ptx::tmem_ld_wait();
-          if (row_ok) {
+          for (int j = 0; j < COLS; j += 32) {
+            float y[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              dot = fmaf(v[j], y[j], dot);
-              ssq = fmaf(v[j], v[j], ssq);
+            for (int i = 0; i < 32; ++i) y[i] = __ldg(ycol + (long)(j + i) * p.ldy);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              dot = fmaf(acc[j + i], y[i], dot);
+              ssq = fmaf(acc[j + i], acc[j + i], ssq);
             }
           }
+          const long part = (long)nt * 2 + half;
+          p.dot_part[part * p.ld_part + row] = dot;
+          p.ssq_part[part * p.ld_part + row] = ssq;
         }
-        if (row_ok) {
-          p.dot_part[(long)nt * p.ld_part + row] = dot;
-          p.ssq_part[(long)nt * p.ld_part + row] = ssq;
-        }
-      }
-      // Release this accumulator buffer back to the MMA issuer (leader CTA).
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 1)
-          ptx::mbar_arrive(&tmem_empty_bar[as]);
-        else
-          ptx::mbar_arrive_cluster(&tmem_empty_bar[as], 0);
       }
     }
   }
@@ -379,6 +411,20 @@ static int make_operand_map(CUtensorMap* tm, const float* base, long rows, long 
   return LIT_OK;
 }
 
+// K chunk (in 32-wide k-blocks) accumulated inside TMEM between register drains.  4 (K = 128) keeps the
+// truncation bias of the tensor-core accumulator below fp32 rounding noise; LIT_GEMM_KC_BLOCKS overrides it
+// (development knob: a huge value reproduces plain in-TMEM accumulation).
+static int kc_blocks_default() {
+  static int v = [] {
+    const char* e = getenv("LIT_GEMM_KC_BLOCKS");
+    int x = e ? atoi(e) : 4;
+    return x > 0 ? x : 4;
+  }();
+  return v;
+}
+
+static int g_sm_limit = 0;  // 0 = use every SM
+
 template <int BN, int CG, int EPI>
 static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,
                        GemmParams p, cudaStream_t stream) {
@@ -395,6 +441,7 @@ static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const flo
   p.num_k_blocks = (p.K + S::BK - 1) / S::BK;
   if (p.num_k_blocks < 1) p.num_k_blocks = 1;  // K == 0 still zero-initialises the accumulator via OOB fill
   if (p.group_m <= 0) p.group_m = 16 / CG;
+  if (p.kc_blocks <= 0) p.kc_blocks = kc_blocks_default();
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return LIT_OK;
 
@@ -404,11 +451,14 @@ static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const flo
     LIT_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
     attr_set = true;
   }
-  int workers = sm_count() / CG;
+  int sms = sm_count();
+  if (g_sm_limit > 0 && g_sm_limit < sms) sms = g_sm_limit;
+  int workers = sms / CG;
+  if (workers < 1) workers = 1;
   if (workers > tiles) workers = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(workers * CG);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(S::THREADS);
   cfg.dynamicSmemBytes = S::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -425,6 +475,12 @@ static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const flo
 }  // namespace lit
 
 using namespace lit;
+
+extern "C" int lit_gemm_set_sm_limit(int n_sms) {
+  LIT_REQUIRE(n_sms >= 0, "gemm_set_sm_limit: negative SM count");
+  g_sm_limit = n_sms;
+  return LIT_OK;
+}
 
 extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
                                   const float* B_lo, long ldb, int M, int N, int K, float alpha, const float* Cin,
@@ -447,8 +503,10 @@ extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda
   p.alpha = alpha;
   p.beta = beta;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // AUTO: the CTA-pair kernel (256 x 256 tile, B halves shared through the pair) is ~10 % faster
+  // whenever there is more than one 128-row block of A to pair up.
+  if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
   switch (variant) {
-    case LIT_GEMM_AUTO:
     case LIT_GEMM_1CTA_N256:
       return launch_gemm<256, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     case LIT_GEMM_1CTA_N128:
@@ -481,8 +539,8 @@ extern "C" int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, lon
   p.ssq_part = ssq_part;
   p.ld_part = ld_part;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
   switch (variant) {
-    case LIT_GEMM_AUTO:
     case LIT_GEMM_1CTA_N256:
       return launch_gemm<256, 1, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     case LIT_GEMM_2CTA_N256:

@@ -223,6 +223,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Warpgroup-wide register re-allocation (all 4 warps of an aligned warpgroup must execute it).
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // Round-to-nearest fp32 -> tf32 (result is an fp32 bit pattern with 13 zero low bits).
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;

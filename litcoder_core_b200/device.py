@@ -13,6 +13,8 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import queue
+import threading
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -57,8 +59,45 @@ class Partials:
         self.dot, self.ssq, self.n_tiles, self.ld = dot, ssq, n_tiles, ld
 
 
+class _EigTicket:
+    __slots__ = ("issued", "done", "error")
+
+    def __init__(self):
+        self.issued = threading.Event()  # set once the worker has issued the call and recorded `done`
+        self.done = None  # CUDA event on the side stream
+        self.error = None
+
+
+class _EigWorker(threading.Thread):
+    """Issues the (host-blocking) cuSOLVER calls on the side stream, in submission order."""
+
+    def __init__(self, ops: "DeviceOps"):
+        super().__init__(name="litridge-eig", daemon=True)
+        self.ops = ops
+        self.jobs: "queue.Queue" = queue.Queue()
+
+    def run(self):
+        ops, t = self.ops, self.ops.torch
+        t.cuda.set_device(ops.device)
+        while True:
+            job = self.jobs.get()
+            if job is None:
+                return
+            G, lam, ready, ticket = job
+            try:
+                with t.cuda.stream(ops._side):
+                    ops._side.wait_event(ready)
+                    ops.syevd(G, lam=lam)
+                    ticket.done = t.cuda.Event()
+                    ticket.done.record()
+            except BaseException as e:  # surfaced by wait()
+                ticket.error = e
+            ticket.issued.set()
+
+
 class DeviceOps:
-    TILE_N = 256  # accumulator columns per tile of the fused-correlation GEMM
+    TILE_N = 256  # accumulator columns per tile of the fused-correlation GEMM (row padding of the stacked design)
+    PART_N = 128  # columns reduced into one partial sum by the fused epilogue (half a tile)
 
     def __init__(self, device_index: Optional[int] = None, gemm_variant: int = _lib.GEMM_AUTO):
         import torch
@@ -79,6 +118,7 @@ class DeviceOps:
         self._eig_ws: Dict[Tuple[int, int], tuple] = {}
         self._bh_ws = None
         self._side = None  # side stream for the eigendecompositions
+        self._eig_worker = None
         self._eig_infos: List[object] = []
 
     # ------------------------------------------------------------------ bookkeeping
@@ -87,6 +127,8 @@ class DeviceOps:
         self.gemm_flops = 0.0  # algorithmic 2*M*N*K of the executed GEMMs (x3 tensor-core MMAs each)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.corr_flops = 0.0  # of which: the fused prediction + correlation GEMM (the dominant kernel)
+        self.corr_launches = 0
         self._timed: Dict[str, List[tuple]] = {}
 
     @property
@@ -290,6 +332,10 @@ class DeviceOps:
         return out
 
     # ------------------------------------------------------------------ GEMMs
+    def set_gemm_sm_limit(self, n_sms: int) -> None:
+        """Restrict the persistent GEMM grids to n_sms SMs (0 = all); see lit_gemm_set_sm_limit."""
+        check(self.lib.lit_gemm_set_sm_limit(int(n_sms)), "gemm_set_sm_limit")
+
     def gemm(self, A: Mat, B: Mat, alpha: float = 1.0, Cin: Optional[Mat] = None, beta: float = 0.0,
              split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None) -> Mat:
         """out[M,N] = alpha * A[M,K] @ B[N,K]^T + beta * Cin (A, B split pairs)."""
@@ -300,14 +346,18 @@ class DeviceOps:
         M, N, K = A.rows, B.rows, A.cols
         if out is None:
             out = self.empty(M, N, split=split_out, ld=ld_out)
+        with self.timed("gemm"):
+            self._gemm_call(A, B, M, N, K, alpha, Cin, beta, out)
+        self.launches += 1
+        self.gemm_flops += 2.0 * M * N * K
+        return out
+
+    def _gemm_call(self, A, B, M, N, K, alpha, Cin, beta, out):
         check(self.lib.lit_gemm_tf32x3_nt(
             _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M, N, K,
             alpha, _vp(Cin.hi.data_ptr() if Cin is not None else 0), Cin.ld if Cin is not None else 0, beta,
             _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr() if out.is_split else 0), out.ld, self.gemm_variant,
             _vp(self.stream)), "gemm_tf32x3_nt")
-        self.launches += 1
-        self.gemm_flops += 2.0 * M * N * K
-        return out
 
     def gemm_corr(self, A: Mat, B: Mat, n_groups: int, rows_per_group: int, Yz: Mat) -> Partials:
         """Fused prediction + per-voxel reduction (see lit_gemm_tf32x3_nt_corr)."""
@@ -316,19 +366,22 @@ class DeviceOps:
         if Yz.cols != A.rows or A.cols != B.cols:
             raise ValueError("gemm_corr: shape mismatch")
         M, K = A.rows, A.cols
-        n_tiles = n_groups * rows_per_group // self.TILE_N
+        n_tiles = n_groups * rows_per_group // self.PART_N
         ld = round_up(M, 32)
         t = self.torch
         dot = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
         ssq = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
         variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256, _lib.GEMM_2CTA_N256) \
             else _lib.GEMM_AUTO
-        check(self.lib.lit_gemm_tf32x3_nt_corr(
-            _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
-            n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
-            variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
+        with self.timed("gemm_corr"):
+            check(self.lib.lit_gemm_tf32x3_nt_corr(
+                _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
+                n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()),
+                ld, variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
         self.launches += 1
         self.gemm_flops += 2.0 * M * (n_groups * rows_per_group) * K
+        self.corr_flops += 2.0 * M * (n_groups * rows_per_group) * K
+        self.corr_launches += 1
         return Partials(dot, ssq, n_tiles, ld)
 
     # ------------------------------------------------------------------ eigendecomposition
@@ -363,23 +416,36 @@ class DeviceOps:
             raise _lib.LitRidgeError(f"cuSOLVER syevd did not converge (info = {bad})")
 
     def syevd_async(self, G: Mat):
-        """Queue syevd(G) on the side stream behind everything already queued on the current stream.
-        Returns (lam, ticket); G and lam may be read on the current stream after wait(ticket)."""
+        """Queue syevd(G) behind everything already queued on the current stream, to run on the side
+        stream.  Returns (lam, ticket); G and lam may be read on the current stream after wait(ticket).
+
+        cuSOLVER's syevd blocks its calling host thread for the whole decomposition (measured: host call
+        42.7 ms of 45.0 ms device time at n = 3072), so the calls are issued by a worker thread; the
+        caller keeps feeding the main stream meanwhile."""
         t = self.torch
-        if self._side is None:
+        if self._eig_worker is None:
             self._side = t.cuda.Stream(device=self.device)
+            self._eig_worker = _EigWorker(self)
+            self._eig_worker.start()
         lam = self.vec(G.rows)
         ready = t.cuda.Event()
         ready.record()
-        self._side.wait_event(ready)
-        with t.cuda.stream(self._side):
-            self.syevd(G, lam=lam)
-            done = t.cuda.Event()
-            done.record()
-        return lam, done
+        ticket = _EigTicket()
+        self._eig_worker.jobs.put((G, lam, ready, ticket))
+        return lam, ticket
 
     def wait(self, ticket) -> None:
-        self.torch.cuda.current_stream(self.device).wait_event(ticket)
+        """Make the current stream wait for an eigendecomposition queued with syevd_async."""
+        ticket.issued.wait()
+        if ticket.error is not None:
+            raise ticket.error
+        self.torch.cuda.current_stream(self.device).wait_event(ticket.done)
+
+    def close(self) -> None:
+        if self._eig_worker is not None:
+            self._eig_worker.jobs.put(None)
+            self._eig_worker.join(timeout=10)
+            self._eig_worker = None
 
     # ------------------------------------------------------------------ ridge kernels
     def build_alpha_stack(self, L: Mat, n_rows: int, rows_pad: int, lam, alphas_dev, n_alphas: int, normalpha: bool,

@@ -182,7 +182,7 @@ class RidgeCVEngine:
             mean, std = ops.col_stats(Y, va_dev, n_va, ddof=1)
             Yz = ops.gather_normalize(Y, va_dev, n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
             parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz)
-            ops.corr_finalize(parts, rows_pad // ops.TILE_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
+            ops.corr_finalize(parts, rows_pad // ops.PART_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
                               accumulate=(i > 0), metric=metric, resp_std=std)
             del Zt, Lst, Yz, parts
             d["G"] = d["XRt"] = d["XtT"] = None
@@ -224,23 +224,16 @@ class RidgeCVEngine:
         r, p = ops.pearson_finalize(parts, Wt.rows, n_te, cfg.p_round_f32)
         return Wt, r, p
 
-    def _normalised(self, X, Y, Xte_src, Yte_src, train_rows, cfg: RidgeConfig, same_source: bool):
-        """DataNormalizer (ridge_utils.py:70-180): z-score with the training rows' statistics."""
+    def _normalised(self, M, Mte_src, train_rows, enabled: bool, same_source: bool):
+        """DataNormalizer (ridge_utils.py:70-180): z-score a matrix (and its test source) with the
+        training rows' statistics (unbiased std, eps added to the std)."""
+        if not enabled:
+            return M, Mte_src
         ops = self.ops
-        if not (cfg.normalize_features or cfg.normalize_targets):
-            return X, Y, Xte_src, Yte_src
-        tr_dev = ops.upload_index(train_rows)
-        n = len(train_rows)
-        Xn, Yn, Xtn, Ytn = X, Y, Xte_src, Yte_src
-        if cfg.normalize_features:
-            m, s = ops.col_stats(X, tr_dev, n, ddof=1)
-            Xn = ops.gather_normalize(X, None, X.rows, m, s, 0, EPS)
-            Xtn = Xn if same_source else ops.gather_normalize(Xte_src, None, Xte_src.rows, m, s, 0, EPS)
-        if cfg.normalize_targets:
-            m, s = ops.col_stats(Y, tr_dev, n, ddof=1)
-            Yn = ops.gather_normalize(Y, None, Y.rows, m, s, 0, EPS)
-            Ytn = Yn if same_source else ops.gather_normalize(Yte_src, None, Yte_src.rows, m, s, 0, EPS)
-        return Xn, Yn, Xtn, Ytn
+        m, s = ops.col_stats(M, ops.upload_index(train_rows), len(train_rows), ddof=1)
+        Mn = ops.gather_normalize(M, None, M.rows, m, s, 0, EPS)
+        Mtn = Mn if same_source else ops.gather_normalize(Mte_src, None, Mte_src.rows, m, s, 0, EPS)
+        return Mn, Mtn
 
     # ------------------------------------------------------------------------------------------
     # drivers
@@ -259,15 +252,21 @@ class RidgeCVEngine:
         res = ShardResult()
         same_source = X_test is None
         inv = 1.0 / len(plans)
+        # Design side of EVERY outer fold first: Grams are cheap and depend on X only, and queueing all the
+        # eigendecompositions now lets the side stream run ahead of the response-side GEMMs.
+        Xte_src, Yte_src = (X, Y) if same_source else (X_test, Y_test)
+        prepared = []
         for plan in plans:
-            Xs, Ys, Xts, Yts = self._normalised(X, Y, X if same_source else X_test, Y if same_source else Y_test,
-                                                plan.train_rows, cfg, same_source)
-            outer, inners = self._design_side(Xs, plan, cfg)
+            Xs, Xts = self._normalised(X, Xte_src, plan.train_rows, cfg.normalize_features, same_source)
+            prepared.append((Xs, Xts) + self._design_side(Xs, plan, cfg))
+        for plan in plans:
+            Xs, Xts, outer, inners = prepared.pop(0)
+            Ys, Yts = self._normalised(Y, Yte_src, plan.train_rows, cfg.normalize_targets, same_source)
             corr_sum, Ct_o = self._inner_scores(Xs, Ys, plan, outer, inners, alphas_f64, len(alphas), cfg)
             alpha_v = self._select_alphas(corr_sum, len(plan.inner), alphas_f32, cfg, n_vox_total)
             del corr_sum, inners
             Wt, r, p = self._outer_fit_and_score(Xts, Yts, plan, outer, Ct_o, alpha_v, cfg)
-            del outer, Ct_o
+            del outer, Ct_o, Xs, Xts, Ys, Yts
             if len(plans) == 1:
                 res.Wt_mean = Wt
             else:

@@ -36,6 +36,7 @@ class FMat:
 
 class FakeOps:
     TILE_N = 256
+    PART_N = 128
 
     def __init__(self):
         self.reset_counters()
@@ -148,14 +149,14 @@ class FakeOps:
         assert rows_per_group % self.TILE_N == 0 and B.rows == n_groups * rows_per_group
         assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
         acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][group*R + t]
-        tpg = rows_per_group // self.TILE_N
+        tpg = rows_per_group // self.PART_N
         dot = np.zeros((n_groups * tpg, A.rows), dtype=F32)
         ssq = np.zeros_like(dot)
         for g in range(n_groups):
             for t in range(tpg):
-                c0 = g * rows_per_group + t * self.TILE_N
-                blk = acc[:, c0:c0 + self.TILE_N].astype(np.float64)
-                yz = Yz.a[t * self.TILE_N:(t + 1) * self.TILE_N].astype(np.float64).T
+                c0 = g * rows_per_group + t * self.PART_N
+                blk = acc[:, c0:c0 + self.PART_N].astype(np.float64)
+                yz = Yz.a[t * self.PART_N:(t + 1) * self.PART_N].astype(np.float64).T
                 dot[g * tpg + t] = (blk * yz).sum(1)
                 ssq[g * tpg + t] = (blk * blk).sum(1)
         self.launches += 1
