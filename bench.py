@@ -1,0 +1,365 @@
+"""Benchmark of the nested-CV ridge hot path (BASELINE.json: "nested-CV ridge fit s & voxel*alpha*fold/s
+(95k vox, 3072 feat) @1/2/4/8 B200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one full nested-CV ridge fit (5 x 5 chunked folds, 20 alphas, per-voxel alpha) of the
+BASELINE config-2 problem: 9,400 TRs x 3,072 delayed features x 95,000 voxels, synthetic data.
+With N GPUs the SAME problem is split over voxels (strong scaling): each rank holds X and its
+column block of Y; ranks exchange only per-voxel result vectors.
+
+Legs (rank 0 prints ONE JSON line):
+  value   fits with X and Y already resident in HBM, weights left on the device; K steps bracketed by
+          barrier + synchronize, CUDA events on the launching stream, max over ranks.
+  e2e     the same fits through the public API with HOST (pinned) float32 arrays: H2D of X and the
+          rank's Y block, D2H of weights and per-voxel vectors inside the timed region.
+  roofline     the fused prediction+correlation GEMM (dominant kernel), timed per launch with CUDA events.
+  cpu_baseline the CPU oracle (NumPy port of the reference's algorithm) on a bounded sample, N = 1 only.
+--impl reference times that CPU port alone (rank 0; the other ranks exit) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (TRs, features, voxels, alphas, outer folds, inner folds, chunk length)
+    "config2_gpt2_9400x3072x95000": (9400, 3072, 95000, 20, 5, 5, 20),
+    "config1_wordrate_9400x4x95000": (9400, 4, 95000, 20, 5, 5, 20),
+    "config4_narratives_2226x3072x81924": (2226, 3072, 81924, 20, 5, 5, 20),
+    "dev_small_2000x256x4096": (2000, 256, 4096, 20, 5, 5, 20),
+}
+METRIC = "nested_cv_ridge_voxel_alpha_folds_per_s"
+UNIT = "voxel*alpha*fold/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, as in /opt/skills/guides/B200_PROFILING.md)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms",
+                 "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [x.strip() for x in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, w in zip(sm, power) if w > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle leg (cpu_baseline and --impl reference)
+# ----------------------------------------------------------------------------------------------
+def oracle_sample(workload: str, sample_voxels: int, seed: int = 0):
+    """One outer fold of the workload (5 inner folds + final fit + test scoring, i.e. the reference's
+    train/test mode, nested_cv.py:105-171) on `sample_voxels` voxels with the NumPy oracle, all host
+    threads.  The SVDs do not depend on the number of voxels, everything else is linear in it, so the
+    full-fit time is extrapolated as  Ko * (t_svd + t_rest * V / V_sample)  and reported as such."""
+    from oracle import ridge_oracle as O
+
+    N, p, V, A, Ko, Ki, chunk = WORKLOADS[workload]
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Vs = min(sample_voxels, V)
+    Y = (X[:, : min(p, 64)] @ rng.standard_normal((min(p, 64), Vs)).astype(np.float32) * 0.1
+         + rng.standard_normal((N, Vs)).astype(np.float32))
+    n_test = (N // chunk // Ko) * chunk
+    ntr = (N // chunk) * chunk - n_test
+    svd_time = [0.0]
+    orig = O.svd_truncated
+
+    def timed_svd(*a, **k):
+        t0 = time.perf_counter()
+        out = orig(*a, **k)
+        svd_time[0] += time.perf_counter() - t0
+        return out
+
+    O.svd_truncated = timed_svd
+    try:
+        random.seed(seed)
+        t0 = time.perf_counter()
+        O.fit_predict(X[:ntr], Y[:ntr], X_test=X[ntr:ntr + n_test], y_test=Y[ntr:ntr + n_test], n_inner_folds=Ki,
+                      chunk_length=chunk, alphas=np.logspace(-1, 8, A))
+        total = time.perf_counter() - t0
+    finally:
+        O.svd_truncated = orig
+    t_svd, t_rest = svd_time[0], total - svd_time[0]
+    full_fit_s = Ko * (t_svd + t_rest * V / Vs)
+    units_full = V * A * Ko * Ki
+    return {"sample_s": total, "svd_s": t_svd, "rest_s": t_rest, "sample_voxels": Vs, "full_fit_s_extrapolated": full_fit_s,
+            "value": units_full / full_fit_s,
+            "sample": (f"1 of {Ko} outer folds (train/test mode: {Ki} inner folds + final fit + SciPy pearsonr loop) on "
+                       f"{Vs} of {V} voxels, {N}x{p} design; full fit extrapolated as Ko*(t_svd + t_rest*V/V_sample)")}
+
+
+def cpu_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: the CPU port of the reference's algorithm, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, p, V, A, Ko, Ki, chunk = WORKLOADS[args.workload]
+    vals = []
+    for step in range(args.warmup + args.steps):
+        res = oracle_sample(args.workload, args.sample_voxels, seed=step)
+        if step >= args.warmup:
+            vals.append(res)
+    value = statistics.mean(r["value"] for r in vals)
+    fit_s = statistics.mean(r["full_fit_s_extrapolated"] for r in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": fit_s * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "TRs": N, "features": p, "voxels": V, "alphas": A,
+                   "folds": f"{Ko}x{Ki} chunked({chunk})"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": vals[-1]["sample"],
+                         "sample_s": vals[-1]["sample_s"], "svd_s": vals[-1]["svd_s"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "fit_seconds": fit_s,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 legs
+# ----------------------------------------------------------------------------------------------
+def synth_on_device(torch, N, p, V, seed=0):
+    """Synthetic LeBel-shaped problem, generated on the device (data generation is not the product):
+    temporally smooth, z-scored features; 30 % of the voxels carry signal.  Same seed -> same arrays on
+    every rank."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    X = torch.randn((N, p), device="cuda", generator=g)
+    for _ in range(3):  # cheap temporal smoothing (3 passes of a 2-tap filter)
+        X[1:] = 0.6 * X[:-1] + 0.8 * X[1:]
+    X = (X - X.mean(0)) / X.std(0)
+    W = torch.randn((p, V), device="cuda", generator=g) / p ** 0.5
+    W *= (torch.rand((1, V), device="cuda", generator=g) < 0.3)
+    Y = X @ W
+    del W
+    for r0 in range(0, N, 2048):  # noise in row blocks (bounded scratch)
+        Y[r0:r0 + 2048] += 3.0 * torch.randn((min(2048, N - r0), V), device="cuda", generator=g)
+    return X.contiguous(), Y.contiguous()
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import litcoder_core_b200 as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, p, V, A, Ko, Ki, chunk = WORKLOADS[args.workload]
+    if args.voxels:
+        V = args.voxels
+    alphas = np.logspace(-1, 8, A)
+    # every rank holds the full arrays, as a caller of the drop-in API would; fit_predict moves / reads only
+    # the rank's own voxel block of the responses
+    X_dev, Y_dev = synth_on_device(torch, N, p, V)
+    units = V * A * Ko * Ki
+    model = L.NestedCVModel("ridge_regression")
+    kw = dict(alphas=alphas, n_outer_folds=Ko, n_inner_folds=Ki, chunk_length=chunk, folding_type="chunked")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fit_resident():
+        return model.fit_predict(X_dev, Y_dev, device_outputs=True, **kw)
+
+    # ---------------- value leg: resident inputs ----------------
+    for step in range(args.warmup):
+        random.seed(step)
+        fit_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    corr_ms, corr_flops, eig_ms, phase = [], [], [], {}
+    e0.record()
+    for step in range(args.steps):
+        random.seed(1000 + step)
+        metrics, _, _ = fit_resident()
+        launches += model.last_stats["launches"]
+        for k, v in model.last_timings.items():
+            phase[k] = phase.get(k, 0.0) + v / args.steps
+        corr_ms += model.last_stats["corr_launch_ms"]
+        corr_flops += model.last_stats["corr_launch_flops"]
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_value = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # ---------------- e2e leg: host (pinned) inputs through the public API ----------------
+    X_host = torch.empty((N, p), dtype=torch.float32, pin_memory=True)
+    X_host.copy_(X_dev)
+    Y_host = torch.empty((N, V), dtype=torch.float32, pin_memory=True)
+    Y_host.copy_(Y_dev)
+    del X_dev, Y_dev
+    torch.cuda.empty_cache()
+    Xh, Yh = X_host.numpy(), Y_host.numpy()
+    for step in range(max(1, args.warmup - 2)):
+        random.seed(step)
+        model.fit_predict(Xh, Yh, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for step in range(args.steps):
+        random.seed(1000 + step)
+        m_e2e, W_host, _ = model.fit_predict(Xh, Yh, **kw)
+        h2d += model.last_stats["h2d_bytes"]
+        d2h += model.last_stats["d2h_bytes"]
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    if world > 1:
+        tot = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot)
+        h2d, d2h = int(tot[0].item()), int(tot[1].item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        # dominant kernel: the alpha-stacked prediction GEMM with the fused correlation epilogue
+        big = [(ms, fl) for ms, fl in zip(corr_ms, corr_flops) if fl >= 0.5 * max(corr_flops)]
+        avg_ms = statistics.mean(ms for ms, _ in big)
+        flops = statistics.mean(fl for _, fl in big)
+        achieved = flops / avg_ms / 1e9  # TFLOP/s, algorithmic 2*M*N*K
+        peak = peaks["bf16_tflops_sustained"]
+        line = {
+            "metric": METRIC, "value": units / (ms_value / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulation)", "data": "synthetic",
+            "config": {"workload": args.workload, "TRs": N, "features": p, "voxels": V, "alphas": A,
+                       "folds": f"{Ko}x{Ki} chunked({chunk})", "parallelism": f"voxel-sharded x{world}",
+                       "l2": "inputs (3.6 GB of responses) exceed the 126 MB L2; no flush needed"},
+            "fit_seconds": ms_value / 1e3,
+            "e2e": {"value": units / (ms_e2e / 1e3), "unit": UNIT, "fit_seconds": ms_e2e / 1e3,
+                    "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "gemm_tf32x3_kernel<256,2,EPI_CORR> (alpha-stacked predictions + fused per-voxel correlation)",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": f"{peaks['source']} cuBLAS bf16 dense, sustained (kernel timed inside a long step)",
+                "traffic": None, "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
+                "note": ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 TF32 MMAs per "
+                         "product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the tensor pipe "
+                         "itself sustains 3x this figure against a TF32 dense rate of about peak/2"),
+                "tensor_pipe": {"executed_tf32_tflops": 3 * achieved, "tf32_dense_peak_est": peak / 2,
+                                "frac": 3 * achieved / (peak / 2)},
+            },
+            "phases_ms": {k: round(v, 2) for k, v in sorted(phase.items())},
+            "result_check": {"median_r": metrics["median_score"], "n_significant": metrics["n_significant"],
+                             "e2e_median_r": m_e2e["median_score"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = oracle_sample(args.workload, args.sample_voxels)
+            line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                                    "sample": res["sample"], "sample_s": res["sample_s"], "svd_s": res["svd_s"],
+                                    "full_fit_s_extrapolated": res["full_fit_s_extrapolated"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2_gpt2_9400x3072x95000", choices=sorted(WORKLOADS))
+    ap.add_argument("--voxels", type=int, default=0, help="override the voxel count (development)")
+    ap.add_argument("--sample-voxels", type=int, default=1024, help="voxels in the CPU oracle's bounded sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,8 +127,7 @@ class DeviceOps:
         self.gemm_flops = 0.0  # algorithmic 2*M*N*K of the executed GEMMs (x3 tensor-core MMAs each)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.corr_flops = 0.0  # of which: the fused prediction + correlation GEMM (the dominant kernel)
-        self.corr_launches = 0
+        self._corr_log: List[tuple] = []  # (start, stop, flops) of every fused prediction+correlation GEMM
         self._timed: Dict[str, List[tuple]] = {}
 
     @property
@@ -151,6 +150,11 @@ class DeviceOps:
         """Milliseconds per category (synchronises the device)."""
         self.torch.cuda.synchronize(self.device)
         return {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self._timed.items()}
+
+    def corr_launches(self):
+        """(milliseconds, algorithmic flops) of every fused prediction+correlation GEMM launch (synchronises)."""
+        self.torch.cuda.synchronize(self.device)
+        return [(float(a.elapsed_time(b)), fl) for a, b, fl in self._corr_log]
 
     def synchronize(self):
         self.torch.cuda.synchronize(self.device)
@@ -373,15 +377,18 @@ class DeviceOps:
         ssq = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
         variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256, _lib.GEMM_2CTA_N256) \
             else _lib.GEMM_AUTO
-        with self.timed("gemm_corr"):
-            check(self.lib.lit_gemm_tf32x3_nt_corr(
-                _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
-                n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()),
-                ld, variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
+        flops = 2.0 * M * (n_groups * rows_per_group) * K
+        e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        self._timed.setdefault("gemm_corr", []).append((e0, e1))
+        self._corr_log.append((e0, e1, flops))
+        e0.record()
+        check(self.lib.lit_gemm_tf32x3_nt_corr(
+            _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
+            n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
+            variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
+        e1.record()
         self.launches += 1
-        self.gemm_flops += 2.0 * M * (n_groups * rows_per_group) * K
-        self.corr_flops += 2.0 * M * (n_groups * rows_per_group) * K
-        self.corr_launches += 1
+        self.gemm_flops += flops
         return Partials(dot, ssq, n_tiles, ld)
 
     # ------------------------------------------------------------------ eigendecomposition

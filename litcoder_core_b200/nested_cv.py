@@ -185,11 +185,14 @@ class NestedCVModel:
         normalize_targets: bool = False,
         singcutoff: float = 1e-10,
         gather_weights: bool = True,
+        device_outputs: bool = False,
     ) -> Tuple[Dict[str, Union[float, List[float], List[bool]]], np.ndarray, np.ndarray]:
         """Fit with nested CV (or inner CV + a given test set), per-voxel or single alpha, FDR correction.
 
         Arguments and return value as the reference (nested_cv.py:18-70).  ``gather_weights`` (extension,
         multi-GPU only): False returns this rank's (p x V_rank) weight block instead of the full matrix.
+        ``device_outputs`` (extension): leave the weights on the device and return this rank's (p x V_rank)
+        block as a torch CUDA tensor (no D2H of the 1.2 GB weight matrix).
         """
         t_start = time.perf_counter()
         if alphas is None:
@@ -256,9 +259,13 @@ class NestedCVModel:
                 r_f = comm.all_gather_concat(r_f, counts)
                 p_f = comm.all_gather_concat(p_f, counts)
                 a_f = comm.all_gather_concat(a_f, counts)
-            W = ops.download_matrix(engine.weights_matrix(res))  # (p x V_rank) float32
-            if comm.world > 1 and gather_weights:
-                W = comm.all_gather_concat(W, counts)
+            Wd = engine.weights_matrix(res)  # (p x V_rank) float32 on the device
+            if device_outputs:
+                W = Wd.hi[:, : Wd.cols]
+            else:
+                W = ops.download_matrix(Wd)
+                if comm.world > 1 and gather_weights:
+                    W = comm.all_gather_concat(W, counts)
         del res
 
         with ops.timed("stats"):
@@ -280,6 +287,10 @@ class NestedCVModel:
         self.last_stats = {"launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
                            "world": comm.world, "voxels_this_rank": c1 - c0,
                            "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0)}
+        if hasattr(ops, "corr_launches"):
+            log = ops.corr_launches()
+            self.last_stats["corr_launch_ms"] = [ms for ms, _ in log]
+            self.last_stats["corr_launch_flops"] = [fl for _, fl in log]
         logger.info("Median correlation: %.3f", metrics["median_score"])
         logger.info("Significant voxels: %d/%d (%.1f%%)", metrics["n_significant"], n_vox,
                     metrics["percent_significant"])
