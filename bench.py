@@ -306,6 +306,12 @@ def run_b200(args):
         flops = statistics.mean(fl for _, fl in big)
         achieved = flops / avg_ms / 1e9  # TFLOP/s, algorithmic 2*M*N*K
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel and shape
+        tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
+        if os.path.exists(tpath) and world == 1 and not args.voxels and args.workload.startswith("config2"):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         line = {
             "metric": METRIC, "value": units / (ms_value / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
@@ -322,7 +328,8 @@ def run_b200(args):
                 "kernel": "gemm_tf32x3_kernel<256,2,EPI_CORR> (alpha-stacked predictions + fused per-voxel correlation)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 dense, sustained (kernel timed inside a long step)",
-                "traffic": None, "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
                 "note": ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 TF32 MMAs per "
                          "product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the tensor pipe "
                          "itself sustains 3x this figure against a TF32 dense rate of about peak/2"),
