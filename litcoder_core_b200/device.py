@@ -128,6 +128,7 @@ class DeviceOps:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._corr_log: List[tuple] = []  # (start, stop, flops) of every fused prediction+correlation GEMM
+        self._staging: List[object] = []
         self._timed: Dict[str, List[tuple]] = {}
 
     @property
@@ -189,6 +190,27 @@ class DeviceOps:
             out[: a.size].copy_(t.from_numpy(a), non_blocking=False)
             self.h2d_bytes += a.nbytes
         return out
+
+    def stage_indices(self, arrays) -> list:
+        """Row-index vectors (int32) for a whole fit: one pinned staging buffer, ONE asynchronous H2D copy on
+        the current stream; returns a device view per input array (each padded to a 16-byte boundary)."""
+        t = self.torch
+        offs, total = [], 0
+        for a in arrays:
+            offs.append(total)
+            total += (len(a) + 3) // 4 * 4
+        host = t.empty((max(total, 4),), dtype=t.int32, pin_memory=True)
+        hv = host.numpy()
+        for a, o in zip(arrays, offs):
+            a = np.asarray(a, dtype=np.int64)
+            if len(a) and (a.min() < 0 or a.max() > 2 ** 31 - 1):
+                raise ValueError("row index out of int32 range")
+            hv[o:o + len(a)] = a
+        dev = t.empty((max(total, 4),), dtype=t.int32, device=self.device)
+        dev.copy_(host, non_blocking=True)
+        self._staging.append(host)  # keep the pinned buffer alive until the counters are reset
+        self.h2d_bytes += total * 4
+        return [dev[o:o + max(len(a), 1)] for a, o in zip(arrays, offs)]
 
     def upload_index(self, idx) -> "object":
         return self.upload_vector(np.asarray(idx, dtype=np.int64), "i32")
@@ -254,13 +276,22 @@ class DeviceOps:
             raise ValueError("column block must start on a multiple of 4 columns (16-byte alignment)")
         return Mat(tensor[:, c0:c1], None, full.rows, c1 - c0, ld=full.ld)
 
+    def raw(self, x):
+        """Underlying torch tensor of a Mat (first plane) or device vector, for in-place collectives."""
+        return x.hi if isinstance(x, Mat) else x
+
     def download(self, t) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()
         return t.detach().cpu().numpy()
 
     def download_matrix(self, m: Mat) -> np.ndarray:
         """D2H of the logical [rows][cols] block (hi + lo for split pairs is NOT applied here)."""
-        out = np.empty((m.rows, m.cols), dtype=np.float32)
+        if m.rows * m.cols >= (1 << 22):
+            # large results land in page-locked memory (PCIe rate instead of the pageable staging rate); the
+            # returned ndarray owns that buffer
+            out = self.torch.empty((m.rows, m.cols), dtype=self.torch.float32, pin_memory=True).numpy()
+        else:
+            out = np.empty((m.rows, m.cols), dtype=np.float32)
         if m.rows and m.cols:
             check(self.lib.lit_memcpy_2d(_vp(out.ctypes.data), m.cols * 4, _vp(m.hi.data_ptr()), m.ld * 4, m.cols * 4,
                                          m.rows, 2, _vp(self.stream)), "memcpy_2d(D2H)")

@@ -86,6 +86,9 @@ class SingleProcess:
     def all_gather_concat(self, arr: np.ndarray, counts=None) -> np.ndarray:
         return arr
 
+    def broadcast_inplace(self, buffers, src: int) -> None:
+        pass
+
 
 def removed_rows(outer_rows: np.ndarray, inner_rows: np.ndarray) -> Optional[np.ndarray]:
     """Rows of the outer training set that are absent from the inner one, or None when the inner set
@@ -104,35 +107,79 @@ class RidgeCVEngine:
     def __init__(self, ops, comm=None):
         self.ops = ops
         self.comm = comm if comm is not None else SingleProcess()
+        self._eig_jobs = 0  # running count of eigenproblems; job j is solved by rank j % world
+
+    # ------------------------------------------------------------------------------------------
+    # row-index vectors of every fold, staged to the device in ONE asynchronous copy
+    # ------------------------------------------------------------------------------------------
+    def stage_plans(self, plans: List[FoldPlan], cfg: RidgeConfig):
+        """Per plan: device int32 row-index vectors for the outer train / test rows and, per inner fold,
+        the train and validation rows plus the removed rows R when the fold can be downdated.
+        (A synchronous upload per fold would drain the stream ~150 times per fit.)"""
+        arrays, staged = [], []
+        for plan in plans:
+            tr_o = np.asarray(plan.train_rows, dtype=np.int64)
+            entry = {"train_rows": tr_o, "test_rows": np.asarray(plan.test_rows, dtype=np.int64), "inner": []}
+            arrays += [entry["train_rows"], entry["test_rows"]]
+            for tr_i, va_i in plan.inner:
+                tr_i, va_i = np.asarray(tr_i, dtype=np.int64), np.asarray(va_i, dtype=np.int64)
+                R = removed_rows(tr_o, tr_i) if cfg.downdate else None
+                if R is not None and not (0 < len(R) <= len(tr_i) // 2):
+                    R = None  # the downdate only pays when it is much shorter than the direct product
+                entry["inner"].append({"train_rows": tr_i, "val_rows": va_i, "R_rows": R})
+                arrays += [tr_i, va_i] + ([R] if R is not None else [])
+            staged.append(entry)
+        dev = iter(self.ops.stage_indices(arrays))
+        for entry in staged:
+            entry["train"], entry["test"] = next(dev), next(dev)
+            for d in entry["inner"]:
+                d["train"], d["val"] = next(dev), next(dev)
+                d["R"] = next(dev) if d["R_rows"] is not None else None
+        return staged
 
     # ------------------------------------------------------------------------------------------
     # design side: Grams and their eigendecompositions (depend on X only)
     # ------------------------------------------------------------------------------------------
-    def _design_side(self, X, plan: FoldPlan, cfg: RidgeConfig):
-        """Gram + syevd for the outer training set and for every inner fold.
+    def _design_side(self, X, sp, cfg: RidgeConfig):
+        """Gram + syevd for the outer training set and for every inner fold of one staged plan `sp`.
 
         Returns (outer, inners): dicts with XtT (p x n split, or None when downdated), XRt (p x |R| split)
-        / R for downdated folds, G (holds Vt after the eig), lam and the eig ticket."""
-        ops = self.ops
-        tr_o = np.asarray(plan.train_rows, dtype=np.int64)
-        XoT = ops.gather_rows_T_split(X, ops.upload_index(tr_o), len(tr_o))  # (p x n_o)
+        for downdated folds, G (holds Vt after the eig), lam and the eig ticket."""
+        ops, comm = self.ops, self.comm
+        p = X.cols
+        XoT = ops.gather_rows_T_split(X, sp["train"], len(sp["train_rows"]))  # (p x n_o)
         G_o = ops.gemm(XoT, XoT)  # outer Gram, p x p
         inners = []
-        for tr_i, va_i in plan.inner:
-            R = removed_rows(tr_o, tr_i) if cfg.downdate else None
-            d = {"train": np.asarray(tr_i, dtype=np.int64), "val": np.asarray(va_i, dtype=np.int64), "R": None}
-            if R is not None and 0 < len(R) <= len(tr_i) // 2:
-                XRt = ops.gather_rows_T_split(X, ops.upload_index(R), len(R))  # (p x |R|)
-                d.update(R=R, XRt=XRt, XtT=None, G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0))
+        for d in sp["inner"]:
+            d = dict(d)
+            d["owner"] = self._next_eig_owner()
+            mine = d["owner"] == comm.rank
+            if d["R"] is not None:
+                XRt = ops.gather_rows_T_split(X, d["R"], len(d["R_rows"]))  # (p x |R|)
+                d.update(XRt=XRt, XtT=None,
+                         G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0) if mine else ops.empty(p, p))
             else:
-                XtT = ops.gather_rows_T_split(X, ops.upload_index(d["train"]), len(d["train"]))
-                d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT))
+                XtT = ops.gather_rows_T_split(X, d["train"], len(d["train_rows"]))
+                d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if mine else ops.empty(p, p))
             inners.append(d)
-        outer = {"XtT": XoT, "G": ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o, "G_keep": G_o}
-        # queue every eigendecomposition (inner folds first: they are needed first)
+        outer = {"XtT": XoT, "owner": self._next_eig_owner(), "G_keep": G_o,
+                 "G": ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o}
+        # Queue the eigendecompositions this rank owns (inner folds first: they are needed first).  With
+        # several ranks every eigenproblem is solved once, by rank (job index mod world), and broadcast when
+        # it is consumed: X is replicated, so the 30 decompositions of a fit would otherwise be redundant.
         for d in inners + [outer]:
-            d["lam"], d["ticket"] = ops.syevd_async(d["G"]) if cfg.overlap_eig else (ops.syevd(d["G"]), None)
+            if d["owner"] != comm.rank:
+                d["lam"], d["ticket"] = ops.vec(p), None
+            elif cfg.overlap_eig:
+                d["lam"], d["ticket"] = ops.syevd_async(d["G"])
+            else:
+                d["lam"], d["ticket"] = ops.syevd(d["G"]), None
         return outer, inners
+
+    def _next_eig_owner(self) -> int:
+        owner = self._eig_jobs % self.comm.world
+        self._eig_jobs += 1
+        return owner
 
     def _eig_ready(self, d):
         """Wait (on the main stream) for d's eigendecomposition; returns (Vt split, Vt fp32, lam)."""
@@ -140,47 +187,46 @@ class RidgeCVEngine:
         if d["ticket"] is not None:
             ops.wait(d["ticket"])
             d["ticket"] = None
+        if self.comm.world > 1:
+            self.comm.broadcast_inplace([ops.raw(d["G"]), ops.raw(d["lam"])], src=d["owner"])
         return ops.split(d["G"]), d["G"], d["lam"]
 
     # ------------------------------------------------------------------------------------------
     # inner CV
     # ------------------------------------------------------------------------------------------
-    def _inner_scores(self, X, Y, plan: FoldPlan, outer, inners, alphas_dev, n_alphas: int, cfg: RidgeConfig):
+    def _inner_scores(self, X, Y, sp, outer, inners, alphas_dev, n_alphas: int, cfg: RidgeConfig):
         """Sum over inner folds of the (n_alphas x V_r) validation scores (ridge_corr_torch per fold).
         Also returns C_o^T (V_r x p fp32) for the outer fit."""
         ops = self.ops
-        tr_o = np.asarray(plan.train_rows, dtype=np.int64)
-        YoT = ops.gather_rows_T_split(Y, ops.upload_index(tr_o), len(tr_o))  # (V_r x n_o)
+        YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
         Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
         del YoT
         corr_sum = ops.empty(n_alphas, Y.cols)
         metric = 0 if cfg.use_corr else 1
         for i, d in enumerate(inners):
-            tr, va = d["train"], d["val"]
-            n_tr, n_va = len(tr), len(va)
+            n_tr, n_va = len(d["train_rows"]), len(d["val_rows"])
             if n_va < 2 or n_tr < 1:
                 raise ValueError("inner fold needs >= 1 training and >= 2 validation samples")
             # cross product of the inner training rows
             if d["R"] is not None:
-                YRt = ops.gather_rows_T_split(Y, ops.upload_index(d["R"]), len(d["R"]))  # (V_r x |R|)
+                YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]))  # (V_r x |R|)
                 Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True)
                 del YRt
             else:
-                YtT = ops.gather_rows_T_split(Y, ops.upload_index(tr), n_tr)
+                YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
                 Ct = ops.gemm(YtT, d["XtT"], split_out=True)
                 del YtT
             Vt, _, lam = self._eig_ready(d)
             Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
             del Ct
             # validation design in the eigenbasis, centred and stacked over alphas
-            va_dev = ops.upload_index(va)
             rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
-            Pv = ops.gather_rows(X, va_dev, n_va, split=True)  # (n_v x p)
+            Pv = ops.gather_rows(X, d["val"], n_va, split=True)  # (n_v x p)
             L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
             Lst = ops.build_alpha_stack(L, n_va, rows_pad, lam, alphas_dev, n_alphas, cfg.normalpha, cfg.singcutoff)
             del Pv, L, Vt
-            mean, std = ops.col_stats(Y, va_dev, n_va, ddof=1)
-            Yz = ops.gather_normalize(Y, va_dev, n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
+            mean, std = ops.col_stats(Y, d["val"], n_va, ddof=1)
+            Yz = ops.gather_normalize(Y, d["val"], n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
             parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz)
             ops.corr_finalize(parts, rows_pad // ops.PART_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
                               accumulate=(i > 0), metric=metric, resp_std=std)
@@ -201,11 +247,11 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     # outer fit + test scoring
     # ------------------------------------------------------------------------------------------
-    def _outer_fit_and_score(self, Xte_src, Yte_src, plan: FoldPlan, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+    def _outer_fit_and_score(self, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
         """ridge_torch on the outer training set with the selected alphas, then test r / p."""
         ops = self.ops
-        n_te = len(plan.test_rows)
-        te_dev = ops.upload_index(plan.test_rows)
+        n_te = len(sp["test_rows"])
+        te_dev = sp["test"]
         Vt, G, lam = self._eig_ready(outer)
         Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
         del Vt
@@ -224,13 +270,13 @@ class RidgeCVEngine:
         r, p = ops.pearson_finalize(parts, Wt.rows, n_te, cfg.p_round_f32)
         return Wt, r, p
 
-    def _normalised(self, M, Mte_src, train_rows, enabled: bool, same_source: bool):
+    def _normalised(self, M, Mte_src, train_rows, train_dev, enabled: bool, same_source: bool):
         """DataNormalizer (ridge_utils.py:70-180): z-score a matrix (and its test source) with the
         training rows' statistics (unbiased std, eps added to the std)."""
         if not enabled:
             return M, Mte_src
         ops = self.ops
-        m, s = ops.col_stats(M, ops.upload_index(train_rows), len(train_rows), ddof=1)
+        m, s = ops.col_stats(M, train_dev, len(train_rows), ddof=1)
         Mn = ops.gather_normalize(M, None, M.rows, m, s, 0, EPS)
         Mtn = Mn if same_source else ops.gather_normalize(Mte_src, None, Mte_src.rows, m, s, 0, EPS)
         return Mn, Mtn
@@ -255,17 +301,19 @@ class RidgeCVEngine:
         # Design side of EVERY outer fold first: Grams are cheap and depend on X only, and queueing all the
         # eigendecompositions now lets the side stream run ahead of the response-side GEMMs.
         Xte_src, Yte_src = (X, Y) if same_source else (X_test, Y_test)
+        staged = self.stage_plans(plans, cfg)
+        self._eig_jobs = 0
         prepared = []
-        for plan in plans:
-            Xs, Xts = self._normalised(X, Xte_src, plan.train_rows, cfg.normalize_features, same_source)
-            prepared.append((Xs, Xts) + self._design_side(Xs, plan, cfg))
-        for plan in plans:
+        for sp in staged:
+            Xs, Xts = self._normalised(X, Xte_src, sp["train_rows"], sp["train"], cfg.normalize_features, same_source)
+            prepared.append((Xs, Xts) + self._design_side(Xs, sp, cfg))
+        for plan, sp in zip(plans, staged):
             Xs, Xts, outer, inners = prepared.pop(0)
-            Ys, Yts = self._normalised(Y, Yte_src, plan.train_rows, cfg.normalize_targets, same_source)
-            corr_sum, Ct_o = self._inner_scores(Xs, Ys, plan, outer, inners, alphas_f64, len(alphas), cfg)
+            Ys, Yts = self._normalised(Y, Yte_src, sp["train_rows"], sp["train"], cfg.normalize_targets, same_source)
+            corr_sum, Ct_o = self._inner_scores(Xs, Ys, sp, outer, inners, alphas_f64, len(alphas), cfg)
             alpha_v = self._select_alphas(corr_sum, len(plan.inner), alphas_f32, cfg, n_vox_total)
             del corr_sum, inners
-            Wt, r, p = self._outer_fit_and_score(Xts, Yts, plan, outer, Ct_o, alpha_v, cfg)
+            Wt, r, p = self._outer_fit_and_score(Xts, Yts, sp, outer, Ct_o, alpha_v, cfg)
             del outer, Ct_o, Xs, Xts, Ys, Yts
             if len(plans) == 1:
                 res.Wt_mean = Wt

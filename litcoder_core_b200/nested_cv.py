@@ -53,6 +53,14 @@ class TorchDistComm:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
+    def broadcast_inplace(self, buffers, src: int) -> None:
+        """Broadcast rank `src`'s buffers into everybody's (torch tensors on the communicator's device, or
+        NumPy arrays with the gloo backend), in place."""
+        for b in buffers:
+            t = b if self._torch.is_tensor(b) else self._torch.from_numpy(b)
+            self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, src) if self.group is not None else src,
+                                 group=self.group)
+
     def all_gather_concat(self, arr: np.ndarray, counts: Optional[Sequence[int]] = None) -> np.ndarray:
         """Concatenate the ranks' arrays along the LAST axis; counts[r] = last-axis length on rank r."""
         arr = np.ascontiguousarray(arr)

@@ -73,6 +73,9 @@ class FakeOps:
         dt = {"f32": np.float32, "f64": np.float64, "i32": np.int32}[dtype]
         return np.array(arr, dtype=dt).reshape(-1)
 
+    def stage_indices(self, arrays):
+        return [np.asarray(a, dtype=np.int64).astype(np.int32) for a in arrays]
+
     def upload_index(self, idx):
         return np.asarray(idx, dtype=np.int64).astype(np.int32)
 
@@ -81,6 +84,12 @@ class FakeOps:
         assert host.ndim == 2
         self.h2d_bytes += host[:, col_start:col_stop].nbytes
         return FMat(host[:, col_start:col_stop].astype(F32))
+
+    def raw(self, x):
+        return x.a if isinstance(x, FMat) else x
+
+    def vec(self, n, dtype="f32"):
+        return np.full(n, np.nan, dtype={"f32": np.float32, "f64": np.float64, "i32": np.int32, "u8": np.uint8}[dtype])
 
     def download(self, t):
         return np.array(t)

@@ -1,0 +1,72 @@
+"""World-size-2 test of the multi-rank path on CPU (gloo): voxel sharding, eigenproblem ownership +
+broadcast, the single-alpha all-reduce and the final all-gathers must reproduce the single-process
+result.  The arithmetic runs on the NumPy stand-in of the C ABI (tests/fake_ops.py)."""
+import os
+import random
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _problem():
+    rng = np.random.default_rng(5)
+    N, p, V = 300, 10, 300  # 300 voxels -> blocks of 256 + 44 (shards start on 128-voxel tile boundaries)
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Y = (X @ rng.standard_normal((p, V)) * 0.4 + rng.standard_normal((N, V))).astype(np.float32)
+    return X, Y
+
+
+def _worker(rank, world, port, single_alpha, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from fake_ops import FakeOps
+    from litcoder_core_b200.nested_cv import NestedCVModel, TorchDistComm
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        X, Y = _problem()
+        random.seed(11)
+        model = NestedCVModel("ridge_regression", ops=FakeOps(), comm=TorchDistComm())
+        m, w, a = model.fit_predict(X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10,
+                                    alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
+        assert model.last_stats["world"] == world and model.last_stats["voxels_this_rank"] in (256, 44)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
+                 p=np.asarray(m["p_values"]), sig=np.asarray(m["significant_mask"]), n_sig=m["n_significant"])
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("single_alpha", [False, True])
+def test_two_ranks_match_single_process(tmp_path, single_alpha):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    from fake_ops import FakeOps
+    from litcoder_core_b200.nested_cv import NestedCVModel
+
+    X, Y = _problem()
+    random.seed(11)
+    m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(
+        X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
+    mp.spawn(_worker, args=(2, _free_port(), single_alpha, str(tmp_path)), nprocs=2, join=True)
+    for rank in range(2):
+        g = np.load(tmp_path / f"rank{rank}.npz")
+        np.testing.assert_array_equal(g["a"], a)
+        np.testing.assert_allclose(g["r"], np.asarray(m["correlations"]), atol=1e-6)
+        np.testing.assert_allclose(g["w"], w, atol=1e-6 * np.abs(w).max())
+        np.testing.assert_allclose(g["p"], np.asarray(m["p_values"]), rtol=1e-4, atol=1e-12)
+        assert int(g["n_sig"]) == m["n_significant"]
+        np.testing.assert_array_equal(g["sig"], np.asarray(m["significant_mask"]))

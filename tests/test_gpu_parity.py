@@ -255,8 +255,9 @@ def test_ridge_corr_and_weights_match_reference_golden(ops, name):
     for normalpha in (True, False):
         for use_corr in (True, False):
             cfg = RidgeConfig(alphas=alphas, normalpha=normalpha, use_corr=use_corr, singcutoff=1e-10)
-            outer, inners = eng._design_side(Xd, plan, cfg)
-            corr, _ = eng._inner_scores(Xd, Yd, plan, outer, inners, ops.upload_vector(np.asarray(alphas), "f64"),
+            sp = eng.stage_plans([plan], cfg)[0]
+            outer, inners = eng._design_side(Xd, sp, cfg)
+            corr, _ = eng._inner_scores(Xd, Yd, sp, outer, inners, ops.upload_vector(np.asarray(alphas), "f64"),
                                         len(alphas), cfg)
             eng._eig_ready(outer)
             out = ops.download_matrix(corr)
