@@ -15,10 +15,10 @@ struct SolverCtx {
   cusolverDnParams_t params = nullptr;
 };
 
+// One cuSOLVER handle per calling host thread: syevd blocks its caller, so concurrent decompositions are
+// issued from several worker threads, each on its own stream with its own handle and workspace.
 static int get_solver(SolverCtx** out) {
-  static SolverCtx ctx;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
+  static thread_local SolverCtx ctx;
   if (!ctx.handle) {
     cusolverStatus_t st = cusolverDnCreate(&ctx.handle);
     if (st != CUSOLVER_STATUS_SUCCESS) {

@@ -423,7 +423,10 @@ static int kc_blocks_default() {
   return v;
 }
 
-static int g_sm_limit = 0;  // 0 = use every SM
+static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it (development knob)
+  const char* e = getenv("LIT_GEMM_SM_LIMIT");
+  return e ? atoi(e) : 0;
+}();
 
 template <int BN, int CG, int EPI>
 static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,

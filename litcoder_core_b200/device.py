@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 import queue
 import threading
 from typing import Dict, List, Optional, Tuple
@@ -69,12 +70,13 @@ class _EigTicket:
 
 
 class _EigWorker(threading.Thread):
-    """Issues the (host-blocking) cuSOLVER calls on the side stream, in submission order."""
+    """Issues (host-blocking) cuSOLVER calls on its own side stream.  A decomposition of a few thousand
+    rows is latency-bound (thousands of small kernels), so several of them in flight on separate streams
+    overlap with each other and with the tensor-core GEMMs."""
 
-    def __init__(self, ops: "DeviceOps"):
+    def __init__(self, ops: "DeviceOps", jobs: "queue.Queue", stream):
         super().__init__(name="litridge-eig", daemon=True)
-        self.ops = ops
-        self.jobs: "queue.Queue" = queue.Queue()
+        self.ops, self.jobs, self.stream = ops, jobs, stream
 
     def run(self):
         ops, t = self.ops, self.ops.torch
@@ -85,13 +87,15 @@ class _EigWorker(threading.Thread):
                 return
             G, lam, ready, ticket = job
             try:
-                with t.cuda.stream(ops._side):
-                    ops._side.wait_event(ready)
+                with t.cuda.stream(self.stream):
+                    self.stream.wait_event(ready)
                     ops.syevd(G, lam=lam)
                     ticket.done = t.cuda.Event()
                     ticket.done.record()
             except BaseException as e:  # surfaced by wait()
                 ticket.error = e
+            with ops._eig_lock:
+                ops.eig_pending -= 1
             ticket.issued.set()
 
 
@@ -117,8 +121,17 @@ class DeviceOps:
         self.reset_counters()
         self._eig_ws: Dict[Tuple[int, int], tuple] = {}
         self._bh_ws = None
-        self._side = None  # side stream for the eigendecompositions
-        self._eig_worker = None
+        # concurrent eigendecompositions: more than one in flight was measured to be SLOWER on one GPU
+        # (3.3 s per config-2 fit with 1 worker, 3.7 s with 2 or 3: they contend for the SMs the GEMMs leave)
+        self.eig_workers = int(os.environ.get("LIT_EIG_WORKERS", "1"))
+        self._eig_workers: List[object] = []
+        self._eig_jobs = None
+        self._eig_lock = threading.Lock()
+        self.eig_pending = 0  # decompositions queued or running
+        self.overlap_sms = int(os.environ.get("LIT_GEMM_OVERLAP_SMS", "100"))  # GEMM grid while eigs are in flight
+        self._overlap_always = os.environ.get("LIT_GEMM_OVERLAP_ALWAYS", "0") == "1"  # development knob
+        self._cur_sm_limit = 0
+        self.set_gemm_sm_limit(0)
         self._eig_infos: List[object] = []
 
     # ------------------------------------------------------------------ bookkeeping
@@ -370,6 +383,15 @@ class DeviceOps:
     def set_gemm_sm_limit(self, n_sms: int) -> None:
         """Restrict the persistent GEMM grids to n_sms SMs (0 = all); see lit_gemm_set_sm_limit."""
         check(self.lib.lit_gemm_set_sm_limit(int(n_sms)), "gemm_set_sm_limit")
+        self._cur_sm_limit = int(n_sms)
+
+    def _apply_sm_limit(self) -> None:
+        """While eigendecompositions are queued or running, leave SMs free for them: the GEMMs are
+        persistent kernels that otherwise occupy every SM (all registers) until they finish, which would
+        serialise the two.  Measured on config 2 (1 GPU): 4.00 s per fit with 148 SMs, 3.1 s with 100."""
+        want = self.overlap_sms if ((self.eig_pending > 0 or self._overlap_always) and self.overlap_sms > 0) else 0
+        if want != self._cur_sm_limit:
+            self.set_gemm_sm_limit(want)
 
     def gemm(self, A: Mat, B: Mat, alpha: float = 1.0, Cin: Optional[Mat] = None, beta: float = 0.0,
              split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None) -> Mat:
@@ -381,6 +403,7 @@ class DeviceOps:
         M, N, K = A.rows, B.rows, A.cols
         if out is None:
             out = self.empty(M, N, split=split_out, ld=ld_out)
+        self._apply_sm_limit()
         with self.timed("gemm"):
             self._gemm_call(A, B, M, N, K, alpha, Cin, beta, out)
         self.launches += 1
@@ -412,6 +435,7 @@ class DeviceOps:
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         self._timed.setdefault("gemm_corr", []).append((e0, e1))
         self._corr_log.append((e0, e1, flops))
+        self._apply_sm_limit()
         e0.record()
         check(self.lib.lit_gemm_tf32x3_nt_corr(
             _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
@@ -428,13 +452,15 @@ class DeviceOps:
         n = G.rows
         if G.cols != n:
             raise ValueError("syevd needs a square matrix")
-        key = (n, 0)
+        key = (n, threading.get_ident())
         if key not in self._eig_ws:
             dev_b, host_b = C.c_size_t(0), C.c_size_t(0)
             check(self.lib.lit_syevd_workspace(n, 0, 1, C.byref(dev_b), C.byref(host_b)), "syevd_workspace")
             work = self.torch.empty((max(dev_b.value, 16),), dtype=self.torch.uint8, device=self.device)
             work_h = (C.c_uint8 * max(host_b.value, 16))()
-            self._eig_ws = {key: (work, dev_b.value, work_h, host_b.value)}  # keep only the latest size
+            for k in [k for k in self._eig_ws if k[1] == key[1]]:
+                del self._eig_ws[k]  # keep only the latest size per calling thread
+            self._eig_ws[key] = (work, dev_b.value, work_h, host_b.value)
         work, dev_b, work_h, host_b = self._eig_ws[key]
         info = self.vec(1, "i32")
         self._eig_infos.append(info)
@@ -461,15 +487,19 @@ class DeviceOps:
         42.7 ms of 45.0 ms device time at n = 3072), so the calls are issued by a worker thread; the
         caller keeps feeding the main stream meanwhile."""
         t = self.torch
-        if self._eig_worker is None:
-            self._side = t.cuda.Stream(device=self.device)
-            self._eig_worker = _EigWorker(self)
-            self._eig_worker.start()
+        if not self._eig_workers:
+            self._eig_jobs = queue.Queue()
+            for _ in range(self.eig_workers):
+                w = _EigWorker(self, self._eig_jobs, t.cuda.Stream(device=self.device))
+                w.start()
+                self._eig_workers.append(w)
         lam = self.vec(G.rows)
         ready = t.cuda.Event()
         ready.record()
         ticket = _EigTicket()
-        self._eig_worker.jobs.put((G, lam, ready, ticket))
+        with self._eig_lock:
+            self.eig_pending += 1
+        self._eig_jobs.put((G, lam, ready, ticket))
         return lam, ticket
 
     def wait(self, ticket) -> None:
@@ -480,10 +510,11 @@ class DeviceOps:
         self.torch.cuda.current_stream(self.device).wait_event(ticket.done)
 
     def close(self) -> None:
-        if self._eig_worker is not None:
-            self._eig_worker.jobs.put(None)
-            self._eig_worker.join(timeout=10)
-            self._eig_worker = None
+        for w in self._eig_workers:
+            self._eig_jobs.put(None)
+        for w in self._eig_workers:
+            w.join(timeout=10)
+        self._eig_workers = []
 
     # ------------------------------------------------------------------ ridge kernels
     def build_alpha_stack(self, L: Mat, n_rows: int, rows_pad: int, lam, alphas_dev, n_alphas: int, normalpha: bool,
