@@ -47,6 +47,23 @@ class TorchDistComm:
         backend = dist.get_backend(group)
         self._dev = device if (backend == "nccl" and device is not None) else (
             torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+        self.device_collectives = backend == "nccl"  # tensors can be exchanged without leaving the GPU
+
+    def all_gather_cols_device(self, block, counts: Sequence[int], ld: int):
+        """All-gather of per-rank column blocks (rows x counts[r], CUDA tensors) into one (rows x ld) device
+        matrix whose first sum(counts) columns are the concatenation -- NCCL over NVLink, no host hop."""
+        t = self._torch
+        rows, width = block.shape[0], max(counts)
+        pad = t.zeros((rows, width), dtype=block.dtype, device=block.device)
+        pad[:, : block.shape[1]] = block
+        out = t.empty((self.world, rows, width), dtype=block.dtype, device=block.device)
+        self._dist.all_gather_into_tensor(out, pad, group=self.group)
+        full = t.empty((rows, ld), dtype=block.dtype, device=block.device)
+        c0 = 0
+        for r, c in enumerate(counts):
+            full[:, c0:c0 + c] = out[r][:, :c]
+            c0 += c
+        return full
 
     def all_reduce_sum(self, arr: np.ndarray) -> np.ndarray:
         t = self._torch.from_numpy(np.ascontiguousarray(arr)).to(self._dev)
@@ -270,6 +287,10 @@ class NestedCVModel:
             Wd = engine.weights_matrix(res)  # (p x V_rank) float32 on the device
             if device_outputs:
                 W = Wd.hi[:, : Wd.cols]
+            elif comm.world > 1 and gather_weights and getattr(comm, "device_collectives", False):
+                ld = -(-n_vox // 32) * 32
+                full = comm.all_gather_cols_device(Wd.hi[:, : Wd.cols], counts, ld)
+                W = ops.download_matrix(type(Wd)(full, None, Wd.rows, n_vox))
             else:
                 W = ops.download_matrix(Wd)
                 if comm.world > 1 and gather_weights:
