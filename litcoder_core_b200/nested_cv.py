@@ -284,6 +284,7 @@ class NestedCVModel:
                 r_f = comm.all_gather_concat(r_f, counts)
                 p_f = comm.all_gather_concat(p_f, counts)
                 a_f = comm.all_gather_concat(a_f, counts)
+            t_w0 = time.perf_counter()
             Wd = engine.weights_matrix(res)  # (p x V_rank) float32 on the device
             if device_outputs:
                 W = Wd.hi[:, : Wd.cols]
@@ -296,7 +297,9 @@ class NestedCVModel:
                 if comm.world > 1 and gather_weights:
                     W = comm.all_gather_concat(W, counts)
         del res
+        t_w = (time.perf_counter() - t_w0) * 1e3
 
+        t_s0 = time.perf_counter()
         with ops.timed("stats"):
             masks, comb_p, sig, padj = engine.significance(p_f, cfg)
 
@@ -311,8 +314,11 @@ class NestedCVModel:
             best = np.mean(a_f.astype(np.float64) if single_alpha else a_f, axis=0)  # nested_cv.py:293
             metrics = _metrics(corr.astype(np.float64), comb_p, padj, sig, best, majority)
 
+        t_stats_end = time.perf_counter()
         self.last_timings = ops.timings()
         self.last_timings["wall_ms"] = (time.perf_counter() - t_start) * 1e3
+        self.last_timings["host_weights_ms"] = t_w
+        self.last_timings["host_stats_metrics_ms"] = (t_stats_end - t_s0) * 1e3
         self.last_stats = {"launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
                            "world": comm.world, "voxels_this_rank": c1 - c0,
                            "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0)}
