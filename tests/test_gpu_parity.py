@@ -394,3 +394,47 @@ def test_full_width_properties(ops):
     assert np.abs(r2[same] - r[perm][same]).max() < 1e-4
     assert abs(m2["n_significant"] - m["n_significant"]) <= 3
     np.testing.assert_allclose(w2[:, same], (w[:, perm] * scale[None, :])[:, same], rtol=0, atol=2e-4 * np.abs(w2).max())
+
+
+def test_full_width_matches_oracle(ops):
+    """BASELINE config-2 design (9,400 TRs x 3,072 features, 20 alphas, 5 inner chunked folds) on 384 voxels,
+    train/test mode, against the CPU oracle (six fp32 SVDs of 7,520 x 3,072: ~30 s of host time)."""
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(21)
+    N, p, V = 9400, 3072, 384
+    X, Y = _synthetic(rng, N, p, V, frac=0.5, noise=4.0)
+    Y[:, 7] = 1.0
+    ntr = 7520
+    kw = dict(n_inner_folds=5, chunk_length=20, alphas=np.logspace(-1, 8, 20))
+    random.seed(9)
+    m, w, a = L.fit_nested_cv(features=X[:ntr], targets=Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], **kw)
+    random.seed(9)
+    mo, wo, ao = O.fit_predict(X[:ntr], Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], vectorised_stats=True, **kw)
+    same = np.isclose(a, ao, rtol=1e-6)
+    same[7] = False
+    assert same.mean() > 0.9, same.mean()
+    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
+    assert np.abs(r[same] - ro[same]).max() < 1e-4, np.abs(r[same] - ro[same]).max()
+    assert np.abs(w[:, same] - wo[:, same]).max() < 2e-4 * np.abs(wo).max()
+    assert abs(m["n_significant"] - mo["n_significant"]) <= 1 + (~same).sum()
+    assert r[7] == 0.0 and m["p_values"][7] == 1.0
+
+
+def test_wide_design_matches_oracle(ops):
+    """Narratives-shaped problem (BASELINE config 4: fewer TRs than features, 2,226 x 3,072) on 1,000 voxels,
+    full nested CV with 3 x 3 folds: the Gram is rank-deficient in every fold."""
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(22)
+    N, p, V = 2226, 3072, 1000
+    X, Y = _synthetic(rng, N, p, V, frac=0.5, noise=4.0)
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 8, 20), folding_type="kfold_trimmed")
+    m, w, a = L.fit_nested_cv(features=X, targets=Y, **kw)
+    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
+    same = np.isclose(a, ao, rtol=1e-6)
+    assert same.mean() > 0.9, same.mean()
+    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
+    assert np.abs(r[same] - ro[same]).max() < 1e-4, np.abs(r[same] - ro[same]).max()
+    assert np.abs(w[:, same] - wo[:, same]).max() < 2e-4 * np.abs(wo).max()
+    assert abs(m["n_significant"] - mo["n_significant"]) <= 2 + (~same).sum()
