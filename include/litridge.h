@@ -119,6 +119,7 @@ int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx,
  *   mode 0: scale = 1 / (std[c] + eps)                  (z_score, eps = 1e-8)
  *   mode 1: scale = 1 / (std[c] * sqrt(n_idx - 1))      (unit-norm centred column; NaN if std == 0)
  *   mode 2: scale = 1                                   (centre only)
+ *   mode 3: scale = 1 / std[c] if std[c] != 0 else 1    (zs / zscore of the trainers, encoding/utils.py:23-34)
  * Optional split output. */
 int lit_gather_normalize_rows(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
                               const float* mean, const float* std, int mode, float eps, float* dst, float* dst_lo,
@@ -157,6 +158,7 @@ int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, lon
  *   metric 0: corr[a][v] = nan_to_num( (sum_tiles dot / n_rows) / (sqrt(sum_tiles ssq / (n_rows-1)) + eps) )
  *             (Yz z-scored with the unbiased std + eps)
  *   metric 1: signed sqrt of R^2 = 1 - var(Q - pred)/var(Q) (Yz centred only; resp_std = unbiased std of Q)
+ *   metric | 2: the same without the nan_to_num scrub (ridge_corr_pred_torch, ridge_regression.py:203-214)
  * accumulate != 0 adds into corr (fold sum for nested_cv.py:391-393). */
 int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group, int n_groups,
                       long n_vox, long n_rows, float eps, int accumulate, int metric, const float* resp_std,

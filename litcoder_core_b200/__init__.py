@@ -14,6 +14,8 @@ from .downsample import Downsampler
 from .fir import FIR
 from .folding import create_folds
 from .nested_cv import NestedCVModel, fit_nested_cv
+from .ridge_regression import ridge, ridge_corr, ridge_corr_pred, ridge_corr_pred_torch, ridge_corr_torch, ridge_torch, zs
 
-__all__ = ["NestedCVModel", "fit_nested_cv", "Downsampler", "FIR", "create_folds"]
+__all__ = ["NestedCVModel", "fit_nested_cv", "Downsampler", "FIR", "create_folds", "ridge", "ridge_corr",
+           "ridge_corr_pred", "ridge_torch", "ridge_corr_torch", "ridge_corr_pred_torch", "zs"]
 __version__ = "0.1.0"

@@ -116,6 +116,9 @@ __global__ void gather_normalize_kernel(const float* __restrict__ src, long ld_s
           // reduction and becomes (r, p) = (0, 1) in pearson_finalize, as SciPy's pearsonr -> NaN
           const float sd = stdv[c + u];
           sc = sd > 0.f ? rs / sd : __int_as_float(0x7fc00000);
+        } else if (mode == 3) {
+          const float sd = stdv[c + u];
+          sc = sd != 0.f ? 1.f / sd : 1.f;  // zs(): zero-variance columns are centred only
         }
         x[u] = (x[u] - m) * sc;
       }
@@ -222,6 +225,8 @@ __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const f
   if (v >= n_vox) return;
   const float inv_n = 1.f / (float)n_rows;
   const float inv_nm1 = 1.f / (float)(n_rows - 1);
+  const bool raw = (metric & 2) != 0;  // keep NaN / inf (ridge_corr_pred_torch does not scrub them)
+  metric &= 1;
   float qvar = 0.f;
   if (metric == 1) {
     const float sd = resp_std[v];
@@ -244,7 +249,7 @@ __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const f
       c = sqrtf(fabsf(rsq)) * (rsq > 0.f ? 1.f : (rsq < 0.f ? -1.f : 0.f));
       if (isnan(rsq)) c = rsq;
     }
-    c = nan_to_num(c);
+    if (!raw) c = nan_to_num(c);
     float* dst = corr + (long)g * ld_corr + v;
     *dst = accumulate ? *dst + c : c;
   }
@@ -320,7 +325,7 @@ extern "C" int lit_gather_normalize_rows(const float* src, long ld_src, const in
                                          const float* mean, const float* stdv, int mode, float eps, float* dst,
                                          float* dst_lo, long ld_dst, long n_rows_out, void* stream) {
   LIT_REQUIRE(ld_src >= cols && ld_dst >= cols && n_rows_out >= n_idx, "gather_normalize: bad extents");
-  LIT_REQUIRE(mode >= 0 && mode <= 2, "gather_normalize: mode must be 0, 1 or 2");
+  LIT_REQUIRE(mode >= 0 && mode <= 3, "gather_normalize: mode must be 0..3");
   LIT_REQUIRE(mode == 2 || stdv != nullptr, "gather_normalize: std required");
   if (n_rows_out == 0 || cols == 0) return LIT_OK;
   const bool vec = cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && aligned16(src) && aligned16(dst) &&
@@ -387,7 +392,8 @@ extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, l
                                  int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
                                  const float* resp_std, float* corr, long ld_corr, void* stream) {
   LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
-  LIT_REQUIRE(metric == 0 || (metric == 1 && resp_std), "corr_finalize: metric 1 (R^2) needs the response std");
+  LIT_REQUIRE(metric >= 0 && metric <= 3, "corr_finalize: metric must be 0..3");
+  LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize: the R^2 metric needs the response std");
   if (n_vox == 0 || n_groups == 0) return LIT_OK;
   corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
       dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, corr,

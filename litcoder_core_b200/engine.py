@@ -247,19 +247,27 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     # outer fit + test scoring
     # ------------------------------------------------------------------------------------------
+    def _shrunk_coefficients(self, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+        """(Z_o^T * keep / (lam_o + (alpha_v s0)^2))  (V_r x k split) and V_o (G, rows = eigenvectors)."""
+        ops = self.ops
+        Vt, G, lam = self._eig_ready(outer)
+        Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
+        del Vt
+        return ops.scale_rows_by_alpha(Zt, lam, alpha_v, cfg.normalpha, cfg.singcutoff), G
+
+    def _outer_weights(self, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+        """ridge_torch (ridge_regression.py:29-63) for every voxel at once -> W^T (V_r x p split)."""
+        ops = self.ops
+        ZS, G = self._shrunk_coefficients(outer, Ct_o, alpha_v, cfg)
+        Vmat = ops.transpose(G, split=True)  # (p x k): rows = features
+        return ops.gemm(ZS, Vmat, split_out=True)
+
     def _outer_fit_and_score(self, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
         """ridge_torch on the outer training set with the selected alphas, then test r / p."""
         ops = self.ops
         n_te = len(sp["test_rows"])
         te_dev = sp["test"]
-        Vt, G, lam = self._eig_ready(outer)
-        Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
-        del Vt
-        ZS = ops.scale_rows_by_alpha(Zt, lam, alpha_v, cfg.normalpha, cfg.singcutoff)  # (V_r x k)
-        del Zt
-        Vmat = ops.transpose(G, split=True)  # (p x k): rows = features
-        Wt = ops.gemm(ZS, Vmat, split_out=True)  # (V_r x p) voxel-major weights
-        del ZS, Vmat
+        Wt = self._outer_weights(outer, Ct_o, alpha_v, cfg)  # (V_r x p) voxel-major weights
         # test predictions, centred so that the fused epilogue yields Pearson's r directly
         rows_pad = -(-n_te // ops.TILE_N) * ops.TILE_N
         pm, _ = ops.col_stats(Xte_src, te_dev, n_te, ddof=0)
@@ -269,6 +277,63 @@ class RidgeCVEngine:
         parts = ops.gemm_corr(Wt, Pt, 1, rows_pad, Ytz)
         r, p = ops.pearson_finalize(parts, Wt.rows, n_te, cfg.p_round_f32)
         return Wt, r, p
+
+    # ------------------------------------------------------------------------------------------
+    # stand-alone ridge kernels of the reference (encoding/models/ridge_regression.py)
+    # ------------------------------------------------------------------------------------------
+    def _single_split(self, n_train: int, n_val: int, cfg: RidgeConfig, inner: bool = True):
+        """One staged plan whose outer training rows are [0, n_train) and whose test rows -- and, when
+        `inner`, the validation rows of a single inner fold on the same training rows -- follow them."""
+        tr = np.arange(n_train, dtype=np.int64)
+        va = np.arange(n_train, n_train + n_val, dtype=np.int64)
+        self._eig_jobs = 0
+        return self.stage_plans([FoldPlan(tr, va, [(tr, va)] if (inner and n_val) else [])], cfg)[0]
+
+    def ridge_corr(self, XX, YY, n_train: int, cfg: RidgeConfig):
+        """ridge_corr_torch (ridge_regression.py:66-141): XX / YY hold the training rows followed by the
+        prediction rows; returns the (n_alphas x V) score matrix (device)."""
+        ops = self.ops
+        sp = self._single_split(n_train, XX.rows - n_train, cfg)
+        outer, inners = self._design_side(XX, sp, cfg)
+        alphas = ops.upload_vector(np.asarray(cfg.alphas, dtype=np.float64), "f64")
+        corr, _ = self._inner_scores(XX, YY, sp, outer, inners, alphas, len(cfg.alphas), cfg)
+        self._eig_ready(outer)  # consume the (unused) outer ticket
+        return corr
+
+    def ridge_weights(self, X, Y, alpha_v, cfg: RidgeConfig):
+        """ridge_torch (ridge_regression.py:9-63): returns W^T (V x p, split pair) on the device."""
+        ops = self.ops
+        sp = self._single_split(X.rows, 0, cfg)
+        outer, _ = self._design_side(X, sp, cfg)
+        YoT = ops.gather_rows_T_split(Y, sp["train"], X.rows)
+        Ct_o = ops.gemm(YoT, outer["XtT"])
+        return self._outer_weights(outer, Ct_o, alpha_v, cfg)
+
+    def ridge_corr_pred(self, XX, YY, n_train: int, alpha_v, cfg: RidgeConfig):
+        """ridge_corr_pred_torch (ridge_regression.py:144-216): per-voxel alphas, no weights formed:
+        pred^T = (Z^T * d_v) (P V)^T reduced against the z-scored responses in the GEMM epilogue.
+        Returns the (1 x V) score (device); NaNs are kept, as in the reference."""
+        ops = self.ops
+        n_va = XX.rows - n_train
+        sp = self._single_split(n_train, n_va, cfg, inner=False)
+        outer, _ = self._design_side(XX, sp, cfg)
+        val = sp["test"]
+        YoT = ops.gather_rows_T_split(YY, sp["train"], n_train)
+        Ct_o = ops.gemm(YoT, outer["XtT"])
+        del YoT
+        ZS, G = self._shrunk_coefficients(outer, Ct_o, alpha_v, cfg)
+        rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
+        Pv = ops.gather_rows(XX, val, n_va, split=True)
+        L = ops.gemm(Pv, ops.split(G))  # (n_v x k)
+        lm, _ = ops.col_stats(L, None, n_va, ddof=0)
+        Lc = ops.gather_normalize(L, None, n_va, lm, None, 2, EPS, rows_out=rows_pad, split=True)
+        mean, std = ops.col_stats(YY, val, n_va, ddof=1)
+        Yz = ops.gather_normalize(YY, val, n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
+        parts = ops.gemm_corr(ZS, Lc, 1, rows_pad, Yz)
+        corr = ops.empty(1, YY.cols)
+        ops.corr_finalize(parts, rows_pad // ops.PART_N, 1, YY.cols, n_va, EPS, corr, accumulate=False,
+                          metric=(0 if cfg.use_corr else 1) | 2, resp_std=std)
+        return corr
 
     def _normalised(self, M, Mte_src, train_rows, train_dev, enabled: bool, same_source: bool):
         """DataNormalizer (ridge_utils.py:70-180): z-score a matrix (and its test source) with the

@@ -248,6 +248,39 @@ def ridge_weights(Rstim, Rresp, valphas, singcutoff=1e-30, normalpha=False) -> n
     return wt
 
 
+def ridge_corr_pred(Rstim, Pstim, Rresp, Presp, valphas, singcutoff=1e-30, use_corr=True, normalpha=True) -> np.ndarray:
+    """ridge_regression.ridge_corr_pred_torch (:144-216) -> (n_voxels,) float32; NaNs are NOT scrubbed."""
+    U, S, Vh = svd_truncated(Rstim, singcutoff)
+    valphas = np.asarray(valphas, dtype=F32)
+    nal = (valphas * F32(S[0])).astype(F32) if normalpha else valphas
+    UR = U.T @ Rresp.astype(F32, copy=False)
+    PVh = Pstim.astype(F32, copy=False) @ Vh.T
+    Presp = Presp.astype(F32, copy=False)
+    zP = z_score_f32(Presp)
+    Pvar = Presp.var(axis=0, ddof=1, dtype=F32)
+    corr = np.zeros(Rresp.shape[1], dtype=F32)
+    for ua in np.unique(nal):
+        sel = np.nonzero(nal == ua)[0]
+        D = (S / (S ** 2 + ua ** 2)).astype(F32)
+        pred = (PVh * D[None, :]) @ UR[:, sel]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if use_corr:
+                corr[sel] = (zP[:, sel] * z_score_f32(pred)).mean(axis=0, dtype=F32)
+            else:
+                rsq = 1 - (Presp[:, sel] - pred).var(axis=0, ddof=1, dtype=F32) / Pvar[sel]
+                corr[sel] = np.sqrt(np.abs(rsq)) * np.sign(rsq)
+    return corr
+
+
+def zs(v: np.ndarray) -> np.ndarray:
+    """encoding/utils.py:23-29 `zscore`: population std; zero-std columns are centred only."""
+    s = v.std(0)
+    m = v - v.mean(0)
+    nz = s != 0.0
+    m[:, nz] /= s[nz]
+    return m
+
+
 def find_best_alphas(X, Y, splits, alphas, single_alpha=False, normalpha=False, use_corr=True,
                      singcutoff=1e-10, return_corrs=False):
     """nested_cv._find_best_alphas (:334-415)."""

@@ -275,5 +275,41 @@ def main():
         print(f"  {f}: {os.path.getsize(os.path.join(OUT, f))} bytes")
 
 
+def extra_golden():
+    """ridge_corr_pred_torch and the trainers' zs() on the inputs already stored in ridge_kernels.npz
+    (kept separate so that the vectors above stay byte-identical when these are added)."""
+    import_reference()
+    import torch
+    from encoding.models.ridge_regression import ridge_corr_pred_torch
+    from encoding.utils import zs
+
+    torch.set_num_threads(4)
+    g = np.load(os.path.join(OUT, "ridge_kernels.npz"))
+    out = {}
+    with quiet():
+        for name in ("tall", "dupcol", "wide"):
+            X, Y, n = g[f"{name}__X"], g[f"{name}__Y"], int(g[f"{name}__n_train"])
+            for normalpha in (True, False):
+                va = torch.tensor(g[f"{name}_n{int(normalpha)}__valphas"])
+                for use_corr in (True, False):
+                    c = ridge_corr_pred_torch(torch.tensor(X[:n]), torch.tensor(X[n:]), torch.tensor(Y[:n]),
+                                              torch.tensor(Y[n:]), va, singcutoff=1e-10, use_corr=use_corr,
+                                              normalpha=normalpha).numpy()
+                    out[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corrpred"] = c
+    rng = np.random.default_rng(44)
+    Z = rng.standard_normal((57, 9)) * 3 + 2
+    Z[:, 4] = 1.5  # zero-variance column: centred only
+    out["zs__in64"], out["zs__out64"] = Z, zs(Z.copy())
+    Z32 = Z.astype(np.float32)
+    out["zs__in32"], out["zs__out32"] = Z32, zs(Z32.copy())
+    np.savez_compressed(os.path.join(OUT, "ridge_extra.npz"), **out)
+    print("ridge_extra.npz written")
+
+
 if __name__ == "__main__":
-    main()
+    if "--extra-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        extra_golden()
+    else:
+        main()
+        extra_golden()

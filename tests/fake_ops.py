@@ -138,6 +138,8 @@ class FakeOps:
             elif mode == 1:
                 sc = np.where(std > 0, F32(1.0 / math.sqrt(n - 1)) / std, np.nan).astype(F32)
                 x = x * sc[None, :]
+            elif mode == 3:
+                x = x * np.where(std != 0, F32(1) / std, F32(1)).astype(F32)[None, :]
         out = np.zeros((rows_out, src.cols), dtype=F32)
         out[:n] = x
         return FMat(out, split)
@@ -225,6 +227,7 @@ class FakeOps:
 
     def corr_finalize(self, parts, tiles_per_group, n_groups, n_vox, n_rows, eps, corr, accumulate, metric=0,
                       resp_std=None):
+        raw, metric = bool(metric & 2), metric & 1
         for g in range(n_groups):
             d = parts["dot"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
             q = parts["ssq"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
@@ -236,7 +239,7 @@ class FakeOps:
                     resvar = (qvar * F32(n_rows - 1) - 2 * d + q) / F32(n_rows - 1)
                     rsq = 1 - resvar / qvar
                     c = np.sqrt(np.abs(rsq)) * np.sign(rsq)
-            c = np.nan_to_num(c.astype(F32))
+            c = c.astype(F32) if raw else np.nan_to_num(c.astype(F32))
             corr.a[g] = corr.a[g] + c if accumulate else c
 
     def argmax_alpha(self, corr_sum, n_folds, alphas_dev, want_sums):

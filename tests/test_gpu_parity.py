@@ -438,3 +438,35 @@ def test_wide_design_matches_oracle(ops):
     assert np.abs(r[same] - ro[same]).max() < 1e-4, np.abs(r[same] - ro[same]).max()
     assert np.abs(w[:, same] - wo[:, same]).max() < 2e-4 * np.abs(wo).max()
     assert abs(m["n_significant"] - mo["n_significant"]) <= 2 + (~same).sum()
+
+
+@pytest.mark.parametrize("name", ["tall", "dupcol"])
+def test_ridge_functions_match_reference_golden(ops, name):
+    """ridge_torch / ridge_corr_torch / ridge_corr_pred_torch / zs drop-ins through the public API."""
+    import litcoder_core_b200 as L
+
+    g, e = load_golden("ridge_kernels.npz"), load_golden("ridge_extra.npz")
+    alphas = g["alphas"].tolist()
+    X, Y, n = g[f"{name}__X"], g[f"{name}__Y"], int(g[f"{name}__n_train"])
+    nonconst = Y[n:].std(0) > 0
+    for normalpha in (True, False):
+        tol = 5e-4 if (name != "tall" and not normalpha) else 5e-5
+        va = g[f"{name}_n{int(normalpha)}__valphas"]
+        for use_corr in (True, False):
+            out = L.ridge_corr_torch(X[:n], X[n:], Y[:n], Y[n:], alphas, singcutoff=1e-10, use_corr=use_corr,
+                                     normalpha=normalpha)
+            ref = g[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corr"]
+            cp = L.ridge_corr_pred_torch(X[:n], X[n:], Y[:n], Y[n:], va, singcutoff=1e-10, use_corr=use_corr,
+                                         normalpha=normalpha)
+            refp = e[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corrpred"]
+            ok = np.isfinite(refp) & nonconst
+            if not use_corr:
+                out, ref = np.sign(out) * out ** 2, np.sign(ref) * ref ** 2
+                cp, refp = np.sign(cp) * cp ** 2, np.sign(refp) * refp ** 2
+            np.testing.assert_allclose(out[:, nonconst], ref[:, nonconst], rtol=0, atol=tol)
+            np.testing.assert_allclose(cp[ok], refp[ok], rtol=0, atol=tol)
+        w = L.ridge_torch(X[:n], Y[:n], va, singcutoff=1e-10, normalpha=normalpha)
+        ref = g[f"{name}_n{int(normalpha)}__wt"]
+        assert np.abs(w - ref).max() <= (5e-3 if (name != "tall" and not normalpha) else 1e-4) * np.abs(ref).max()
+    np.testing.assert_allclose(L.zs(e["zs__in64"]), e["zs__out64"], atol=2e-6)
+    np.testing.assert_allclose(L.zs(e["zs__in32"]), e["zs__out32"], atol=2e-6)

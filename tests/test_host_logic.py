@@ -237,3 +237,45 @@ def test_engine_edge_cases_on_fake_ops():
     same[[7, 8]] = False  # the reference picks alphas for constant voxels from rounding noise
     assert same.mean() > 0.8
     np.testing.assert_allclose(r[same], np.asarray(mo["correlations"], dtype=np.float64)[same], atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------------ stand-alone ridge kernels
+@pytest.mark.parametrize("name", ["tall", "dupcol"])
+def test_ridge_functions_on_fake_ops_match_reference_golden(name):
+    g, e = load_golden("ridge_kernels.npz"), load_golden("ridge_extra.npz")
+    alphas = g["alphas"].tolist()
+    X, Y, n = g[f"{name}__X"], g[f"{name}__Y"], int(g[f"{name}__n_train"])
+    ops = FakeOps()
+    nonconst = Y[n:].std(0) > 0
+    for normalpha in (True, False):
+        tol = 2e-4 if (name != "tall" and not normalpha) else 3e-5
+        for use_corr in (True, False):
+            out = L.ridge_corr(X[:n], X[n:], Y[:n], Y[n:], alphas, singcutoff=1e-10, use_corr=use_corr,
+                               normalpha=normalpha, ops=ops)
+            ref = g[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corr"]
+            assert out.shape == ref.shape and out.dtype == np.float32
+            if not use_corr:
+                out, ref = np.sign(out) * out ** 2, np.sign(ref) * ref ** 2
+            np.testing.assert_allclose(out[:, nonconst], ref[:, nonconst], rtol=0, atol=tol)
+            va = g[f"{name}_n{int(normalpha)}__valphas"]
+            cp = L.ridge_corr_pred(X[:n], X[n:], Y[:n], Y[n:], va, singcutoff=1e-10, use_corr=use_corr,
+                                   normalpha=normalpha, ops=ops)
+            refp = e[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corrpred"]
+            ok = np.isfinite(refp) & nonconst
+            if not use_corr:
+                cp, refp = np.sign(cp) * cp ** 2, np.sign(refp) * refp ** 2
+            np.testing.assert_allclose(cp[ok], refp[ok], rtol=0, atol=tol)
+        w = L.ridge(X[:n], Y[:n], g[f"{name}_n{int(normalpha)}__valphas"], singcutoff=1e-10, normalpha=normalpha, ops=ops)
+        ref = g[f"{name}_n{int(normalpha)}__wt"]
+        assert w.shape == ref.shape and w.dtype == np.float32
+        assert np.abs(w - ref).max() <= (5e-3 if (name != "tall" and not normalpha) else 1e-4) * np.abs(ref).max()
+    z = L.zs(e["zs__in64"], ops=ops)
+    assert z.dtype == np.float64
+    np.testing.assert_allclose(z, e["zs__out64"], atol=2e-6)
+    np.testing.assert_allclose(L.zs(e["zs__in32"], ops=ops), e["zs__out32"], atol=2e-6)
+    # scalar alpha and torch tensors in -> torch tensor out
+    import torch
+
+    w1 = L.ridge_torch(torch.from_numpy(X[:n]), torch.from_numpy(Y[:n]), 10.0, ops=ops)
+    assert torch.is_tensor(w1) and tuple(w1.shape) == (X.shape[1], Y.shape[1])
+    np.testing.assert_allclose(w1.numpy(), O.ridge_weights(X[:n], Y[:n], 10.0), atol=1e-4 * np.abs(w1.numpy()).max())

@@ -112,6 +112,28 @@ def test_ridge_kernels_match_reference(name):
         assert np.abs(w - ref).max() <= tol * scale, (name, normalpha, np.abs(w - ref).max() / scale)
 
 
+@pytest.mark.parametrize("name", ["tall", "dupcol", "wide"])
+def test_ridge_corr_pred_and_zs_match_reference(name):
+    g, e = load_golden("ridge_kernels.npz"), load_golden("ridge_extra.npz")
+    X, Y, n = g[f"{name}__X"], g[f"{name}__Y"], int(g[f"{name}__n_train"])
+    for normalpha in (True, False):
+        va = g[f"{name}_n{int(normalpha)}__valphas"]
+        for use_corr in (True, False):
+            ref = e[f"{name}_n{int(normalpha)}_c{int(use_corr)}__corrpred"]
+            out = O.ridge_corr_pred(X[:n], X[n:], Y[:n], Y[n:], va, singcutoff=1e-10, use_corr=use_corr,
+                                    normalpha=normalpha)
+            ok = np.isfinite(ref) & (Y[n:].std(0) > 0)
+            np.testing.assert_array_equal(np.isnan(out), np.isnan(ref))
+            tol = 2e-4 if (name != "tall" and not normalpha) else 2e-5
+            if not use_corr:
+                out, ref = np.sign(out) * out ** 2, np.sign(ref) * ref ** 2
+            np.testing.assert_allclose(out[ok], ref[ok], rtol=0, atol=tol, err_msg=f"{name} {normalpha} {use_corr}")
+    np.testing.assert_allclose(O.zs(e["zs__in64"].copy()), e["zs__out64"], rtol=1e-13, atol=1e-13)
+    out32 = O.zs(e["zs__in32"].copy())
+    assert out32.dtype == np.float32
+    np.testing.assert_allclose(out32, e["zs__out32"], rtol=1e-6, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------ statistics
 def test_bh_known_answer():
     p = np.array([0.001, 0.008, 0.039, 0.041, 0.042, 0.06, 0.074, 0.205, 0.212, 0.216])
