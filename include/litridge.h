@@ -205,6 +205,26 @@ int lit_lanczos_downsample(const void* data, int dtype_in, long n_samples, long 
                            const double* data_times, const double* tr_times, long n_tr, double window, double cutoff,
                            int rectify, const int32_t* lo, const int32_t* hi, double* out, long ld_out, void* stream);
 
+/* Sinc resampling (interpdata.sincfun / sincinterp2D, :29-84): W[i][j] = 2B sin(2 pi B t)/(2 pi B t + 1e-20),
+ * t = tr_i - t_j, B = cutoff; zero for |t| > window / (2B) and, if causal, for t < 0; if renorm each row is
+ * divided by its sum unless that sum is exactly 0.  lo / hi as for Lanczos. */
+int lit_sinc_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                        const double* data_times, const double* tr_times, long n_tr, double window, double cutoff,
+                        int causal, int renorm, const int32_t* lo, const int32_t* hi, double* out, long ld_out,
+                        void* stream);
+/* Membership (CSR) row reduction: out[r][:] = sum_{e in [row_ptr[r], row_ptr[r+1])} w[e] * data[col_idx[e]][:]
+ * (w == NULL: 1; mean != 0: divided by the entry count); rows without entries are zero.  Device form of the
+ * rect / average / sum / last / legacy_* downsamplers (downsampling.py:24-319): the host builds only the
+ * integer membership lists. */
+int lit_csr_rows_apply(const void* data, int dtype_in, long ndim, long ld_data, const int32_t* row_ptr,
+                       const int32_t* col_idx, const double* weights, long n_rows_out, int mean, double* out,
+                       long ld_out, void* stream);
+/* Gabor transform magnitude (interpdata.gabor_xfm2D, :129-145; downsampling.py:159-166):
+ * out[i][d * n_freq + f] = | sum_j exp(-0.5 (t_j - tr_i)^2 / (2 sigma^2)) data[j][d] exp(i 2 pi f t_j) |. */
+int lit_gabor_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                         const double* data_times, const double* tr_times, long n_tr, const double* freqs, int n_freq,
+                         double sigma, double* out, long ld_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,29 +55,58 @@ __device__ __forceinline__ double lanczos_weight(double t, double window) {
   const double pit = pi * t;
   return window * sin(pit) * sin(pit / window) / (pi * pi * (t * t));
 }
+// interpdata.sincfun (:29-42) before renormalisation: B = cutoff, t = newtime - oldtime (seconds).
+__device__ __forceinline__ double sinc_weight(double t, double B, double window, int causal) {
+  const double two_pi = 6.283185307179586;
+  double v = 2.0 * B * sin(two_pi * B * t) / (two_pi * B * t + 1e-20);
+  if (fabs(t) > window / (2.0 * B)) v = 0.0;
+  if (causal && t < 0.0) v = 0.0;
+  return v;
+}
 
 // grid.x = TR index, grid.y = column tile.  The block first evaluates the weights of a chunk
 // of samples cooperatively into shared memory, then every thread accumulates its column(s).
-template <typename T, int CHUNK>
-__global__ void lanczos_kernel(const T* __restrict__ data, long n_samples, long ndim, long ld_data,
-                               const double* __restrict__ data_times, const double* __restrict__ tr_times,
-                               double window, double cutoff, int rectify, const int32_t* __restrict__ lo,
-                               const int32_t* __restrict__ hi, double* __restrict__ out, long ld_out) {
+// KIND 0: Lanczos (optionally rectified output); KIND 1: sinc (optionally causal / renormalised by the
+// row sum of the weights, which is accumulated in a first pass over the same sample range).
+template <typename T, int CHUNK, int KIND>
+__global__ void resample_kernel(const T* __restrict__ data, long n_samples, long ndim, long ld_data,
+                                const double* __restrict__ data_times, const double* __restrict__ tr_times,
+                                double window, double cutoff, int flag_a, int flag_b, const int32_t* __restrict__ lo,
+                                const int32_t* __restrict__ hi, double* __restrict__ out, long ld_out) {
   __shared__ double w_sh[CHUNK];
+  __shared__ double red_sh[32];
   const long i = blockIdx.x;
   const long c = (long)blockIdx.y * blockDim.x + threadIdx.x;
   const double tr = tr_times[i];
   const long j_begin = lo ? (long)lo[i] : 0;
   const long j_end = hi ? (long)hi[i] : n_samples;
+  const int rectify = KIND == 0 ? flag_a : 0;
+  const int causal = KIND == 1 ? flag_a : 0;
+  const int renorm = KIND == 1 ? flag_b : 0;
   // Without a band (lo == NULL) the kernel is the dense product of the reference: zero weights are
   // multiplied too, so that non-finite samples poison the output exactly as np.dot(sincmat, data) does.
   const bool dense = lo == nullptr;
+  double scale = 1.0;
+  if (renorm) {  // val = val / np.sum(val) unless the sum is exactly 0 (interpdata.py:36-37)
+    double part = 0.0;
+    for (long j = j_begin + threadIdx.x; j < j_end; j += blockDim.x)
+      part += sinc_weight(tr - data_times[j], cutoff, window, causal);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red_sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red_sh[w];
+    if (tot != 0.0) scale = 1.0 / tot;
+  }
   double acc = 0.0, acc_neg = 0.0;
   for (long j0 = j_begin; j0 < j_end; j0 += CHUNK) {
     const long cnt = (j_end - j0) < CHUNK ? (j_end - j0) : CHUNK;
     __syncthreads();
-    for (long q = threadIdx.x; q < cnt; q += blockDim.x)
-      w_sh[q] = lanczos_weight((tr - data_times[j0 + q]) * cutoff, window);
+    for (long q = threadIdx.x; q < cnt; q += blockDim.x) {
+      const double dt = tr - data_times[j0 + q];
+      w_sh[q] = KIND == 0 ? lanczos_weight(dt * cutoff, window) : sinc_weight(dt, cutoff, window, causal) * scale;
+    }
     __syncthreads();
     if (c < ndim) {
       for (long q = 0; q < cnt; ++q) {
@@ -103,6 +132,77 @@ __global__ void lanczos_kernel(const T* __restrict__ data, long n_samples, long 
       out[i * ld_out + c] = acc;
     }
   }
+}
+
+// out[r][c] = reduce over e in [row_ptr[r], row_ptr[r+1]) of weights[e] * data[col_idx[e]][c]
+// (weights == NULL: 1), divided by the number of entries when `mean`; rows without entries are zero.
+// This is the device form of the split-index / membership downsamplers of the reference
+// (downsampling.py:24-319): the host only builds the integer membership lists.
+// Unweighted rows are accumulated in the INPUT precision, one entry after the other, and divided by the
+// count in that precision: exactly what np.sum / np.mean(axis=0) do on a float32 (or float64) block, so the
+// result is bit-identical to the reference's before it is widened to float64.
+template <typename T>
+__global__ void csr_rows_kernel(const T* __restrict__ data, long ndim, long ld_data,
+                                const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                const double* __restrict__ weights, int mean, double* __restrict__ out, long ld_out) {
+  const long r = blockIdx.x;
+  const long c = (long)blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= ndim) return;
+  const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
+  double res;
+  if (weights) {
+    double acc = 0.0;
+    for (int e = e0; e < e1; ++e) acc = fma(weights[e], (double)data[(long)col_idx[e] * ld_data + c], acc);
+    if (mean && e1 > e0) acc /= (double)(e1 - e0);
+    res = acc;
+  } else {
+    T acc = (T)0;
+    for (int e = e0; e < e1; ++e) acc += data[(long)col_idx[e] * ld_data + c];
+    if (mean && e1 > e0) acc /= (T)(e1 - e0);
+    res = (double)acc;
+  }
+  out[r * ld_out + c] = res;
+}
+
+// Gabor transform magnitude (interpdata.gabor_xfm / gabor_xfm2D, :129-145, and downsampling.py:165):
+//   out[i][d * n_freq + f] = | sum_j exp(-0.5 (t_j - tr_i)^2 / (2 sigma^2)) * data[j][d] * exp(i 2 pi f t_j) |
+// grid.x = TR, grid.y = tile over the (d, f) pairs; the Gaussian envelope of a chunk of samples is staged
+// in shared memory, sin / cos are evaluated per (sample, frequency) by the owning thread.
+template <typename T, int CHUNK>
+__global__ void gabor_kernel(const T* __restrict__ data, long n_samples, long ndim, long ld_data,
+                             const double* __restrict__ data_times, const double* __restrict__ tr_times,
+                             const double* __restrict__ freqs, int n_freq, double sigma, double* __restrict__ out,
+                             long ld_out) {
+  __shared__ double g_sh[CHUNK];
+  __shared__ double t_sh[CHUNK];
+  const long i = blockIdx.x;
+  const long pair = (long)blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = pair < ndim * n_freq;
+  const long d = active ? pair / n_freq : 0;
+  const double f = active ? freqs[pair % n_freq] : 0.0;
+  const double tr = tr_times[i];
+  const double two_pi = 6.283185307179586;
+  double re = 0.0, im = 0.0;
+  for (long j0 = 0; j0 < n_samples; j0 += CHUNK) {
+    const long cnt = (n_samples - j0) < CHUNK ? (n_samples - j0) : CHUNK;
+    __syncthreads();
+    for (long q = threadIdx.x; q < cnt; q += blockDim.x) {
+      const double tj = data_times[j0 + q];
+      t_sh[q] = tj;
+      g_sh[q] = exp(-0.5 * (tj - tr) * (tj - tr) / (2.0 * sigma * sigma));
+    }
+    __syncthreads();
+    if (active) {
+      for (long q = 0; q < cnt; ++q) {
+        const double gx = g_sh[q] * (double)data[(j0 + q) * ld_data + d];
+        double sn, cs;
+        sincos(t_sh[q] * f * two_pi, &sn, &cs);
+        re = fma(cs, gx, re);
+        im = fma(sn, gx, im);
+      }
+    }
+  }
+  if (active) out[i * ld_out + pair] = sqrt(re * re + im * im);
 }
 
 }  // namespace lit
@@ -132,6 +232,26 @@ extern "C" int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, lon
   return LIT_OK;
 }
 
+template <int KIND>
+static int launch_resample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                           const double* data_times, const double* tr_times, long n_tr, double window, double cutoff,
+                           int flag_a, int flag_b, const int32_t* lo, const int32_t* hi, double* out, long ld_out,
+                           void* stream) {
+  const int block = ndim >= 256 ? 256 : (ndim >= 128 ? 128 : 64);
+  dim3 grid((unsigned)n_tr, (unsigned)((ndim + block - 1) / block));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype_in == 0)
+    resample_kernel<float, 256, KIND><<<grid, block, 0, s>>>((const float*)data, n_samples, ndim, ld_data, data_times,
+                                                             tr_times, window, cutoff, flag_a, flag_b, lo, hi, out,
+                                                             ld_out);
+  else
+    resample_kernel<double, 256, KIND><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data,
+                                                              data_times, tr_times, window, cutoff, flag_a, flag_b, lo,
+                                                              hi, out, ld_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
 extern "C" int lit_lanczos_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
                                       const double* data_times, const double* tr_times, long n_tr, double window,
                                       double cutoff, int rectify, const int32_t* lo, const int32_t* hi, double* out,
@@ -142,15 +262,62 @@ extern "C" int lit_lanczos_downsample(const void* data, int dtype_in, long n_sam
   LIT_REQUIRE((lo == nullptr) == (hi == nullptr), "lanczos: lo and hi must be given together");
   LIT_REQUIRE(n_tr <= 2147483647L, "lanczos: too many TRs");
   if (n_tr == 0 || ndim == 0) return LIT_OK;
+  return launch_resample<0>(data, dtype_in, n_samples, ndim, ld_data, data_times, tr_times, n_tr, window, cutoff,
+                            rectify, 0, lo, hi, out, ld_out, stream);
+}
+
+extern "C" int lit_sinc_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                                   const double* data_times, const double* tr_times, long n_tr, double window,
+                                   double cutoff, int causal, int renorm, const int32_t* lo, const int32_t* hi,
+                                   double* out, long ld_out, void* stream) {
+  LIT_REQUIRE(n_samples >= 0 && ndim >= 0 && n_tr >= 0, "sinc: negative extent");
+  LIT_REQUIRE(ld_data >= ndim && ld_out >= ndim, "sinc: pitch too small");
+  LIT_REQUIRE(dtype_in == 0 || dtype_in == 1, "sinc: dtype_in must be 0 (f32) or 1 (f64)");
+  LIT_REQUIRE((lo == nullptr) == (hi == nullptr), "sinc: lo and hi must be given together");
+  LIT_REQUIRE(n_tr <= 2147483647L, "sinc: too many TRs");
+  if (n_tr == 0 || ndim == 0) return LIT_OK;
+  return launch_resample<1>(data, dtype_in, n_samples, ndim, ld_data, data_times, tr_times, n_tr, window, cutoff, causal,
+                            renorm, lo, hi, out, ld_out, stream);
+}
+
+extern "C" int lit_csr_rows_apply(const void* data, int dtype_in, long ndim, long ld_data, const int32_t* row_ptr,
+                                  const int32_t* col_idx, const double* weights, long n_rows_out, int mean, double* out,
+                                  long ld_out, void* stream) {
+  LIT_REQUIRE(ndim >= 0 && n_rows_out >= 0 && ld_data >= ndim && ld_out >= ndim, "csr_rows: bad extents");
+  LIT_REQUIRE(dtype_in == 0 || dtype_in == 1, "csr_rows: dtype_in must be 0 (f32) or 1 (f64)");
+  LIT_REQUIRE(n_rows_out <= 2147483647L, "csr_rows: too many rows");
+  if (n_rows_out == 0 || ndim == 0) return LIT_OK;
   const int block = ndim >= 256 ? 256 : (ndim >= 128 ? 128 : 64);
-  dim3 grid((unsigned)n_tr, (unsigned)((ndim + block - 1) / block));
+  dim3 grid((unsigned)n_rows_out, (unsigned)((ndim + block - 1) / block));
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype_in == 0)
-    lanczos_kernel<float, 256><<<grid, block, 0, s>>>((const float*)data, n_samples, ndim, ld_data, data_times,
-                                                      tr_times, window, cutoff, rectify, lo, hi, out, ld_out);
+    csr_rows_kernel<float><<<grid, block, 0, s>>>((const float*)data, ndim, ld_data, row_ptr, col_idx, weights, mean,
+                                                  out, ld_out);
   else
-    lanczos_kernel<double, 256><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data, data_times,
-                                                       tr_times, window, cutoff, rectify, lo, hi, out, ld_out);
+    csr_rows_kernel<double><<<grid, block, 0, s>>>((const double*)data, ndim, ld_data, row_ptr, col_idx, weights, mean,
+                                                   out, ld_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_gabor_downsample(const void* data, int dtype_in, long n_samples, long ndim, long ld_data,
+                                    const double* data_times, const double* tr_times, long n_tr, const double* freqs,
+                                    int n_freq, double sigma, double* out, long ld_out, void* stream) {
+  LIT_REQUIRE(n_samples >= 0 && ndim >= 0 && n_tr >= 0 && n_freq >= 0, "gabor: negative extent");
+  LIT_REQUIRE(ld_data >= ndim && ld_out >= ndim * n_freq, "gabor: pitch too small");
+  LIT_REQUIRE(dtype_in == 0 || dtype_in == 1, "gabor: dtype_in must be 0 (f32) or 1 (f64)");
+  LIT_REQUIRE(n_tr <= 2147483647L, "gabor: too many TRs");
+  const long pairs = ndim * n_freq;
+  if (n_tr == 0 || pairs == 0) return LIT_OK;
+  const int block = pairs >= 256 ? 256 : (pairs >= 128 ? 128 : 64);
+  dim3 grid((unsigned)n_tr, (unsigned)((pairs + block - 1) / block));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype_in == 0)
+    gabor_kernel<float, 256><<<grid, block, 0, s>>>((const float*)data, n_samples, ndim, ld_data, data_times, tr_times,
+                                                    freqs, n_freq, sigma, out, ld_out);
+  else
+    gabor_kernel<double, 256><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data, data_times,
+                                                     tr_times, freqs, n_freq, sigma, out, ld_out);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

@@ -621,35 +621,88 @@ class DeviceOps:
         t.from_numpy(out_h).copy_(d_out)
         return out_h
 
-    def lanczos_downsample(self, data: np.ndarray, data_times: np.ndarray, tr_times: np.ndarray, window: float,
-                           cutoff: float, rectify: bool, lo: Optional[np.ndarray], hi: Optional[np.ndarray]) -> np.ndarray:
-        t = self.torch
+    def _feature_in(self, data: np.ndarray):
         data = np.ascontiguousarray(data)
         if data.dtype not in (np.float32, np.float64):
             data = data.astype(np.float64)
+        self.h2d_bytes += data.nbytes
+        return data, self.torch.from_numpy(data).to(self.device), 0 if data.dtype == np.float32 else 1
+
+    def _feature_out(self, d_out) -> np.ndarray:
+        out_h = np.empty(tuple(d_out.shape), dtype=np.float64)
+        self.torch.from_numpy(out_h).copy_(d_out)
+        self.d2h_bytes += out_h.nbytes
+        return out_h
+
+    def resample(self, kind: str, data: np.ndarray, data_times: np.ndarray, tr_times: np.ndarray, window: float,
+                 cutoff: float, flag_a: bool, flag_b: bool, lo: Optional[np.ndarray], hi: Optional[np.ndarray]) -> np.ndarray:
+        """Weighted resampling onto the TR grid.  kind "lanczos": flag_a = rectify; kind "sinc": flag_a = causal,
+        flag_b = renorm.  Host arrays in, host float64 array out."""
+        t = self.torch
         n_s, ndim = data.shape
         n_tr = len(tr_times)
-        width = (2 if rectify else 1) * ndim
-        out_h = np.empty((n_tr, width), dtype=np.float64)
-        if out_h.size == 0:
-            return out_h
+        width = (2 if (kind == "lanczos" and flag_a) else 1) * ndim
+        if n_tr * width == 0:
+            return np.empty((n_tr, width), dtype=np.float64)
         if n_s == 0:
-            out_h[:] = 0.0
-            return out_h
-        d_data = t.from_numpy(data).to(self.device)
+            return np.zeros((n_tr, width), dtype=np.float64)
+        data, d_data, dt = self._feature_in(data)
         d_dt = self.upload_vector(data_times, "f64")
         d_tr = self.upload_vector(tr_times, "f64")
         d_lo = self.upload_vector(lo, "i32") if lo is not None else None
         d_hi = self.upload_vector(hi, "i32") if hi is not None else None
         d_out = t.empty((n_tr, width), dtype=t.float64, device=self.device)
-        check(self.lib.lit_lanczos_downsample(
-            _vp(d_data.data_ptr()), 0 if data.dtype == np.float32 else 1, n_s, ndim, ndim, _vp(d_dt.data_ptr()),
-            _vp(d_tr.data_ptr()), n_tr, float(window), float(cutoff), int(bool(rectify)),
-            _vp(d_lo.data_ptr() if d_lo is not None else 0), _vp(d_hi.data_ptr() if d_hi is not None else 0),
-            _vp(d_out.data_ptr()), width, _vp(self.stream)), "lanczos_downsample")
+        common = (_vp(d_data.data_ptr()), dt, n_s, ndim, ndim, _vp(d_dt.data_ptr()), _vp(d_tr.data_ptr()), n_tr,
+                  float(window), float(cutoff))
+        tail = (_vp(d_lo.data_ptr() if d_lo is not None else 0), _vp(d_hi.data_ptr() if d_hi is not None else 0),
+                _vp(d_out.data_ptr()), width, _vp(self.stream))
+        if kind == "lanczos":
+            check(self.lib.lit_lanczos_downsample(*common, int(bool(flag_a)), *tail), "lanczos_downsample")
+        elif kind == "sinc":
+            check(self.lib.lit_sinc_downsample(*common, int(bool(flag_a)), int(bool(flag_b)), *tail), "sinc_downsample")
+        else:
+            raise ValueError(f"unknown resampling kind {kind}")
         self.launches += 1
-        t.from_numpy(out_h).copy_(d_out)
-        return out_h
+        return self._feature_out(d_out)
+
+    def lanczos_downsample(self, data, data_times, tr_times, window, cutoff, rectify, lo, hi) -> np.ndarray:
+        return self.resample("lanczos", data, data_times, tr_times, window, cutoff, rectify, False, lo, hi)
+
+    def csr_rows_apply(self, data: np.ndarray, row_ptr: np.ndarray, col_idx: np.ndarray,
+                       weights: Optional[np.ndarray], mean: bool) -> np.ndarray:
+        """out[r] = (mean of | sum of) weights[e] * data[col_idx[e]] over the entries of row r (float64)."""
+        t = self.torch
+        n_out, ndim = len(row_ptr) - 1, data.shape[1]
+        if n_out * ndim == 0:
+            return np.zeros((n_out, ndim), dtype=np.float64)
+        data, d_data, dt = self._feature_in(data)
+        d_rp = self.upload_vector(row_ptr, "i32")
+        d_ci = self.upload_vector(col_idx, "i32")
+        d_w = self.upload_vector(weights, "f64") if weights is not None else None
+        d_out = t.empty((n_out, ndim), dtype=t.float64, device=self.device)
+        check(self.lib.lit_csr_rows_apply(_vp(d_data.data_ptr()), dt, ndim, ndim, _vp(d_rp.data_ptr()),
+                                          _vp(d_ci.data_ptr()), _vp(d_w.data_ptr() if d_w is not None else 0), n_out,
+                                          int(bool(mean)), _vp(d_out.data_ptr()), ndim, _vp(self.stream)), "csr_rows_apply")
+        self.launches += 1
+        return self._feature_out(d_out)
+
+    def gabor_downsample(self, data: np.ndarray, data_times: np.ndarray, tr_times: np.ndarray, freqs: np.ndarray,
+                         sigma: float) -> np.ndarray:
+        t = self.torch
+        n_s, ndim = data.shape
+        n_tr, n_f = len(tr_times), len(freqs)
+        if n_tr * ndim * n_f == 0:
+            return np.zeros((n_tr, ndim * n_f), dtype=np.float64)
+        data, d_data, dt = self._feature_in(data)
+        d_dt = self.upload_vector(data_times, "f64")
+        d_tr = self.upload_vector(tr_times, "f64")
+        d_f = self.upload_vector(freqs, "f64")
+        d_out = t.empty((n_tr, ndim * n_f), dtype=t.float64, device=self.device)
+        check(self.lib.lit_gabor_downsample(_vp(d_data.data_ptr()), dt, n_s, ndim, ndim, _vp(d_dt.data_ptr()),
+                                            _vp(d_tr.data_ptr()), n_tr, _vp(d_f.data_ptr()), n_f, float(sigma),
+                                            _vp(d_out.data_ptr()), ndim * n_f, _vp(self.stream)), "gabor_downsample")
+        self.launches += 1
+        return self._feature_out(d_out)
 
 
 _default_ops: Optional[DeviceOps] = None

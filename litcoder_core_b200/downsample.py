@@ -9,9 +9,10 @@ of each TR are read (lit_lanczos_downsample).
 
 Parameter validation follows the reference: required / optional keyword table per method,
 unknown keywords are dropped silently (downsampling.py:361-393), unknown methods and missing
-required parameters raise ValueError.  The other nine methods of the reference are registered so
-that `available_methods` / `get_method_params` answer identically, but they are not on the B200 path
-yet and raise NotImplementedError instead of silently running on the CPU.
+required parameters raise ValueError.  The other nine methods run on the device too:
+`sinc` shares the resampling kernel (lit_sinc_downsample), `gabor` has its own (lit_gabor_downsample), and
+the membership-based ones (`rect`, `average`, `sum`, `last`, `legacy_*`) reduce rows through a CSR kernel
+(lit_csr_rows_apply) -- for those the host only builds the integer membership lists.
 """
 from __future__ import annotations
 
@@ -84,12 +85,7 @@ class Downsampler:
                    **kwargs) -> np.ndarray:
         """Downsample `data` (n_samples, n_features) sampled at `data_times` onto `tr_times`."""
         params = self._validate_method_params(method, **kwargs)
-        fn = self._methods[method]
-        if fn is None:
-            raise NotImplementedError(
-                f"downsampling method '{method}' is not implemented on the B200 path (only 'lanczos' is); "
-                "litcoder_core_b200 has no CPU fallback")
-        return fn(data, data_times, tr_times, **params)
+        return self._methods[method](data, data_times, tr_times, **params)
 
     @property
     def available_methods(self) -> List[str]:
@@ -118,3 +114,90 @@ class Downsampler:
             lo = hi = None  # 0 * inf / 0 * nan must poison the output exactly as the dense product does
         return self._get_ops().lanczos_downsample(data, data_times, tr_times, float(window), cutoff, bool(rectify), lo,
                                                   hi)
+
+    def _sinc(self, data, data_times, tr_times, window=1, cutoff_mult=1.0, causal=False, renorm=True) -> np.ndarray:
+        """interpdata.sincinterp2D (:66-84): rows of sinc weights, optionally causal / renormalised."""
+        data = np.asarray(data)
+        data_times = np.ascontiguousarray(np.asarray(data_times, dtype=np.float64))
+        tr_times = np.ascontiguousarray(np.asarray(tr_times, dtype=np.float64))
+        if len(data_times) != data.shape[0]:
+            raise ValueError(f"shapes ({len(tr_times)},{len(data_times)}) and {data.shape} not aligned")
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cutoff = float(1 / np.mean(np.diff(tr_times)) * cutoff_mult) if len(tr_times) > 1 else float("nan")
+        lo = hi = None
+        if np.isfinite(cutoff) and cutoff != 0 and np.isfinite(window):
+            lo, hi = lanczos_band(data_times, tr_times, float(window) / 2.0, cutoff)  # |t| <= window / (2 B)
+        if lo is not None and data.dtype.kind == "f" and not np.isfinite(data).all():
+            lo = hi = None
+        return self._get_ops().resample("sinc", data, data_times, tr_times, float(window), cutoff, bool(causal),
+                                        bool(renorm), lo, hi)
+
+    def _gabor(self, data, data_times, tr_times, freqs=None, sigma=None) -> np.ndarray:
+        """np.abs(interpdata.gabor_xfm2D(data.T, ...)).T (downsampling.py:159-166): (n_TR, n_features * n_freqs)."""
+        data = np.asarray(data)
+        return self._get_ops().gabor_downsample(data, np.ascontiguousarray(np.asarray(data_times, dtype=np.float64)),
+                                                np.ascontiguousarray(np.asarray(tr_times, dtype=np.float64)),
+                                                np.ascontiguousarray(np.asarray(freqs, dtype=np.float64)), float(sigma))
+
+    # membership-based methods: the host builds integer (row_ptr, col_idx) lists, the device reduces the rows
+    def _csr(self, data, groups: List[np.ndarray], mean: bool) -> np.ndarray:
+        data = np.asarray(data)
+        counts = np.fromiter((len(g) for g in groups), dtype=np.int64, count=len(groups))
+        row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        col_idx = np.concatenate(groups).astype(np.int64) if len(groups) and row_ptr[-1] else np.zeros(0, np.int64)
+        return self._get_ops().csr_rows_apply(data, row_ptr, col_idx, None, mean)
+
+    def _rect(self, data, data_times, tr_times) -> np.ndarray:
+        """RectangularDownsampler (downsampling.py:24-38): mean of the samples in [t - TR/2, t + TR/2)."""
+        data_times = np.asarray(data_times, dtype=np.float64)
+        tr_times = np.asarray(tr_times, dtype=np.float64)
+        with np.errstate(invalid="ignore"):
+            tr = np.mean(np.diff(tr_times)) if len(tr_times) > 1 else np.nan
+        if len(data_times) and np.all(np.diff(data_times) >= 0) and np.isfinite(tr):
+            lo = np.searchsorted(data_times, tr_times - tr / 2, side="left")
+            hi = np.searchsorted(data_times, tr_times + tr / 2, side="left")
+            groups = [np.arange(a, max(a, b)) for a, b in zip(lo, hi)]
+        else:
+            groups = [np.flatnonzero((data_times >= t - tr / 2) & (data_times < t + tr / 2)) for t in tr_times]
+        return self._csr(data, groups, mean=True)
+
+    @staticmethod
+    def _split_groups(split_indices, what: str) -> List[np.ndarray]:
+        """Words of each TR for the split-index methods (downsampling.py:41-135, 232-279)."""
+        if split_indices is None:
+            raise ValueError(f"split_indices must be provided for {what} downsampling")
+        arr = np.asarray(split_indices, dtype=np.int64)
+        n_trs = int(arr.max()) + 1 if len(arr) else 0
+        order = np.argsort(arr, kind="stable")
+        order = order[arr[order] >= 0]
+        bounds = np.searchsorted(arr[order], np.arange(n_trs + 1), side="left")
+        return [order[bounds[i]:bounds[i + 1]] for i in range(n_trs)]
+
+    def _average(self, data, data_times=None, tr_times=None, split_indices=None) -> np.ndarray:
+        return self._csr(data, self._split_groups(split_indices, "average"), mean=True)
+
+    def _sum(self, data, data_times=None, tr_times=None, split_indices=None) -> np.ndarray:
+        return self._csr(data, self._split_groups(split_indices, "sum"), mean=False)
+
+    def _last(self, data, data_times=None, tr_times=None, split_indices=None) -> np.ndarray:
+        groups = self._split_groups(split_indices, "last point")
+        return self._csr(data, [g[-1:] for g in groups], mean=False)
+
+    @staticmethod
+    def _legacy_groups(n_rows: int, split_indices) -> List[np.ndarray]:
+        """np.split(data, split_indices) as index lists (downsampling.py:169-230, 282-319)."""
+        if split_indices is None:
+            raise ValueError("split_indices must be provided for Legacy downsampling")
+        cuts = [0] + [int(i) for i in split_indices] + [n_rows]
+        rows = np.arange(n_rows, dtype=np.int64)
+        return [rows[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+
+    def _legacy_average(self, data, data_times, tr_times, split_indices=None) -> np.ndarray:
+        return self._csr(data, self._legacy_groups(np.asarray(data).shape[0], split_indices), mean=True)
+
+    def _legacy_sum(self, data, data_times, tr_times, split_indices=None) -> np.ndarray:
+        return self._csr(data, self._legacy_groups(np.asarray(data).shape[0], split_indices), mean=False)
+
+    def _legacy_last(self, data, data_times, tr_times, split_indices=None) -> np.ndarray:
+        groups = self._legacy_groups(np.asarray(data).shape[0], split_indices)
+        return self._csr(data, [g[-1:] for g in groups], mean=False)

@@ -76,6 +76,73 @@ def lanczos_interp2d(data, oldtime, newtime, window=3, cutoff_mult=1.0, rectify=
 
 
 # ----------------------------------------------------------------------------------------------
+# The other downsamplers of the facade  (encoding/downsample/downsampling.py:24-319, interpdata.py:29-145)
+# ----------------------------------------------------------------------------------------------
+def downsample_rect(data, data_times, tr_times) -> np.ndarray:
+    """RectangularDownsampler (:24-38)."""
+    out = np.zeros((len(tr_times), data.shape[1]))
+    tr = np.mean(np.diff(tr_times))
+    for i, t in enumerate(tr_times):
+        mask = (data_times >= t - tr / 2) & (data_times < t + tr / 2)
+        if np.any(mask):
+            out[i] = np.mean(data[mask], axis=0)
+    return out
+
+
+def downsample_by_tr(data, split_indices, how: str) -> np.ndarray:
+    """Average / Sum / LastPoint downsamplers (:41-135, 232-279): words grouped by their TR index."""
+    arr = np.asarray(split_indices)
+    n_trs = int(arr.max()) + 1
+    out = np.zeros((n_trs, data.shape[1]))
+    for tr in range(n_trs):
+        idx = np.flatnonzero(arr == tr)
+        if len(idx):
+            out[tr] = {"average": lambda r: np.mean(r, axis=0), "sum": lambda r: np.sum(r, axis=0),
+                       "last": lambda r: r[-1]}[how](data[idx])
+    return out
+
+
+def downsample_legacy(data, split_indices, how: str) -> np.ndarray:
+    """Legacy average / sum / last (:169-230, 282-319): chunks of np.split(data, split_indices)."""
+    out = np.zeros((len(split_indices) + 1, data.shape[1]))
+    for ci, chunk in enumerate(np.split(data, split_indices)):
+        if len(chunk):
+            out[ci] = {"average": lambda r: np.mean(r, axis=0), "sum": lambda r: np.sum(r, axis=0),
+                       "last": lambda r: r[-1]}[how](chunk)
+    return out
+
+
+def sinc_interp2d(data, oldtime, newtime, cutoff_mult=1.0, window=1, causal=False, renorm=True) -> np.ndarray:
+    """interpdata.sincfun / sincinterp2D (:29-42, 66-84)."""
+    B = 1 / np.mean(np.diff(newtime)) * cutoff_mult
+    W = np.zeros((len(newtime), len(oldtime)))
+    for i in range(len(newtime)):
+        t = newtime[i] - oldtime
+        val = 2 * B * np.sin(2 * np.pi * B * t) / (2 * np.pi * B * t + 1e-20)
+        val[np.abs(t) > window / (2 * B)] = 0
+        if causal:
+            val[t < 0] = 0
+        if not np.sum(val) == 0.0 and renorm:
+            val = val / np.sum(val)
+        W[i] = val
+    return W @ data
+
+
+def gabor_downsample(data, oldtimes, newtimes, freqs, sigma) -> np.ndarray:
+    """np.abs(interpdata.gabor_xfm2D(data.T, ...)).T (:129-145; downsampling.py:159-166)."""
+    sinv = np.vstack([np.sin(oldtimes * f * 2 * np.pi) for f in freqs])
+    cosv = np.vstack([np.cos(oldtimes * f * 2 * np.pi) for f in freqs])
+    blocks = []
+    for d in data.T:
+        out = np.zeros((len(newtimes), len(freqs)), dtype=np.complex128)
+        for ti, t in enumerate(newtimes):
+            g = np.exp(-0.5 * (oldtimes - t) ** 2 / (2 * sigma ** 2)) * d
+            out[ti] = cosv @ g + 1j * (sinv @ g)
+        blocks.append(out.T)
+    return np.abs(np.vstack(blocks)).T
+
+
+# ----------------------------------------------------------------------------------------------
 # Fold construction  (encoding/models/folding.py:8-255)
 # ----------------------------------------------------------------------------------------------
 def _kfold_contiguous(n: int, k: int):

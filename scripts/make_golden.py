@@ -305,6 +305,49 @@ def extra_golden():
     np.savez_compressed(os.path.join(OUT, "ridge_extra.npz"), **out)
     print("ridge_extra.npz written")
 
+    # ---- the nine non-Lanczos downsamplers of the facade (downsampling.py:24-319)
+    from encoding.downsample.downsampling import Downsampler
+
+    ds = Downsampler()
+    rng = np.random.default_rng(55)
+    n_s, n_tr, D = 260, 40, 6
+    tr_times = np.arange(n_tr) * 2.0 + 1.0
+    times = np.sort(np.cumsum(rng.exponential(0.33, size=n_s)))
+    times[5] = tr_times[2] - 1.0  # exactly on a rect-window edge
+    times = np.sort(times)
+    unsorted = rng.permutation(times)
+    d32 = rng.standard_normal((n_s, D)).astype(np.float32)
+    d64 = rng.standard_normal((n_s, D))
+    split_tr = np.minimum((times // 2.0).astype(int), n_tr - 1)  # TR membership of each word (some TRs empty)
+    split_tr[split_tr == 7] = 8
+    cuts = np.sort(rng.choice(np.arange(1, n_s), size=30, replace=False))
+    cuts[3] = cuts[2]  # an empty chunk
+    cases = {
+        "rect_sorted32": ("rect", d32, times, {}),
+        "rect_unsorted64": ("rect", d64, unsorted, {}),
+        "sinc_w3": ("sinc", d32, times, dict(window=3, cutoff_mult=1.0)),
+        "sinc_w2_causal_c05": ("sinc", d64, times, dict(window=2, cutoff_mult=0.5, causal=True)),
+        "sinc_w3_norenorm_unsorted": ("sinc", d32, unsorted, dict(window=3, cutoff_mult=1.0, renorm=False)),
+        "average": ("average", d32, times, dict(split_indices=split_tr.tolist())),
+        "sum": ("sum", d64, times, dict(split_indices=split_tr.tolist())),
+        "last": ("last", d32, times, dict(split_indices=split_tr.tolist())),
+        "legacy_average": ("legacy_average", d32, times, dict(split_indices=cuts)),
+        "legacy_sum": ("legacy_sum", d64, times, dict(split_indices=cuts)),
+        "legacy_last": ("legacy_last", d32, times, dict(split_indices=cuts)),
+        "gabor": ("gabor", d32[:, :3], times, dict(freqs=[0.05, 0.11, 0.3], sigma=1.5)),
+    }
+    dsx = {"tr_times": tr_times, "split_tr": split_tr, "cuts": cuts}
+    with quiet():
+        for name, (method, data, dt, kw) in cases.items():
+            dsx[f"{name}__data"], dsx[f"{name}__data_times"] = data, dt
+            dsx[f"{name}__method"] = np.asarray(method)
+            for k, v in kw.items():
+                if k != "split_indices":
+                    dsx[f"{name}__kw_{k}"] = np.asarray(v)
+            dsx[f"{name}__out"] = ds.downsample(data, dt, tr_times, method=method, **kw)
+    np.savez_compressed(os.path.join(OUT, "downsample_extra.npz"), **dsx)
+    print("downsample_extra.npz written")
+
 
 if __name__ == "__main__":
     if "--extra-only" in sys.argv:

@@ -318,20 +318,56 @@ class FakeOps:
                     out[t, i * ndim:(i + 1) * ndim] = stim[src]
         return out
 
-    def lanczos_downsample(self, data, data_times, tr_times, window, cutoff, rectify, lo, hi):
+    def resample(self, kind, data, data_times, tr_times, window, cutoff, flag_a, flag_b, lo, hi):
         data = np.asarray(data, dtype=np.float64)
         n_tr = len(tr_times)
-        outs = []
+        rectify = kind == "lanczos" and flag_a
         parts = [np.clip(data, -np.inf, 0), np.clip(data, 0, np.inf)] if rectify else [data]
+        outs = []
         for part in parts:
             out = np.zeros((n_tr, data.shape[1]))
             for i in range(n_tr):
                 j0, j1 = (0, len(data_times)) if lo is None else (int(lo[i]), int(hi[i]))
-                t = (tr_times[i] - data_times[j0:j1]) * cutoff
+                dt = tr_times[i] - data_times[j0:j1]
                 with np.errstate(divide="ignore", invalid="ignore"):
-                    w = window * np.sin(np.pi * t) * np.sin(np.pi * t / window) / (np.pi ** 2 * t ** 2)
-                w[t == 0] = 1.0
-                w[np.abs(t) > window] = 0.0
+                    if kind == "lanczos":
+                        t = dt * cutoff
+                        w = window * np.sin(np.pi * t) * np.sin(np.pi * t / window) / (np.pi ** 2 * t ** 2)
+                        w[t == 0] = 1.0
+                        w[np.abs(t) > window] = 0.0
+                    else:
+                        w = 2 * cutoff * np.sin(2 * np.pi * cutoff * dt) / (2 * np.pi * cutoff * dt + 1e-20)
+                        w[np.abs(dt) > window / (2 * cutoff)] = 0
+                        if flag_a:
+                            w[dt < 0] = 0
+                        if flag_b and w.sum() != 0.0:
+                            w = w / w.sum()
                 out[i] = w @ part[j0:j1]
             outs.append(out)
         return np.hstack(outs)
+
+    def lanczos_downsample(self, data, data_times, tr_times, window, cutoff, rectify, lo, hi):
+        return self.resample("lanczos", data, data_times, tr_times, window, cutoff, rectify, False, lo, hi)
+
+    def csr_rows_apply(self, data, row_ptr, col_idx, weights, mean):
+        data = np.asarray(data)
+        if data.dtype not in (np.float32, np.float64) or weights is not None:
+            data = data.astype(np.float64)
+        out = np.zeros((len(row_ptr) - 1, data.shape[1]))
+        for r in range(len(row_ptr) - 1):
+            e = slice(int(row_ptr[r]), int(row_ptr[r + 1]))
+            if e.stop > e.start:
+                rows = data[np.asarray(col_idx[e], dtype=np.int64)]
+                if weights is not None:
+                    rows = rows * np.asarray(weights[e])[:, None]
+                out[r] = rows.mean(0) if mean else rows.sum(0)
+        return out
+
+    def gabor_downsample(self, data, data_times, tr_times, freqs, sigma):
+        data = np.asarray(data, dtype=np.float64)
+        out = np.zeros((len(tr_times), data.shape[1] * len(freqs)))
+        phase = np.exp(1j * 2 * np.pi * np.outer(np.asarray(freqs, dtype=np.float64), data_times))  # (F, n_s)
+        for i, t in enumerate(tr_times):
+            g = np.exp(-0.5 * (data_times - t) ** 2 / (2 * sigma ** 2))
+            out[i] = np.abs((phase * g[None, :]) @ data).T.reshape(-1)  # (F, D) -> d-major, f-minor
+        return out

@@ -470,3 +470,19 @@ def test_ridge_functions_match_reference_golden(ops, name):
         assert np.abs(w - ref).max() <= (5e-3 if (name != "tall" and not normalpha) else 1e-4) * np.abs(ref).max()
     np.testing.assert_allclose(L.zs(e["zs__in64"]), e["zs__out64"], atol=2e-6)
     np.testing.assert_allclose(L.zs(e["zs__in32"]), e["zs__out32"], atol=2e-6)
+
+
+def test_other_downsamplers_match_reference_golden(ops):
+    """rect / sinc / average / sum / last / legacy_* / gabor on the device against the reference's outputs."""
+    import litcoder_core_b200 as L
+    from test_oracle_golden import _run_extra_downsampler
+
+    ds = L.Downsampler()
+    g = load_golden("downsample_extra.npz")
+    for name in _cases(g, "__out"):
+        out, ref = _run_extra_downsampler(lambda m, d, t, tr, kw: ds.downsample(d, t, tr, method=m, **kw), g, name)
+        assert out.shape == ref.shape and out.dtype == np.float64, name
+        np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-9 * max(1.0, np.abs(ref).max()), err_msg=name)
+        assert np.abs(out - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), name  # what fp64 actually delivers
+        if not name.startswith(("sinc", "gabor")):
+            np.testing.assert_array_equal(out, ref, err_msg=name)  # membership reductions are bit-exact

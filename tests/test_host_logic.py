@@ -279,3 +279,24 @@ def test_ridge_functions_on_fake_ops_match_reference_golden(name):
     w1 = L.ridge_torch(torch.from_numpy(X[:n]), torch.from_numpy(Y[:n]), 10.0, ops=ops)
     assert torch.is_tensor(w1) and tuple(w1.shape) == (X.shape[1], Y.shape[1])
     np.testing.assert_allclose(w1.numpy(), O.ridge_weights(X[:n], Y[:n], 10.0), atol=1e-4 * np.abs(w1.numpy()).max())
+
+
+# ------------------------------------------------------------------------------------------ the other downsamplers
+def test_other_downsamplers_on_fake_ops_match_reference_golden():
+    from test_oracle_golden import _run_extra_downsampler
+
+    ds = L.Downsampler(ops=FakeOps())
+    g = load_golden("downsample_extra.npz")
+    names = _cases(g, "__out")
+    assert len(names) == 12
+    for name in names:
+        out, ref = _run_extra_downsampler(lambda m, d, t, tr, kw: ds.downsample(d, t, tr, method=m, **kw), g, name)
+        assert out.shape == ref.shape and out.dtype == np.float64, name
+        np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-11, err_msg=name)
+        if not name.startswith(("sinc", "gabor")):
+            np.testing.assert_array_equal(out, ref, err_msg=name)  # membership reductions are bit-exact
+    for method, msg in [("average", "average"), ("sum", "sum"), ("last", "last point"), ("legacy_sum", "Legacy")]:
+        with pytest.raises(ValueError, match=f"split_indices must be provided for {msg} downsampling"):
+            ds.downsample(np.zeros((4, 2)), np.arange(4.0), np.arange(2.0), method=method, split_indices=None)
+    with pytest.raises(ValueError, match="Required parameter 'freqs' missing"):
+        ds.downsample(np.zeros((4, 2)), np.arange(4.0), np.arange(2.0), method="gabor", sigma=1.0)

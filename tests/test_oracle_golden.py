@@ -57,6 +57,38 @@ def test_lanczos_kernel_known_answers():
     assert v[4] < 0 and abs(v[4] + 0.1350949) < 1e-6  # negative side lobe at 1.5 lobes
 
 
+def _run_extra_downsampler(fn, g, name):
+    method = str(g[f"{name}__method"])
+    data, dt, tr = g[f"{name}__data"], g[f"{name}__data_times"], g["tr_times"]
+    kw = {k.split("__kw_")[1]: g[k] for k in g.files if k.startswith(f"{name}__kw_")}
+    kw = {k: (v.tolist() if v.ndim else v.item()) for k, v in kw.items()}
+    if method in ("average", "sum", "last"):
+        kw["split_indices"] = g["split_tr"].tolist()
+    if method.startswith("legacy"):
+        kw["split_indices"] = g["cuts"]
+    return fn(method, data, dt, tr, kw), g[f"{name}__out"]
+
+
+def _oracle_downsample(method, data, dt, tr, kw):
+    if method == "rect":
+        return O.downsample_rect(data, dt, tr)
+    if method == "sinc":
+        return O.sinc_interp2d(data, dt, tr, **kw)
+    if method == "gabor":
+        return O.gabor_downsample(data, dt, tr, **kw)
+    if method.startswith("legacy_"):
+        return O.downsample_legacy(data, kw["split_indices"], method.split("_")[1])
+    return O.downsample_by_tr(data, kw["split_indices"], method)
+
+
+def test_other_downsamplers_match_reference():
+    g = load_golden("downsample_extra.npz")
+    for name in _cases(g, "__out"):
+        out, ref = _run_extra_downsampler(_oracle_downsample, g, name)
+        assert out.shape == ref.shape and out.dtype == ref.dtype == np.float64, name
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-13, err_msg=name)
+
+
 # ------------------------------------------------------------------------------------------ folds
 def test_folds_match_reference():
     g = load_golden("folds.npz")
