@@ -54,6 +54,7 @@ class RidgeConfig:
     singcutoff: float = 1e-10
     n_outer_folds: int = 5
     p_round_f32: bool = True  # SciPy >= 1.14 keeps float32 inputs' dtype for p-values
+    allow_dual: bool = True  # folds with fewer training rows than features use the n x n kernel matrix
     downdate: bool = True  # inner-fold Gram / cross product by subtraction from the outer fold's
     overlap_eig: bool = True  # eigendecompositions on a side stream
 
@@ -143,33 +144,60 @@ class RidgeCVEngine:
     def _design_side(self, X, sp, cfg: RidgeConfig):
         """Gram + syevd for the outer training set and for every inner fold of one staged plan `sp`.
 
-        Returns (outer, inners): dicts with XtT (p x n split, or None when downdated), XRt (p x |R| split)
-        for downdated folds, G (holds Vt after the eig), lam and the eig ticket."""
+        A fold with at least as many training rows as features is solved in the PRIMAL form (p x p Gram
+        X^T X, eigenvectors = right singular vectors); a fold with fewer rows than features in the DUAL form
+        (n x n kernel matrix X X^T, eigenvectors = left singular vectors), which keeps the eigenproblem at
+        min(n, p) -- the reference's thin SVD has exactly that many components (ridge_utils.py:52).
+
+        Returns (outer, inners): dicts with `dual`, XtT / XRt (primal operands), G (holds the eigenvectors as
+        rows after the eig), lam and the eig ticket."""
         ops, comm = self.ops, self.comm
         p = X.cols
-        XoT = ops.gather_rows_T_split(X, sp["train"], len(sp["train_rows"]))  # (p x n_o)
-        G_o = ops.gemm(XoT, XoT)  # outer Gram, p x p
+        n_o = len(sp["train_rows"])
+        outer = {"dual": bool(cfg.allow_dual and n_o < p), "owner": None}
+        if outer["dual"]:
+            XoR = ops.gather_rows(X, sp["train"], n_o, split=True)  # (n_o x p)
+            G_o = None
+            outer["G"] = ops.gemm(XoR, XoR)  # kernel matrix, n_o x n_o (needed on every rank only after the eig)
+            del XoR
+        else:
+            XoT = ops.gather_rows_T_split(X, sp["train"], n_o)  # (p x n_o)
+            G_o = ops.gemm(XoT, XoT)  # outer Gram, p x p
+            outer["XtT"] = XoT
         inners = []
         for d in sp["inner"]:
             d = dict(d)
+            n_i = len(d["train_rows"])
             d["owner"] = self._next_eig_owner()
+            d["dual"] = bool(cfg.allow_dual and n_i < p)
             mine = d["owner"] == comm.rank
-            if d["R"] is not None:
+            if d["dual"]:
+                d["R"] = None
+                if mine:
+                    XiR = ops.gather_rows(X, d["train"], n_i, split=True)  # (n_i x p)
+                    d["G"] = ops.gemm(XiR, XiR)
+                    del XiR
+                else:
+                    d["G"] = ops.empty(n_i, n_i)
+            elif d["R"] is not None and G_o is not None:
                 XRt = ops.gather_rows_T_split(X, d["R"], len(d["R_rows"]))  # (p x |R|)
                 d.update(XRt=XRt, XtT=None,
                          G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0) if mine else ops.empty(p, p))
             else:
-                XtT = ops.gather_rows_T_split(X, d["train"], len(d["train_rows"]))
+                d["R"] = None
+                XtT = ops.gather_rows_T_split(X, d["train"], n_i)
                 d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if mine else ops.empty(p, p))
             inners.append(d)
-        outer = {"XtT": XoT, "owner": self._next_eig_owner(), "G_keep": G_o,
-                 "G": ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o}
+        outer["owner"] = self._next_eig_owner()
+        if not outer["dual"]:
+            outer["G"] = ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o
+            outer["G_keep"] = G_o
         # Queue the eigendecompositions this rank owns (inner folds first: they are needed first).  With
         # several ranks every eigenproblem is solved once, by rank (job index mod world), and broadcast when
         # it is consumed: X is replicated, so the 30 decompositions of a fit would otherwise be redundant.
         for d in inners + [outer]:
             if d["owner"] != comm.rank:
-                d["lam"], d["ticket"] = ops.vec(p), None
+                d["lam"], d["ticket"] = ops.vec(d["G"].rows), None
             elif cfg.overlap_eig:
                 d["lam"], d["ticket"] = ops.syevd_async(d["G"])
             else:
@@ -196,35 +224,50 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     def _inner_scores(self, X, Y, sp, outer, inners, alphas_dev, n_alphas: int, cfg: RidgeConfig):
         """Sum over inner folds of the (n_alphas x V_r) validation scores (ridge_corr_torch per fold).
-        Also returns C_o^T (V_r x p fp32) for the outer fit."""
+        Also returns C_o^T (V_r x p fp32) for a primal outer fit (None when the outer fold is dual)."""
         ops = self.ops
-        YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
-        Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
-        del YoT
+        Ct_o = None
+        if not outer["dual"]:
+            YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
+            Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
+            del YoT
         corr_sum = ops.empty(n_alphas, Y.cols)
         metric = 0 if cfg.use_corr else 1
         for i, d in enumerate(inners):
             n_tr, n_va = len(d["train_rows"]), len(d["val_rows"])
             if n_va < 2 or n_tr < 1:
                 raise ValueError("inner fold needs >= 1 training and >= 2 validation samples")
-            # cross product of the inner training rows
-            if d["R"] is not None:
-                YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]))  # (V_r x |R|)
-                Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True)
-                del YRt
-            else:
-                YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
-                Ct = ops.gemm(YtT, d["XtT"], split_out=True)
-                del YtT
-            Vt, _, lam = self._eig_ready(d)
-            Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
-            del Ct
-            # validation design in the eigenbasis, centred and stacked over alphas
             rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
             Pv = ops.gather_rows(X, d["val"], n_va, split=True)  # (n_v x p)
-            L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
+            if d["dual"]:
+                # dual form: Z^T = Y_tr^T U (V_r x n), L = (P X_tr^T) U (n_v x n); lam = eig(X_tr X_tr^T) = S^2
+                YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)  # (V_r x n)
+                Ut, _, lam = self._eig_ready(d)
+                Zt = ops.gemm(YtT, Ut, split_out=True)
+                del YtT
+                XiR = ops.gather_rows(X, d["train"], n_tr, split=True)  # (n x p)
+                Kpt = ops.gemm(Pv, XiR, split_out=True)  # (n_v x n), K = p
+                del XiR
+                L = ops.gemm(Kpt, Ut)
+                del Kpt, Ut
+            else:
+                # cross product of the inner training rows (downdated from the outer fold's when possible)
+                if d["R"] is not None:
+                    YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]))  # (V_r x |R|)
+                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True)
+                    del YRt
+                else:
+                    YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
+                    Ct = ops.gemm(YtT, d["XtT"], split_out=True)
+                    del YtT
+                Vt, _, lam = self._eig_ready(d)
+                Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
+                del Ct
+                L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
+                del Vt
+            # validation design in the eigenbasis, centred and stacked over alphas
             Lst = ops.build_alpha_stack(L, n_va, rows_pad, lam, alphas_dev, n_alphas, cfg.normalpha, cfg.singcutoff)
-            del Pv, L, Vt
+            del Pv, L
             mean, std = ops.col_stats(Y, d["val"], n_va, ddof=1)
             Yz = ops.gather_normalize(Y, d["val"], n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
             parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz)
@@ -247,27 +290,37 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     # outer fit + test scoring
     # ------------------------------------------------------------------------------------------
-    def _shrunk_coefficients(self, outer, Ct_o, alpha_v, cfg: RidgeConfig):
-        """(Z_o^T * keep / (lam_o + (alpha_v s0)^2))  (V_r x k split) and V_o (G, rows = eigenvectors)."""
+    def _shrunk_coefficients(self, X, Y, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+        """(Z_o^T * keep / (lam_o + (alpha_v s0)^2))  (V_r x k split) and the eigenvector matrix (rows)."""
         ops = self.ops
         Vt, G, lam = self._eig_ready(outer)
-        Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
+        if outer["dual"]:
+            YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
+            Zt = ops.gemm(YoT, Vt, split_out=True)  # Y_tr^T U
+            del YoT
+        else:
+            Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
         del Vt
         return ops.scale_rows_by_alpha(Zt, lam, alpha_v, cfg.normalpha, cfg.singcutoff), G
 
-    def _outer_weights(self, outer, Ct_o, alpha_v, cfg: RidgeConfig):
-        """ridge_torch (ridge_regression.py:29-63) for every voxel at once -> W^T (V_r x p split)."""
+    def _outer_weights(self, X, Y, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+        """ridge_torch (ridge_regression.py:29-63) for every voxel at once -> W^T (V_r x p split).
+        Primal: W^T = ZS V^T.  Dual: W^T = ZS (X_tr^T U)^T with U the eigenvectors of X_tr X_tr^T."""
         ops = self.ops
-        ZS, G = self._shrunk_coefficients(outer, Ct_o, alpha_v, cfg)
-        Vmat = ops.transpose(G, split=True)  # (p x k): rows = features
-        return ops.gemm(ZS, Vmat, split_out=True)
+        ZS, G = self._shrunk_coefficients(X, Y, sp, outer, Ct_o, alpha_v, cfg)
+        if outer["dual"]:
+            XoT = ops.gather_rows_T_split(X, sp["train"], len(sp["train_rows"]))  # (p x n_o)
+            basis = ops.gemm(XoT, ops.split(G), split_out=True)  # X_tr^T U  (p x n_o)
+        else:
+            basis = ops.transpose(G, split=True)  # V (p x k): rows = features
+        return ops.gemm(ZS, basis, split_out=True)
 
-    def _outer_fit_and_score(self, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
+    def _outer_fit_and_score(self, X, Y, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
         """ridge_torch on the outer training set with the selected alphas, then test r / p."""
         ops = self.ops
         n_te = len(sp["test_rows"])
         te_dev = sp["test"]
-        Wt = self._outer_weights(outer, Ct_o, alpha_v, cfg)  # (V_r x p) voxel-major weights
+        Wt = self._outer_weights(X, Y, sp, outer, Ct_o, alpha_v, cfg)  # (V_r x p) voxel-major weights
         # test predictions, centred so that the fused epilogue yields Pearson's r directly
         rows_pad = -(-n_te // ops.TILE_N) * ops.TILE_N
         pm, _ = ops.col_stats(Xte_src, te_dev, n_te, ddof=0)
@@ -305,9 +358,12 @@ class RidgeCVEngine:
         ops = self.ops
         sp = self._single_split(X.rows, 0, cfg)
         outer, _ = self._design_side(X, sp, cfg)
-        YoT = ops.gather_rows_T_split(Y, sp["train"], X.rows)
-        Ct_o = ops.gemm(YoT, outer["XtT"])
-        return self._outer_weights(outer, Ct_o, alpha_v, cfg)
+        Ct_o = None
+        if not outer["dual"]:
+            YoT = ops.gather_rows_T_split(Y, sp["train"], X.rows)
+            Ct_o = ops.gemm(YoT, outer["XtT"])
+            del YoT
+        return self._outer_weights(X, Y, sp, outer, Ct_o, alpha_v, cfg)
 
     def ridge_corr_pred(self, XX, YY, n_train: int, alpha_v, cfg: RidgeConfig):
         """ridge_corr_pred_torch (ridge_regression.py:144-216): per-voxel alphas, no weights formed:
@@ -318,12 +374,18 @@ class RidgeCVEngine:
         sp = self._single_split(n_train, n_va, cfg, inner=False)
         outer, _ = self._design_side(XX, sp, cfg)
         val = sp["test"]
-        YoT = ops.gather_rows_T_split(YY, sp["train"], n_train)
-        Ct_o = ops.gemm(YoT, outer["XtT"])
-        del YoT
-        ZS, G = self._shrunk_coefficients(outer, Ct_o, alpha_v, cfg)
+        Ct_o = None
+        if not outer["dual"]:
+            YoT = ops.gather_rows_T_split(YY, sp["train"], n_train)
+            Ct_o = ops.gemm(YoT, outer["XtT"])
+            del YoT
+        ZS, G = self._shrunk_coefficients(XX, YY, sp, outer, Ct_o, alpha_v, cfg)
         rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
         Pv = ops.gather_rows(XX, val, n_va, split=True)
+        if outer["dual"]:
+            XiR = ops.gather_rows(XX, sp["train"], n_train, split=True)
+            Pv = ops.gemm(Pv, XiR, split_out=True)  # P X_tr^T (n_v x n)
+            del XiR
         L = ops.gemm(Pv, ops.split(G))  # (n_v x k)
         lm, _ = ops.col_stats(L, None, n_va, ddof=0)
         Lc = ops.gather_normalize(L, None, n_va, lm, None, 2, EPS, rows_out=rows_pad, split=True)
@@ -378,7 +440,7 @@ class RidgeCVEngine:
             corr_sum, Ct_o = self._inner_scores(Xs, Ys, sp, outer, inners, alphas_f64, len(alphas), cfg)
             alpha_v = self._select_alphas(corr_sum, len(plan.inner), alphas_f32, cfg, n_vox_total)
             del corr_sum, inners
-            Wt, r, p = self._outer_fit_and_score(Xts, Yts, sp, outer, Ct_o, alpha_v, cfg)
+            Wt, r, p = self._outer_fit_and_score(Xs, Ys, Xts, Yts, sp, outer, Ct_o, alpha_v, cfg)
             del outer, Ct_o, Xs, Xts, Ys, Yts
             if len(plans) == 1:
                 res.Wt_mean = Wt

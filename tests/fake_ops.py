@@ -41,6 +41,7 @@ class FakeOps:
     def __init__(self):
         self.reset_counters()
         self.eig_calls = 0
+        self.eig_sizes = []
         self.pending = 0
 
     def reset_counters(self):
@@ -181,6 +182,7 @@ class FakeOps:
         w, v = np.linalg.eigh(a)
         G.a[...] = v.T.astype(F32)
         self.eig_calls += 1
+        self.eig_sizes.append(G.rows)
         return w.astype(F32)
 
     def syevd_async(self, G):

@@ -273,8 +273,6 @@ def test_ridge_corr_and_weights_match_reference_golden(ops, name):
                 assert (out[:, const] <= 0).all()
                 out, ref = out[:, ~const], ref[:, ~const]
                 out, ref = np.sign(out) * out ** 2, np.sign(ref) * ref ** 2
-            if name == "wide" and not normalpha:
-                continue  # p > n with un-normalised tiny alphas: Gram route is documented as degraded
             np.testing.assert_allclose(out, ref, rtol=0, atol=tol, err_msg=f"{name} {normalpha} {use_corr}")
     ops.check_eig()
 
@@ -440,7 +438,7 @@ def test_wide_design_matches_oracle(ops):
     assert abs(m["n_significant"] - mo["n_significant"]) <= 2 + (~same).sum()
 
 
-@pytest.mark.parametrize("name", ["tall", "dupcol"])
+@pytest.mark.parametrize("name", ["tall", "dupcol", "wide"])
 def test_ridge_functions_match_reference_golden(ops, name):
     """ridge_torch / ridge_corr_torch / ridge_corr_pred_torch / zs drop-ins through the public API."""
     import litcoder_core_b200 as L

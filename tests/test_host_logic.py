@@ -240,7 +240,7 @@ def test_engine_edge_cases_on_fake_ops():
 
 
 # ------------------------------------------------------------------------------------------ stand-alone ridge kernels
-@pytest.mark.parametrize("name", ["tall", "dupcol"])
+@pytest.mark.parametrize("name", ["tall", "dupcol", "wide"])
 def test_ridge_functions_on_fake_ops_match_reference_golden(name):
     g, e = load_golden("ridge_kernels.npz"), load_golden("ridge_extra.npz")
     alphas = g["alphas"].tolist()
@@ -300,3 +300,49 @@ def test_other_downsamplers_on_fake_ops_match_reference_golden():
             ds.downsample(np.zeros((4, 2)), np.arange(4.0), np.arange(2.0), method=method, split_indices=None)
     with pytest.raises(ValueError, match="Required parameter 'freqs' missing"):
         ds.downsample(np.zeros((4, 2)), np.arange(4.0), np.arange(2.0), method="gabor", sigma=1.0)
+
+
+@pytest.mark.parametrize("N,p,label", [(150, 260, "dual everywhere"), (130, 100, "outer primal, inner dual"),
+                                       (300, 40, "primal everywhere")])
+def test_dual_form_matches_oracle_on_fake_ops(N, p, label):
+    """Folds with fewer training rows than features are solved through the n x n kernel matrix."""
+    from litcoder_core_b200 import engine as E
+
+    rng = np.random.default_rng(N + p)
+    V = 30
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Y = (X[:, :20] @ rng.standard_normal((20, V)) * 0.5 + rng.standard_normal((N, V))).astype(np.float32)
+    kw = dict(n_outer_folds=5, n_inner_folds=4, chunk_length=5, alphas=np.logspace(-1, 3, 6))
+    random.seed(2)
+    ops = FakeOps()
+    m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, **kw)
+    n_o = (N // 5 // 5) * 5 * 4
+    if label == "dual everywhere":
+        assert max(ops.eig_sizes) <= n_o < p
+    elif label == "primal everywhere":
+        assert set(ops.eig_sizes) == {p}
+    else:
+        assert p in ops.eig_sizes and min(ops.eig_sizes) < p
+    random.seed(2)
+    mo, wo, ao = O.fit_predict(X, Y, **kw)
+    same = np.isclose(a, ao)
+    assert same.mean() > 0.85, (label, same.mean())
+    np.testing.assert_allclose(np.asarray(m["correlations"])[same], np.asarray(mo["correlations"], dtype=np.float64)[same],
+                               atol=5e-5)
+    assert np.abs(w[:, same] - wo[:, same]).max() <= 2e-4 * np.abs(wo).max()
+    # and the dual path agrees with the primal path on the same problem
+    orig = E.RidgeConfig.__init__
+
+    def patched(self, *a_, **k_):
+        orig(self, *a_, **k_)
+        self.allow_dual = False
+
+    E.RidgeConfig.__init__ = patched
+    try:
+        random.seed(2)
+        m2, w2, a2 = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(X, Y, **kw)
+    finally:
+        E.RidgeConfig.__init__ = orig
+    same2 = np.isclose(a, a2)
+    assert same2.mean() > 0.85
+    np.testing.assert_allclose(np.asarray(m["correlations"])[same2], np.asarray(m2["correlations"])[same2], atol=5e-5)
