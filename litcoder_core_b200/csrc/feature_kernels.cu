@@ -47,6 +47,33 @@ __global__ void fir_kernel(const T* __restrict__ stim, long nt, long ndim, long 
   }
 }
 
+// float32 fast path: one thread per (t, delay, 4 columns): a 16-byte load, two 16-byte stores.
+__global__ void fir_f32x4_kernel(const float* __restrict__ stim, long nt, long ndim, long ld_stim,
+                                 const int32_t* __restrict__ delays, int ndelays, int circpad,
+                                 double* __restrict__ out, long ld_out) {
+  const long quads = ndim / 4;
+  const long total = nt * ndelays * quads;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long c4 = i % quads;
+    const long rest = i / quads;
+    const int di = (int)(rest % ndelays);
+    const long t = rest / ndelays;
+    const long d = delays[di];
+    long ts = t - d;
+    bool valid = ts >= 0 && ts < nt;
+    if (!valid && circpad) {
+      ts = (d < nt && -d < nt) ? ((ts % nt) + nt) % nt : t;
+      valid = true;
+    }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = __ldg(reinterpret_cast<const float4*>(stim + ts * ld_stim + c4 * 4));
+    double* o = out + t * ld_out + (long)di * ndim + c4 * 4;
+    *reinterpret_cast<double2*>(o) = make_double2((double)v.x, (double)v.y);
+    *reinterpret_cast<double2*>(o + 2) = make_double2((double)v.z, (double)v.w);
+  }
+}
+
 // Lanczos kernel value exactly as interpdata.lanczosfun: t already multiplied by the cutoff.
 __device__ __forceinline__ double lanczos_weight(double t, double window) {
   if (t == 0.0) return 1.0;
@@ -64,80 +91,110 @@ __device__ __forceinline__ double sinc_weight(double t, double B, double window,
   return v;
 }
 
-// grid.x = TR index, grid.y = column tile.  The block first evaluates the weights of a chunk
-// of samples cooperatively into shared memory, then every thread accumulates its column(s).
+// grid.x = group of TRS consecutive TRs, grid.y = column tile.  The block first evaluates the weights of a
+// chunk of samples for all its TRs cooperatively into shared memory, then every thread accumulates its
+// column for the TRS outputs from ONE read of each sample (the bands of neighbouring TRs overlap almost
+// entirely, so a sample row is fetched once per block instead of once per TR).
 // KIND 0: Lanczos (optionally rectified output); KIND 1: sinc (optionally causal / renormalised by the
 // row sum of the weights, which is accumulated in a first pass over the same sample range).
-template <typename T, int CHUNK, int KIND>
+template <typename T, int CHUNK, int KIND, int TRS>
 __global__ void resample_kernel(const T* __restrict__ data, long n_samples, long ndim, long ld_data,
-                                const double* __restrict__ data_times, const double* __restrict__ tr_times,
+                                const double* __restrict__ data_times, const double* __restrict__ tr_times, long n_tr,
                                 double window, double cutoff, int flag_a, int flag_b, const int32_t* __restrict__ lo,
                                 const int32_t* __restrict__ hi, double* __restrict__ out, long ld_out) {
-  __shared__ double w_sh[CHUNK];
-  __shared__ double red_sh[32];
-  const long i = blockIdx.x;
+  __shared__ double w_sh[TRS][CHUNK];
+  __shared__ double red_sh[TRS][8];
+  __shared__ double scale_sh[TRS];
+  const long i0 = (long)blockIdx.x * TRS;
+  const int n_here = (int)((n_tr - i0) < TRS ? (n_tr - i0) : TRS);
   const long c = (long)blockIdx.y * blockDim.x + threadIdx.x;
-  const double tr = tr_times[i];
-  const long j_begin = lo ? (long)lo[i] : 0;
-  const long j_end = hi ? (long)hi[i] : n_samples;
   const int rectify = KIND == 0 ? flag_a : 0;
   const int causal = KIND == 1 ? flag_a : 0;
   const int renorm = KIND == 1 ? flag_b : 0;
   // Without a band (lo == NULL) the kernel is the dense product of the reference: zero weights are
   // multiplied too, so that non-finite samples poison the output exactly as np.dot(sincmat, data) does.
   const bool dense = lo == nullptr;
-  double scale = 1.0;
-  if (renorm) {  // val = val / np.sum(val) unless the sum is exactly 0 (interpdata.py:36-37)
-    double part = 0.0;
-    for (long j = j_begin + threadIdx.x; j < j_end; j += blockDim.x)
-      part += sinc_weight(tr - data_times[j], cutoff, window, causal);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) red_sh[threadIdx.x >> 5] = part;
-    __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red_sh[w];
-    if (tot != 0.0) scale = 1.0 / tot;
+  // union of the bands of this block's TRs (each TR still only uses weights inside its own band)
+  long j_begin = n_samples, j_end = 0;
+  for (int r = 0; r < n_here; ++r) {
+    const long b = lo ? (long)lo[i0 + r] : 0, e = hi ? (long)hi[i0 + r] : n_samples;
+    j_begin = b < j_begin ? b : j_begin;
+    j_end = e > j_end ? e : j_end;
   }
-  double acc = 0.0, acc_neg = 0.0;
+  if (threadIdx.x < TRS) scale_sh[threadIdx.x] = 1.0;
+  if (renorm) {  // val = val / np.sum(val) unless the sum is exactly 0 (interpdata.py:36-37)
+    for (int r = 0; r < n_here; ++r) {
+      const double tr = tr_times[i0 + r];
+      const long b = lo ? (long)lo[i0 + r] : 0, e = hi ? (long)hi[i0 + r] : n_samples;
+      double part = 0.0;
+      for (long j = b + threadIdx.x; j < e; j += blockDim.x) part += sinc_weight(tr - data_times[j], cutoff, window, causal);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if ((threadIdx.x & 31) == 0) red_sh[r][threadIdx.x >> 5] = part;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_here) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red_sh[threadIdx.x][w];
+      if (tot != 0.0) scale_sh[threadIdx.x] = 1.0 / tot;
+    }
+  }
+  __syncthreads();
+  double acc[TRS], acc_neg[TRS];
+#pragma unroll
+  for (int r = 0; r < TRS; ++r) acc[r] = acc_neg[r] = 0.0;
   for (long j0 = j_begin; j0 < j_end; j0 += CHUNK) {
     const long cnt = (j_end - j0) < CHUNK ? (j_end - j0) : CHUNK;
     __syncthreads();
-    for (long q = threadIdx.x; q < cnt; q += blockDim.x) {
-      const double dt = tr - data_times[j0 + q];
-      w_sh[q] = KIND == 0 ? lanczos_weight(dt * cutoff, window) : sinc_weight(dt, cutoff, window, causal) * scale;
+    for (long q = threadIdx.x; q < cnt * TRS; q += blockDim.x) {
+      const int r = (int)(q / cnt);
+      const long jj = q - (long)r * cnt;
+      double w = 0.0;
+      if (r < n_here) {
+        const long j = j0 + jj;
+        const long b = lo ? (long)lo[i0 + r] : 0, e = hi ? (long)hi[i0 + r] : n_samples;
+        if (j >= b && j < e) {
+          const double dt = tr_times[i0 + r] - data_times[j];
+          w = KIND == 0 ? lanczos_weight(dt * cutoff, window) : sinc_weight(dt, cutoff, window, causal) * scale_sh[r];
+        }
+      }
+      w_sh[r][jj] = w;
     }
     __syncthreads();
     if (c < ndim) {
       for (long q = 0; q < cnt; ++q) {
-        const double w = w_sh[q];
-        if (w != 0.0 || dense) {
-          const double x = (double)data[(j0 + q) * ld_data + c];
-          if (rectify) {
-            // np.clip keeps NaN; CUDA's fmin / fmax would drop it
-            acc_neg = fma(w, x != x ? x : fmin(x, 0.0), acc_neg);
-            acc = fma(w, x != x ? x : fmax(x, 0.0), acc);
-          } else {
-            acc = fma(w, x, acc);
+        const double x = (double)data[(j0 + q) * ld_data + c];
+        const double xn = x != x ? x : fmin(x, 0.0);  // np.clip keeps NaN; CUDA's fmin / fmax would drop it
+        const double xp = x != x ? x : fmax(x, 0.0);
+#pragma unroll
+        for (int r = 0; r < TRS; ++r) {
+          const double w = w_sh[r][q];
+          if (w != 0.0 || dense) {
+            if (rectify) {
+              acc_neg[r] = fma(w, xn, acc_neg[r]);
+              acc[r] = fma(w, xp, acc[r]);
+            } else {
+              acc[r] = fma(w, x, acc[r]);
+            }
           }
         }
       }
     }
   }
   if (c < ndim) {
-    if (rectify) {
-      out[i * ld_out + c] = acc_neg;
-      out[i * ld_out + ndim + c] = acc;
-    } else {
-      out[i * ld_out + c] = acc;
+#pragma unroll
+    for (int r = 0; r < TRS; ++r) {
+      if (r >= n_here) break;
+      if (rectify) {
+        out[(i0 + r) * ld_out + c] = acc_neg[r];
+        out[(i0 + r) * ld_out + ndim + c] = acc[r];
+      } else {
+        out[(i0 + r) * ld_out + c] = acc[r];
+      }
     }
   }
 }
 
-// out[r][c] = reduce over e in [row_ptr[r], row_ptr[r+1]) of weights[e] * data[col_idx[e]][c]
-// (weights == NULL: 1), divided by the number of entries when `mean`; rows without entries are zero.
-// This is the device form of the split-index / membership downsamplers of the reference
-// (downsampling.py:24-319): the host only builds the integer membership lists.
 // Unweighted rows are accumulated in the INPUT precision, one entry after the other, and divided by the
 // count in that precision: exactly what np.sum / np.mean(axis=0) do on a float32 (or float64) block, so the
 // result is bit-identical to the reference's before it is widened to float64.
@@ -222,6 +279,16 @@ extern "C" int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, lon
   const long cap = (long)sm_count() * 64;
   if (grid > cap) grid = cap;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype_in == 0 && ndim % 4 == 0 && ld_stim % 4 == 0 && ld_out % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(stim) & 15) == 0) {
+    const long items = nt * ndelays * (ndim / 4);
+    long g4 = (items + 255) / 256;
+    if (g4 > cap) g4 = cap;
+    fir_f32x4_kernel<<<(int)g4, 256, 0, s>>>((const float*)stim, nt, ndim, ld_stim, delays, ndelays, circpad, out,
+                                             ld_out);
+    LIT_LAUNCH_CHECK();
+    return LIT_OK;
+  }
   if (dtype_in == 0)
     fir_kernel<float><<<(int)grid, 256, 0, s>>>((const float*)stim, nt, ndim, ld_stim, delays, ndelays, circpad, out,
                                                 ld_out);
@@ -238,16 +305,17 @@ static int launch_resample(const void* data, int dtype_in, long n_samples, long 
                            int flag_a, int flag_b, const int32_t* lo, const int32_t* hi, double* out, long ld_out,
                            void* stream) {
   const int block = ndim >= 256 ? 256 : (ndim >= 128 ? 128 : 64);
-  dim3 grid((unsigned)n_tr, (unsigned)((ndim + block - 1) / block));
+  constexpr int TRS = 4;
+  dim3 grid((unsigned)((n_tr + TRS - 1) / TRS), (unsigned)((ndim + block - 1) / block));
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype_in == 0)
-    resample_kernel<float, 256, KIND><<<grid, block, 0, s>>>((const float*)data, n_samples, ndim, ld_data, data_times,
-                                                             tr_times, window, cutoff, flag_a, flag_b, lo, hi, out,
-                                                             ld_out);
+    resample_kernel<float, 128, KIND, TRS><<<grid, block, 0, s>>>((const float*)data, n_samples, ndim, ld_data,
+                                                                   data_times, tr_times, n_tr, window, cutoff, flag_a,
+                                                                   flag_b, lo, hi, out, ld_out);
   else
-    resample_kernel<double, 256, KIND><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data,
-                                                              data_times, tr_times, window, cutoff, flag_a, flag_b, lo,
-                                                              hi, out, ld_out);
+    resample_kernel<double, 128, KIND, TRS><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data,
+                                                                    data_times, tr_times, n_tr, window, cutoff, flag_a,
+                                                                    flag_b, lo, hi, out, ld_out);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

@@ -423,6 +423,16 @@ static int kc_blocks_default() {
   return v;
 }
 
+// Rasterisation: consecutive tiles walk `group_m` M tiles (of BM*CG rows) before advancing along N, so that a
+// wave of concurrently running tiles shares few A and B strips.  LIT_GEMM_GROUP_M overrides (development knob).
+static int group_m_default(int cg) {
+  static int v = [] {
+    const char* e = getenv("LIT_GEMM_GROUP_M");
+    return e ? atoi(e) : 0;
+  }();
+  return v > 0 ? v : 32 / cg;  // 16 CTA pairs: ~3 % faster than 8 on the config-2 fused GEMM (gpurun_out/group_m_sweep.log)
+}
+
 static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it (development knob)
   const char* e = getenv("LIT_GEMM_SM_LIMIT");
   return e ? atoi(e) : 0;
@@ -443,7 +453,7 @@ static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const flo
   p.num_n_tiles = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + S::BK - 1) / S::BK;
   if (p.num_k_blocks < 1) p.num_k_blocks = 1;  // K == 0 still zero-initialises the accumulator via OOB fill
-  if (p.group_m <= 0) p.group_m = 16 / CG;
+  if (p.group_m <= 0) p.group_m = group_m_default(CG);
   if (p.kc_blocks <= 0) p.kc_blocks = kc_blocks_default();
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return LIT_OK;

@@ -19,43 +19,71 @@ static inline int blocks_for(long items, int block) { return (int)((items + bloc
 // blockIdx.y into ROW_SPLIT slices that are combined with fp64 atomics on (sum, sumsq) of
 // values shifted by the first row (avoids cancellation when |mean| >> std).
 // ---------------------------------------------------------------------------------------------
+template <int CPT>  // columns per thread: 4 (float4 loads) or 1
 __global__ void col_moments_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx,
                                    long n_idx, long cols, double* __restrict__ acc /* [2][cols] */) {
-  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long c = ((long)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
   if (c >= cols) return;
-  const long r_begin = (long)blockIdx.y * ((n_idx + gridDim.y - 1) / gridDim.y);
-  long r_end = r_begin + (n_idx + gridDim.y - 1) / gridDim.y;
+  const long per = (n_idx + gridDim.y - 1) / gridDim.y;
+  const long r_begin = (long)blockIdx.y * per;
+  long r_end = r_begin + per;
   if (r_end > n_idx) r_end = n_idx;
   const long r_first = idx ? (long)idx[0] : 0;
-  const float shift = src[r_first * ld_src + c];
-  double s = 0.0, q = 0.0;
+  float shift[CPT];
+  double s[CPT], q[CPT];
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
+    shift[u] = (c + u < cols) ? src[r_first * ld_src + c + u] : 0.f;
+    s[u] = 0.0;
+    q[u] = 0.0;
+  }
+  constexpr int UNROLL = 4;
   long r = r_begin;
-  for (; r + 4 <= r_end; r += 4) {
-    float v[4];
+  for (; r + UNROLL <= r_end; r += UNROLL) {
+    float v[UNROLL][CPT];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long sr = idx ? (long)idx[r + u] : r + u;
-      v[u] = src[sr * ld_src + c];
+    for (int k = 0; k < UNROLL; ++k) {
+      const long sr = idx ? (long)idx[r + k] : r + k;
+      if (CPT == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(src + sr * ld_src + c);
+        v[k][0] = x.x;
+        v[k][1 % CPT] = x.y;
+        v[k][2 % CPT] = x.z;
+        v[k][3 % CPT] = x.w;
+      } else {
+        v[k][0] = src[sr * ld_src + c];
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double d = (double)v[u] - (double)shift;
-      s += d;
-      q += d * d;
-    }
+    for (int k = 0; k < UNROLL; ++k)
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        const double d = (double)v[k][u] - (double)shift[u];
+        s[u] += d;
+        q[u] += d * d;
+      }
   }
   for (; r < r_end; ++r) {
     const long sr = idx ? (long)idx[r] : r;
-    const double d = (double)src[sr * ld_src + c] - (double)shift;
-    s += d;
-    q += d * d;
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+      if (c + u < cols) {
+        const double d = (double)src[sr * ld_src + c + u] - (double)shift[u];
+        s[u] += d;
+        q[u] += d * d;
+      }
+    }
   }
-  if (gridDim.y == 1) {
-    acc[c] = s;
-    acc[cols + c] = q;
-  } else {
-    atomicAdd(&acc[c], s);
-    atomicAdd(&acc[cols + c], q);
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
+    if (c + u >= cols) break;
+    if (gridDim.y == 1) {
+      acc[c + u] = s[u];
+      acc[cols + c + u] = q[u];
+    } else {
+      atomicAdd(&acc[c + u], s[u]);
+      atomicAdd(&acc[cols + c + u], q[u]);
+    }
   }
 }
 
@@ -76,71 +104,76 @@ __global__ void col_stats_finish_kernel(const float* __restrict__ src, long ld_s
 }
 
 // dst[i][c] = (src[idx[i]][c] - mean[c]) * scale(c)
+// grid.x covers the columns (CPT per thread), grid.y groups of RPT output rows: the per-column mean / scale
+// are computed once per thread and reused for its RPT rows, whose loads are all in flight together.
 template <bool VEC, bool SPLIT>
 __global__ void gather_normalize_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx,
                                         long n_idx, long cols, const float* __restrict__ mean,
                                         const float* __restrict__ stdv, int mode, float eps, float* __restrict__ dst,
                                         float* __restrict__ dst_lo, long ld_dst, long n_rows_out) {
   constexpr int CPT = VEC ? 4 : 1;
-  const long cols_t = (cols + CPT - 1) / CPT;
-  const long total = n_rows_out * cols_t;
-  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int RPT = 4;
+  const long c = ((long)blockIdx.x * blockDim.x + threadIdx.x) * CPT;
+  if (c >= cols) return;
   const float rs = n_idx > 1 ? rsqrtf((float)(n_idx - 1)) : 0.f;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long r = i / cols_t;
-    const long c = (i - r * cols_t) * CPT;
-    float x[CPT];
+  float m[CPT], sc[CPT];
 #pragma unroll
-    for (int u = 0; u < CPT; ++u) x[u] = 0.f;
-    if (r < n_idx) {
-      const long sr = idx ? (long)idx[r] : r;
-      if (VEC) {
-        const float4 v = *reinterpret_cast<const float4*>(src + sr * ld_src + c);
-        x[0] = v.x;
-        if (CPT > 1) {
-          x[1 % CPT] = v.y;
-          x[2 % CPT] = v.z;
-          x[3 % CPT] = v.w;
+  for (int u = 0; u < CPT; ++u) {
+    m[u] = mean[c + u];
+    sc[u] = 1.f;
+    if (mode == 0) {
+      sc[u] = 1.f / (stdv[c + u] + eps);
+    } else if (mode == 1) {
+      // a constant response column has no correlation: NaN here propagates through the fused
+      // reduction and becomes (r, p) = (0, 1) in pearson_finalize, as SciPy's pearsonr -> NaN
+      const float sd = stdv[c + u];
+      sc[u] = sd > 0.f ? rs / sd : __int_as_float(0x7fc00000);
+    } else if (mode == 3) {
+      const float sd = stdv[c + u];
+      sc[u] = sd != 0.f ? 1.f / sd : 1.f;  // zs(): zero-variance columns are centred only
+    }
+  }
+  for (long r0 = (long)blockIdx.y * RPT; r0 < n_rows_out; r0 += (long)gridDim.y * RPT) {
+    float x[RPT][CPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const long r = r0 + k;
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) x[k][u] = 0.f;
+      if (r < n_idx) {
+        const long sr = idx ? (long)idx[r] : r;
+        if (VEC) {
+          const float4 v = *reinterpret_cast<const float4*>(src + sr * ld_src + c);
+          x[k][0] = v.x, x[k][1 % CPT] = v.y, x[k][2 % CPT] = v.z, x[k][3 % CPT] = v.w;
+        } else {
+          x[k][0] = src[sr * ld_src + c];
         }
-      } else {
-        x[0] = src[sr * ld_src + c];
       }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const long r = r0 + k;
+      if (r >= n_rows_out) break;
+      float h[CPT], l[CPT];
 #pragma unroll
       for (int u = 0; u < CPT; ++u) {
-        const float m = mean[c + u];
-        float sc = 1.f;
-        if (mode == 0) {
-          sc = 1.f / (stdv[c + u] + eps);
-        } else if (mode == 1) {
-          // a constant response column has no correlation: NaN here propagates through the fused
-          // reduction and becomes (r, p) = (0, 1) in pearson_finalize, as SciPy's pearsonr -> NaN
-          const float sd = stdv[c + u];
-          sc = sd > 0.f ? rs / sd : __int_as_float(0x7fc00000);
-        } else if (mode == 3) {
-          const float sd = stdv[c + u];
-          sc = sd != 0.f ? 1.f / sd : 1.f;  // zs(): zero-variance columns are centred only
+        const float y = r < n_idx ? (x[k][u] - m[u]) * sc[u] : 0.f;
+        if (SPLIT) {
+          h[u] = ptx::to_tf32(y);
+          l[u] = ptx::to_tf32(y - h[u]);
+        } else {
+          h[u] = y;
+          l[u] = 0.f;
         }
-        x[u] = (x[u] - m) * sc;
       }
-    }
-    float h[CPT], l[CPT];
-#pragma unroll
-    for (int u = 0; u < CPT; ++u) {
-      if (SPLIT) {
-        h[u] = ptx::to_tf32(x[u]);
-        l[u] = ptx::to_tf32(x[u] - h[u]);
+      if (VEC) {
+        *reinterpret_cast<float4*>(dst + r * ld_dst + c) = make_float4(h[0], h[1 % CPT], h[2 % CPT], h[3 % CPT]);
+        if (SPLIT)
+          *reinterpret_cast<float4*>(dst_lo + r * ld_dst + c) = make_float4(l[0], l[1 % CPT], l[2 % CPT], l[3 % CPT]);
       } else {
-        h[u] = x[u];
-        l[u] = 0.f;
+        dst[r * ld_dst + c] = h[0];
+        if (SPLIT) dst_lo[r * ld_dst + c] = l[0];
       }
-    }
-    if (VEC) {
-      *reinterpret_cast<float4*>(dst + r * ld_dst + c) = make_float4(h[0], h[1 % CPT], h[2 % CPT], h[3 % CPT]);
-      if (SPLIT)
-        *reinterpret_cast<float4*>(dst_lo + r * ld_dst + c) = make_float4(l[0], l[1 % CPT], l[2 % CPT], l[3 % CPT]);
-    } else {
-      dst[r * ld_dst + c] = h[0];
-      if (SPLIT) dst_lo[r * ld_dst + c] = l[0];
     }
   }
 }
@@ -154,11 +187,12 @@ __device__ __forceinline__ float norm_scale(const float* lam, int k, int normalp
   return normalpha ? sqrtf(fmaxf(lam[k - 1], 0.f)) : 1.f;
 }
 
+template <int CPT>  // columns per thread (4: float4 accesses)
 __global__ void alpha_stack_kernel(const float* __restrict__ L, long ld_l, long n_rows, long rows_pad, int k,
                                    const float* __restrict__ lam, const double* __restrict__ alphas, int normalpha,
                                    float singcutoff, const float* __restrict__ col_mean, float* __restrict__ out_hi,
                                    float* __restrict__ out_lo, long ld_out, int row_chunk) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * CPT;
   const int n_chunks = (int)((rows_pad + row_chunk - 1) / row_chunk);
   const int a = blockIdx.y / n_chunks;
   const int ch = blockIdx.y - a * n_chunks;
@@ -166,44 +200,98 @@ __global__ void alpha_stack_kernel(const float* __restrict__ L, long ld_l, long 
   const float s = norm_scale(lam, k, normalpha);
   const double an = alphas[a] * (double)s;  // alpha * S[0] in double, as the Python floats of the reference
   const float a2 = (float)(an * an);
-  const float lj = lam[j];
-  const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
-  const float d = keep ? 1.f / (lj + a2) : 0.f;
-  const float m = col_mean[j];
+  float d[CPT], m[CPT];
+#pragma unroll
+  for (int u = 0; u < CPT; ++u) {
+    const float lj = lam[j + u];
+    const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
+    d[u] = keep ? 1.f / (lj + a2) : 0.f;
+    m[u] = col_mean[j + u];
+  }
   const long t0 = (long)ch * row_chunk;
   long t1 = t0 + row_chunk;
   if (t1 > rows_pad) t1 = rows_pad;
-  for (long t = t0; t < t1; ++t) {
-    float v = 0.f;
-    if (t < n_rows) v = (L[t * ld_l + j] - m) * d;
-    const float h = ptx::to_tf32(v);
-    const long o = ((long)a * rows_pad + t) * ld_out + j;
-    out_hi[o] = h;
-    out_lo[o] = ptx::to_tf32(v - h);
+  for (long t = t0; t < t1; t += 2) {  // two rows in flight per thread
+    float v[2][CPT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const bool live = t + r < n_rows;
+      if (CPT == 4) {
+        const float4 x = live ? *reinterpret_cast<const float4*>(L + (t + r) * ld_l + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r][0] = x.x, v[r][1 % CPT] = x.y, v[r][2 % CPT] = x.z, v[r][3 % CPT] = x.w;
+      } else {
+        v[r][0] = live ? L[(t + r) * ld_l + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (t + r >= t1) break;
+      const bool live = t + r < n_rows;
+      float h[CPT], l[CPT];
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        const float x = live ? (v[r][u] - m[u]) * d[u] : 0.f;
+        h[u] = ptx::to_tf32(x);
+        l[u] = ptx::to_tf32(x - h[u]);
+      }
+      const long o = ((long)a * rows_pad + t + r) * ld_out + j;
+      if (CPT == 4) {
+        *reinterpret_cast<float4*>(out_hi + o) = make_float4(h[0], h[1 % CPT], h[2 % CPT], h[3 % CPT]);
+        *reinterpret_cast<float4*>(out_lo + o) = make_float4(l[0], l[1 % CPT], l[2 % CPT], l[3 % CPT]);
+      } else {
+        out_hi[o] = h[0];
+        out_lo[o] = l[0];
+      }
+    }
   }
 }
 
 // out[v][j] = (Zhi+Zlo)[v][j] * keep_j / (lam_j + (alpha_v*s)^2)
+template <bool VEC>
 __global__ void scale_rows_kernel(const float* __restrict__ Z_hi, const float* __restrict__ Z_lo, long ld_z,
                                   long n_vox, int k, const float* __restrict__ lam, const float* __restrict__ alpha_v,
                                   int normalpha, float singcutoff, float* __restrict__ out_hi,
                                   float* __restrict__ out_lo, long ld_out) {
+  constexpr int CPT = VEC ? 4 : 1;
   const float s = norm_scale(lam, k, normalpha);
-  const long total = n_vox * (long)k;
+  const long kt = (k + CPT - 1) / CPT;
+  const long total = n_vox * kt;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long v = i / k;
-    const int j = (int)(i - v * k);
+    const long v = i / kt;
+    const int j = (int)(i - v * kt) * CPT;
     const float an = alpha_v[v] * s;  // fp32 product, as nalphas = alphas * norm in ridge_torch
     const float a2 = an * an;
-    const float lj = lam[j];
-    const bool keep = sqrtf(fmaxf(lj, 0.f)) > singcutoff;
-    float z = Z_hi[v * ld_z + j];
-    if (Z_lo) z += Z_lo[v * ld_z + j];
-    const float o = keep ? z / (lj + a2) : 0.f;
-    const float h = ptx::to_tf32(o);
-    out_hi[v * ld_out + j] = h;
-    out_lo[v * ld_out + j] = ptx::to_tf32(o - h);
+    float z[CPT], lj[CPT];
+    if (VEC) {
+      const float4 zh = *reinterpret_cast<const float4*>(Z_hi + v * ld_z + j);
+      z[0] = zh.x, z[1 % CPT] = zh.y, z[2 % CPT] = zh.z, z[3 % CPT] = zh.w;
+      if (Z_lo) {
+        const float4 zl = *reinterpret_cast<const float4*>(Z_lo + v * ld_z + j);
+        z[0] += zl.x, z[1 % CPT] += zl.y, z[2 % CPT] += zl.z, z[3 % CPT] += zl.w;
+      }
+      const float4 l4 = *reinterpret_cast<const float4*>(lam + j);
+      lj[0] = l4.x, lj[1 % CPT] = l4.y, lj[2 % CPT] = l4.z, lj[3 % CPT] = l4.w;
+    } else {
+      z[0] = Z_hi[v * ld_z + j];
+      if (Z_lo) z[0] += Z_lo[v * ld_z + j];
+      lj[0] = lam[j];
+    }
+    float h[CPT], l[CPT];
+#pragma unroll
+    for (int u = 0; u < CPT; ++u) {
+      const bool keep = sqrtf(fmaxf(lj[u], 0.f)) > singcutoff;
+      const float o = keep ? z[u] / (lj[u] + a2) : 0.f;
+      h[u] = ptx::to_tf32(o);
+      l[u] = ptx::to_tf32(o - h[u]);
+    }
+    if (VEC) {
+      *reinterpret_cast<float4*>(out_hi + v * ld_out + j) = make_float4(h[0], h[1 % CPT], h[2 % CPT], h[3 % CPT]);
+      *reinterpret_cast<float4*>(out_lo + v * ld_out + j) = make_float4(l[0], l[1 % CPT], l[2 % CPT], l[3 % CPT]);
+    } else {
+      out_hi[v * ld_out + j] = h[0];
+      out_lo[v * ld_out + j] = l[0];
+    }
   }
 }
 
@@ -302,7 +390,8 @@ extern "C" int lit_col_stats(const float* src, long ld_src, const int32_t* idx, 
   if (cols == 0) return LIT_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int block = 128;
-  const int gx = blocks_for(cols, block);
+  const bool vec = cols % 4 == 0 && ld_src % 4 == 0 && aligned16(src);
+  const int gx = blocks_for(vec ? cols / 4 : cols, block);
   // enough row slices to fill the machine when there are few columns
   int gy = 1;
   const int target = sm_count() * 8;
@@ -314,9 +403,13 @@ extern "C" int lit_col_stats(const float* src, long ld_src, const int32_t* idx, 
     if (gy > 65535) gy = 65535;
   }
   if (gy > 1) LIT_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * cols, s));
-  col_moments_kernel<<<dim3(gx, gy), block, 0, s>>>(src, ld_src, idx, n_idx, cols, scratch);
+  if (vec)
+    col_moments_kernel<4><<<dim3(gx, gy), block, 0, s>>>(src, ld_src, idx, n_idx, cols, scratch);
+  else
+    col_moments_kernel<1><<<dim3(gx, gy), block, 0, s>>>(src, ld_src, idx, n_idx, cols, scratch);
   LIT_LAUNCH_CHECK();
-  col_stats_finish_kernel<<<gx, block, 0, s>>>(src, ld_src, idx, n_idx, cols, ddof, scratch, mean, stdv);
+  const int gxf = blocks_for(cols, block);
+  col_stats_finish_kernel<<<gxf, block, 0, s>>>(src, ld_src, idx, n_idx, cols, ddof, scratch, mean, stdv);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }
@@ -330,14 +423,17 @@ extern "C" int lit_gather_normalize_rows(const float* src, long ld_src, const in
   if (n_rows_out == 0 || cols == 0) return LIT_OK;
   const bool vec = cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && aligned16(src) && aligned16(dst) &&
                    (!dst_lo || aligned16(dst_lo));
-  const long items = n_rows_out * (vec ? cols / 4 : cols);
-  long grid = (items + 255) / 256;
-  const long cap = (long)sm_count() * 64;
-  if (grid > cap) grid = cap;
+  const int gx = blocks_for(vec ? cols / 4 : cols, 128);
+  long gy = (n_rows_out + 3) / 4;
+  const long want = ((long)sm_count() * 32 + gx - 1) / gx;  // enough blocks to fill the machine a few times over
+  if (gy > want) gy = want;
+  if (gy > 65535) gy = 65535;
+  if (gy < 1) gy = 1;
+  const dim3 grid(gx, (unsigned)gy);
   cudaStream_t s = (cudaStream_t)stream;
-#define LIT_GN(V, S)                                                                                              \
-  gather_normalize_kernel<V, S><<<(int)grid, 256, 0, s>>>(src, ld_src, idx, n_idx, cols, mean, stdv, mode, eps, dst, \
-                                                          dst_lo, ld_dst, n_rows_out)
+#define LIT_GN(V, S)                                                                                             \
+  gather_normalize_kernel<V, S><<<grid, 128, 0, s>>>(src, ld_src, idx, n_idx, cols, mean, stdv, mode, eps, dst, \
+                                                     dst_lo, ld_dst, n_rows_out)
   if (vec) {
     if (dst_lo)
       LIT_GN(true, true);
@@ -363,12 +459,19 @@ extern "C" int lit_build_alpha_stack(const float* L, long ld_l, long n_rows, lon
   int rc = lit_col_stats(L, ld_l, nullptr, n_rows, k, 0, col_mean, nullptr, scratch, stream);
   if (rc) return rc;
   const int block = 128;
-  const int row_chunk = 128;
+  const int row_chunk = 64;
   const int n_chunks = (int)((rows_pad + row_chunk - 1) / row_chunk);
   LIT_REQUIRE((long)n_alphas * n_chunks <= 65535, "alpha_stack: too many (alpha, row-chunk) pairs");
-  dim3 grid(blocks_for(k, block), n_alphas * n_chunks);
-  alpha_stack_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(L, ld_l, n_rows, rows_pad, k, lam, alphas, normalpha,
-                                                               singcutoff, col_mean, out_hi, out_lo, ld_out, row_chunk);
+  const bool vec = k % 4 == 0 && ld_l % 4 == 0 && ld_out % 4 == 0 && aligned16(L) && aligned16(out_hi) && aligned16(out_lo);
+  dim3 grid(blocks_for(vec ? k / 4 : k, block), n_alphas * n_chunks);
+  if (vec)
+    alpha_stack_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(L, ld_l, n_rows, rows_pad, k, lam, alphas, normalpha,
+                                                                    singcutoff, col_mean, out_hi, out_lo, ld_out,
+                                                                    row_chunk);
+  else
+    alpha_stack_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(L, ld_l, n_rows, rows_pad, k, lam, alphas, normalpha,
+                                                                    singcutoff, col_mean, out_hi, out_lo, ld_out,
+                                                                    row_chunk);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }
@@ -378,12 +481,18 @@ extern "C" int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, lon
                                        float* out_hi, float* out_lo, long ld_out, void* stream) {
   LIT_REQUIRE(ld_z >= k && ld_out >= k && k > 0, "scale_rows: bad extents");
   if (n_vox == 0) return LIT_OK;
-  const long items = n_vox * (long)k;
+  const bool vec = k % 4 == 0 && ld_z % 4 == 0 && ld_out % 4 == 0 && aligned16(Z_hi) && (!Z_lo || aligned16(Z_lo)) &&
+                   aligned16(out_hi) && aligned16(out_lo) && aligned16(lam);
+  const long items = n_vox * (long)(vec ? k / 4 : k);
   long grid = (items + 255) / 256;
   const long cap = (long)sm_count() * 64;
   if (grid > cap) grid = cap;
-  scale_rows_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(Z_hi, Z_lo, ld_z, n_vox, k, lam, alpha_v, normalpha,
-                                                                 singcutoff, out_hi, out_lo, ld_out);
+  if (vec)
+    scale_rows_kernel<true><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(Z_hi, Z_lo, ld_z, n_vox, k, lam, alpha_v,
+                                                                         normalpha, singcutoff, out_hi, out_lo, ld_out);
+  else
+    scale_rows_kernel<false><<<(int)grid, 256, 0, (cudaStream_t)stream>>>(Z_hi, Z_lo, ld_z, n_vox, k, lam, alpha_v,
+                                                                          normalpha, singcutoff, out_hi, out_lo, ld_out);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }
