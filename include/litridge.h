@@ -170,6 +170,28 @@ int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_v
                      int32_t* best, float* alpha_out, double* col_sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Eigendecomposition-free inner-fold solver: M_a = P_c (G + a^2 I)^-1 with GEMMs only
+ * (same quantity as PVh * D of ridge_regression.py:105,117-120, rotated back out of the eigenbasis)
+ * ---------------------------------------------------------------------------------------- */
+/* lambda_max of the symmetric positive semi-definite G (n x n) by `steps` steps of the three-term Lanczos
+ * recurrence and a Sturm bisection on the resulting tridiagonal matrix (all on the device).
+ * vec_scratch: 3*n floats; scal_scratch: 2*steps + 4 doubles.  Either output may be NULL.
+ * Replaces S[0] = largest singular value used by normalpha (ridge_regression.py:39,97). */
+int lit_lanczos_lambda_max(const float* G, long ld, int n, int steps, float* vec_scratch, double* scal_scratch,
+                           float* lam_out_f32, double* lam_out_f64, void* stream);
+/* One Chebyshev step on (rows x cols) row-matrices of pitch ld:
+ *   d = c1*d + c2*r (also written as the split pair d_hi/d_lo),  x += d,  t = r - a2*d;
+ * `first` != 0 treats d and x as zero on input.  The caller then forms r = t - d G with lit_gemm_tf32x3_nt. */
+int lit_cheb_update(float* d, const float* r, float* x, float* t, float* d_hi, float* d_lo, long ld, long rows, long cols,
+                    float c1, float c2, float a2, int first, void* stream);
+/* out[slots[g]*rows_pad + t][:] = sum_{q<n_src} coef[g*4+q] * (src_hi[q] + src_lo[q])[t][:]  (t < rows; pad rows 0),
+ * written as a split pair: the truncated Neumann series of (G + a^2 I)^-1 for alphas far above the spectrum.
+ * src_hi / src_lo are HOST arrays of n_src (<= 4) device pointers (src_lo may be NULL or hold NULLs). */
+int lit_poly_combine(const float* const* src_hi, const float* const* src_lo, int n_src, long ld_src, long rows,
+                     long rows_pad, long cols, const double* coef, const int32_t* slots, int n_groups, float* out_hi,
+                     float* out_lo, long ld_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test statistics (nested_cv.py:418-477, statsmodels fdrcorrection)
  * ---------------------------------------------------------------------------------------- */
 /* r[v] = clip(sum_tiles dot / sqrt(sum_tiles ssq), -1, 1) (Yz must hold unit-norm centred columns),

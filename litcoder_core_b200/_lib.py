@@ -47,6 +47,9 @@ PROTOTYPES = {
     "lit_fisher_combine": [_vp, _l, _i, _l, _i, _vp, _vp],
     "lit_fir_make_delayed": [_vp, _i, _l, _l, _l, _vp, _i, _i, _vp, _l, _vp],
     "lit_lanczos_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _d, _d, _i, _vp, _vp, _vp, _l, _vp],
+    "lit_lanczos_lambda_max": [_vp, _l, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "lit_cheb_update": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _l, _f, _f, _f, _i, _vp],
+    "lit_poly_combine": [_vp, _vp, _i, _l, _l, _l, _l, _vp, _vp, _i, _vp, _vp, _l, _vp],
     "lit_sinc_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _d, _d, _i, _i, _vp, _vp, _vp, _l, _vp],
     "lit_csr_rows_apply": [_vp, _i, _l, _l, _vp, _vp, _vp, _l, _i, _vp, _l, _vp],
     "lit_gabor_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _vp, _i, _d, _vp, _l, _vp],

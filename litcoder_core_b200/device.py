@@ -293,6 +293,10 @@ class DeviceOps:
         """Underlying torch tensor of a Mat (first plane) or device vector, for in-place collectives."""
         return x.hi if isinstance(x, Mat) else x
 
+    def planes(self, m: Mat) -> list:
+        """The torch tensors behind a Mat (one, or two for a split pair), for in-place collectives."""
+        return [m.hi] + ([m.lo] if m.lo is not None else [])
+
     def download(self, t) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()
         return t.detach().cpu().numpy()
@@ -515,6 +519,90 @@ class DeviceOps:
         for w in self._eig_workers:
             w.join(timeout=10)
         self._eig_workers = []
+
+    # ------------------------------------------------------------------ eigendecomposition-free inner solver
+    def lambda_max(self, G: Mat, steps: int = 96):
+        """Device scalar (1-element f64 tensor) with lambda_max of the symmetric PSD matrix G (Lanczos + Sturm
+        bisection on the device; lit_lanczos_lambda_max).  Reading it on the host synchronises."""
+        n = G.rows
+        steps = min(steps, n)
+        vec_scratch = self.vec(3 * n)
+        scal_scratch = self.vec(2 * steps + 4, "f64")
+        out = self.vec(1, "f64")
+        check(self.lib.lit_lanczos_lambda_max(_vp(G.hi.data_ptr()), G.ld, n, steps, _vp(vec_scratch.data_ptr()),
+                                              _vp(scal_scratch.data_ptr()), _vp(0), _vp(out.data_ptr()),
+                                              _vp(self.stream)), "lanczos_lambda_max")
+        self.launches += 2 * steps + 2
+        return out
+
+    @staticmethod
+    def chebyshev_plan(lam_max: float, a2: float, tol: float = 2e-7, safety: float = 1.02):
+        """Scalar schedule of the Chebyshev iteration for (G + a2 I) with spec(G) in [0, safety * lam_max]:
+        list of (c1, c2) per step (d = c1 d + c2 r), after Saad, Iterative Methods, alg. 12.1."""
+        u = safety * lam_max
+        theta, delta = a2 + 0.5 * u, 0.5 * u
+        sigma1 = theta / delta
+        kappa = (a2 + u) / a2
+        rate = (np.sqrt(kappa) - 1.0) / (np.sqrt(kappa) + 1.0)
+        n_steps = max(2, int(np.ceil(np.log(2.0 / tol) / -np.log(rate)))) if rate > 0 else 2
+        rho = 1.0 / sigma1
+        plan = [(0.0, 1.0 / theta)]
+        for _ in range(1, n_steps):
+            rho_new = 1.0 / (2.0 * sigma1 - rho)
+            plan.append((rho_new * rho, 2.0 * rho_new / delta))
+            rho = rho_new
+        return plan
+
+    def inverse_stack(self, Gs: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
+                      series_ratio: float = 60.0) -> Mat:
+        """Alpha-stacked M_a = P_c (G + a^2 I)^-1 as a split pair of shape [len(a2_list) * rows_pad][p]
+        (rows >= n_rows of every block are zero), without an eigendecomposition:
+        Chebyshev iteration per alpha with a^2 < series_ratio * lam_max, truncated Neumann series in the
+        shared powers P_c G^q (q <= 3) for the others.  Gs: split pair of G (p x p); Pc: fp32 (n_rows x p)."""
+        p = Gs.rows
+        A = len(a2_list)
+        out = self.empty(A * rows_pad, p, split=True)
+        s = _vp(self.stream)
+        ld = Pc.ld
+        series = [j for j, a2 in enumerate(a2_list) if a2 >= series_ratio * lam_max]
+        cheb = [j for j in range(A) if j not in series]
+        if cheb:
+            d, x, t, r = (self.empty(n_rows, p, ld=ld) for _ in range(4))
+            dsp = self.empty(n_rows, p, split=True, ld=ld)
+            for j in cheb:
+                a2 = float(a2_list[j])
+                plan = self.chebyshev_plan(lam_max, a2)
+                src = Pc
+                for k, (c1, c2) in enumerate(plan):
+                    check(self.lib.lit_cheb_update(_vp(d.hi.data_ptr()), _vp(src.hi.data_ptr()), _vp(x.hi.data_ptr()),
+                                                   _vp(t.hi.data_ptr()), _vp(dsp.hi.data_ptr()), _vp(dsp.lo.data_ptr()), ld,
+                                                   n_rows, p, c1, c2, a2, int(k == 0), s), "cheb_update")
+                    self.launches += 1
+                    if k + 1 < len(plan):
+                        self.gemm(dsp, Gs, alpha=-1.0, Cin=t, beta=1.0, out=r)  # r = t - d G
+                        src = r
+                off = j * rows_pad * out.ld * 4
+                check(self.lib.lit_gather_rows_f32(_vp(x.hi.data_ptr()), ld, _vp(0), n_rows, p,
+                                                   _vp(out.hi.data_ptr() + off), _vp(out.lo.data_ptr() + off), out.ld,
+                                                   rows_pad, s), "gather_rows")
+                self.launches += 1
+        if series:
+            Q = [self.split(Pc)]
+            for _ in range(3):
+                Q.append(self.gemm(Q[-1], Gs, split_out=True, ld_out=ld))
+            hi = (C.c_void_p * 4)(*[q.hi.data_ptr() for q in Q])
+            lo = (C.c_void_p * 4)(*[q.lo.data_ptr() for q in Q])
+            coef = np.zeros((len(series), 4), dtype=np.float64)
+            for g, j in enumerate(series):
+                a2 = float(a2_list[j])
+                coef[g] = [(-1.0) ** q / a2 ** (q + 1) for q in range(4)]
+            d_coef = self.upload_vector(coef.reshape(-1), "f64")
+            d_slots = self.upload_vector(np.asarray(series), "i32")
+            check(self.lib.lit_poly_combine(C.cast(hi, _vp), C.cast(lo, _vp), 4, ld, n_rows, rows_pad, p,
+                                            _vp(d_coef.data_ptr()), _vp(d_slots.data_ptr()), len(series),
+                                            _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld, s), "poly_combine")
+            self.launches += 1
+        return out
 
     # ------------------------------------------------------------------ ridge kernels
     def build_alpha_stack(self, L: Mat, n_rows: int, rows_pad: int, lam, alphas_dev, n_alphas: int, normalpha: bool,

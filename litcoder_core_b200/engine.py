@@ -57,6 +57,9 @@ class RidgeConfig:
     allow_dual: bool = True  # folds with fewer training rows than features use the n x n kernel matrix
     downdate: bool = True  # inner-fold Gram / cross product by subtraction from the outer fold's
     overlap_eig: bool = True  # eigendecompositions on a side stream
+    # inner-fold solver: "eig" (syevd of every inner Gram), "chebyshev" (GEMM-only, no inner eigendecomposition),
+    # "auto" = chebyshev for primal folds when alphas are normalised and the smallest is >= 0.05 (kappa <= 401)
+    inner_solver: str = "auto"
 
 
 @dataclass
@@ -170,6 +173,7 @@ class RidgeCVEngine:
             n_i = len(d["train_rows"])
             d["owner"] = self._next_eig_owner()
             d["dual"] = bool(cfg.allow_dual and n_i < p)
+            d["cheb"] = False
             mine = d["owner"] == comm.rank
             if d["dual"]:
                 d["R"] = None
@@ -179,14 +183,17 @@ class RidgeCVEngine:
                     del XiR
                 else:
                     d["G"] = ops.empty(n_i, n_i)
-            elif d["R"] is not None and G_o is not None:
-                XRt = ops.gather_rows_T_split(X, d["R"], len(d["R_rows"]))  # (p x |R|)
-                d.update(XRt=XRt, XtT=None,
-                         G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0) if mine else ops.empty(p, p))
             else:
-                d["R"] = None
-                XtT = ops.gather_rows_T_split(X, d["train"], n_i)
-                d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if mine else ops.empty(p, p))
+                d["cheb"] = self._use_chebyshev(cfg)
+                need_G = mine  # the Gram is only needed by the rank that solves this fold
+                if d["R"] is not None and G_o is not None:
+                    XRt = ops.gather_rows_T_split(X, d["R"], len(d["R_rows"]))  # (p x |R|)
+                    d.update(XRt=XRt, XtT=None,
+                             G=ops.gemm(XRt, XRt, alpha=-1.0, Cin=G_o, beta=1.0) if need_G else ops.empty(p, p))
+                else:
+                    d["R"] = None
+                    XtT = ops.gather_rows_T_split(X, d["train"], n_i)
+                    d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if need_G else ops.empty(p, p))
             inners.append(d)
         outer["owner"] = self._next_eig_owner()
         if not outer["dual"]:
@@ -196,13 +203,59 @@ class RidgeCVEngine:
         # several ranks every eigenproblem is solved once, by rank (job index mod world), and broadcast when
         # it is consumed: X is replicated, so the 30 decompositions of a fit would otherwise be redundant.
         for d in inners + [outer]:
-            if d["owner"] != comm.rank:
+            if d.get("cheb"):
+                # GEMM-only fold: lambda_max by Lanczos now (read back once for all folds by fit_shard)
+                d["lam"], d["ticket"] = None, None
+                d["lmax_dev"] = ops.lambda_max(d["G"]) if d["owner"] == comm.rank else None
+            elif d["owner"] != comm.rank:
                 d["lam"], d["ticket"] = ops.vec(d["G"].rows), None
             elif cfg.overlap_eig:
                 d["lam"], d["ticket"] = ops.syevd_async(d["G"])
             else:
                 d["lam"], d["ticket"] = ops.syevd(d["G"]), None
         return outer, inners
+
+    @staticmethod
+    def _use_chebyshev(cfg: RidgeConfig) -> bool:
+        if cfg.inner_solver == "chebyshev":
+            return True
+        if cfg.inner_solver == "auto":
+            return bool(cfg.normalpha and len(cfg.alphas) and min(cfg.alphas) >= 0.05)
+        return False
+
+    def _solve_stack(self, X, d, alphas, cfg: RidgeConfig):
+        """Alpha-stacked P_c (G + a^2 I)^-1 of a GEMM-only fold (owner rank): (A * rows_pad x p) split pair."""
+        ops = self.ops
+        n_va = len(d["val_rows"])
+        rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
+        lam_max = float(d["lmax"])
+        if not (lam_max > 0.0) or not np.isfinite(lam_max):
+            raise FloatingPointError("inner-fold Gram has no positive eigenvalue (degenerate design)")
+        s0 = np.sqrt(np.float32(lam_max)) if cfg.normalpha else 1.0  # S[0] as the reference's fp32 scalar
+        a2 = [(float(a) * float(s0)) ** 2 for a in alphas]
+        if min(a2) * 1e4 < lam_max:
+            raise ValueError("inner_solver='chebyshev' needs alpha^2 >= 1e-4 * lambda_max; use inner_solver='eig'")
+        pm, _ = ops.col_stats(X, d["val"], n_va, ddof=0)
+        Pc = ops.gather_normalize(X, d["val"], n_va, pm, None, 2, EPS)  # centred validation design (n_v x p)
+        Lst = ops.inverse_stack(ops.split(d["G"]), Pc, n_va, rows_pad, lam_max, a2)
+        d["G"] = None
+        return Lst
+
+    def _finish_design(self, groups, cfg: RidgeConfig) -> None:
+        """After the design side of every plan is queued: read the Lanczos lambda_max of all GEMM-only folds back
+        in ONE synchronisation, and -- with several ranks -- solve this rank's folds right away so that no rank
+        waits for another one's solve when the fold is consumed.  groups: list of (X, inners)."""
+        ops = self.ops
+        mine = [(X, d) for X, inners in groups for d in inners if d.get("cheb") and d["owner"] == self.comm.rank]
+        if not mine:
+            return
+        vals = [float(ops.download(d["lmax_dev"])[0]) for _, d in mine]
+        for (X, d), v in zip(mine, vals):
+            d["lmax"] = v
+            d["lmax_dev"] = None
+        if self.comm.world > 1:
+            for X, d in mine:
+                d["Lst"] = self._solve_stack(X, d, cfg.alphas, cfg)
 
     def _next_eig_owner(self) -> int:
         owner = self._eig_jobs % self.comm.world
@@ -260,13 +313,26 @@ class RidgeCVEngine:
                     YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
                     Ct = ops.gemm(YtT, d["XtT"], split_out=True)
                     del YtT
-                Vt, _, lam = self._eig_ready(d)
-                Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
+                if d["cheb"]:
+                    # GEMM-only fold: pred_a^T = C^T [P_c (G + a^2 I)^-1]^T, no rotation into an eigenbasis
+                    Zt = Ct
+                    Lst = d.pop("Lst", None)
+                    if d["owner"] == self.comm.rank and Lst is None:
+                        Lst = self._solve_stack(X, d, cfg.alphas, cfg)
+                    if self.comm.world > 1:
+                        if Lst is None:
+                            Lst = ops.empty(n_alphas * rows_pad, X.cols, split=True)
+                        self.comm.broadcast_inplace(ops.planes(Lst), src=d["owner"])
+                    L = None
+                else:
+                    Vt, _, lam = self._eig_ready(d)
+                    Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
+                    L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
+                    del Vt
                 del Ct
-                L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
-                del Vt
             # validation design in the eigenbasis, centred and stacked over alphas
-            Lst = ops.build_alpha_stack(L, n_va, rows_pad, lam, alphas_dev, n_alphas, cfg.normalpha, cfg.singcutoff)
+            if L is not None:
+                Lst = ops.build_alpha_stack(L, n_va, rows_pad, lam, alphas_dev, n_alphas, cfg.normalpha, cfg.singcutoff)
             del Pv, L
             mean, std = ops.col_stats(Y, d["val"], n_va, ddof=1)
             Yz = ops.gather_normalize(Y, d["val"], n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
@@ -348,6 +414,7 @@ class RidgeCVEngine:
         ops = self.ops
         sp = self._single_split(n_train, XX.rows - n_train, cfg)
         outer, inners = self._design_side(XX, sp, cfg)
+        self._finish_design([(XX, inners)], cfg)
         alphas = ops.upload_vector(np.asarray(cfg.alphas, dtype=np.float64), "f64")
         corr, _ = self._inner_scores(XX, YY, sp, outer, inners, alphas, len(cfg.alphas), cfg)
         self._eig_ready(outer)  # consume the (unused) outer ticket
@@ -434,6 +501,7 @@ class RidgeCVEngine:
         for sp in staged:
             Xs, Xts = self._normalised(X, Xte_src, sp["train_rows"], sp["train"], cfg.normalize_features, same_source)
             prepared.append((Xs, Xts) + self._design_side(Xs, sp, cfg))
+        self._finish_design([(pr[0], pr[3]) for pr in prepared], cfg)
         for plan, sp in zip(plans, staged):
             Xs, Xts, outer, inners = prepared.pop(0)
             Ys, Yts = self._normalised(Y, Yte_src, sp["train_rows"], sp["train"], cfg.normalize_targets, same_source)

@@ -211,6 +211,7 @@ class NestedCVModel:
         singcutoff: float = 1e-10,
         gather_weights: bool = True,
         device_outputs: bool = False,
+        inner_solver: str = "auto",
     ) -> Tuple[Dict[str, Union[float, List[float], List[bool]]], np.ndarray, np.ndarray]:
         """Fit with nested CV (or inner CV + a given test set), per-voxel or single alpha, FDR correction.
 
@@ -218,6 +219,9 @@ class NestedCVModel:
         multi-GPU only): False returns this rank's (p x V_rank) weight block instead of the full matrix.
         ``device_outputs`` (extension): leave the weights on the device and return this rank's (p x V_rank)
         block as a torch CUDA tensor (no D2H of the 1.2 GB weight matrix).
+        ``inner_solver`` (extension): "eig" decomposes every inner-fold Gram with cuSOLVER syevd; "chebyshev"
+        solves the inner folds with GEMMs only (Lanczos lambda_max + Chebyshev iteration / Neumann series);
+        "auto" picks chebyshev when alphas are normalised and >= 0.05, else eig.
         """
         t_start = time.perf_counter()
         if alphas is None:
@@ -255,7 +259,10 @@ class NestedCVModel:
 
         cfg = RidgeConfig(alphas=alphas, alpha_fdr=alpha_fdr, single_alpha=single_alpha, normalpha=normalpha,
                           use_corr=use_corr, normalize_features=normalize_features,
-                          normalize_targets=normalize_targets, singcutoff=singcutoff, n_outer_folds=n_outer_folds)
+                          normalize_targets=normalize_targets, singcutoff=singcutoff, n_outer_folds=n_outer_folds,
+                          inner_solver=inner_solver)
+        if inner_solver not in ("auto", "eig", "chebyshev"):
+            raise ValueError(f"Unknown inner_solver: {inner_solver}")
 
         # ---- H2D: X replicated, this rank's voxel block of Y (nested_cv.py:99-100) ----
         ops = self._get_ops()

@@ -89,6 +89,9 @@ class FakeOps:
     def raw(self, x):
         return x.a if isinstance(x, FMat) else x
 
+    def planes(self, m):
+        return [m.a]
+
     def vec(self, n, dtype="f32"):
         return np.full(n, np.nan, dtype={"f32": np.float32, "f64": np.float64, "i32": np.int32, "u8": np.uint8}[dtype])
 
@@ -200,6 +203,22 @@ class FakeOps:
         G.a[...] = vt
         lam_out[...] = lam
         self.pending -= 1
+
+    # ------------------------------------------------------------------ eigendecomposition-free inner solver
+    def lambda_max(self, G, steps=96):
+        a = G.a.astype(np.float64)
+        return np.array([np.linalg.eigvalsh(0.5 * (a + a.T))[-1]])
+
+    def inverse_stack(self, Gs, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
+        assert Gs.is_split
+        p = Gs.rows
+        G = Gs.a.astype(np.float64)
+        out = np.zeros((len(a2_list) * rows_pad, p), dtype=F32)
+        for j, a2 in enumerate(a2_list):
+            M = np.linalg.solve(G + float(a2) * np.eye(p), Pc.a[:n_rows].astype(np.float64).T).T
+            out[j * rows_pad:j * rows_pad + n_rows] = M.astype(F32)
+        self.solver_calls = getattr(self, "solver_calls", 0) + 1
+        return FMat(out, split=True)
 
     # ------------------------------------------------------------------ ridge kernels
     @staticmethod

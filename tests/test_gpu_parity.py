@@ -484,3 +484,54 @@ def test_other_downsamplers_match_reference_golden(ops):
         assert np.abs(out - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), name  # what fp64 actually delivers
         if not name.startswith(("sinc", "gabor")):
             np.testing.assert_array_equal(out, ref, err_msg=name)  # membership reductions are bit-exact
+
+
+def test_gemm_only_inner_solver_kernels(ops):
+    """Lanczos lambda_max and the Chebyshev / Neumann-series stack P_c (G + a^2 I)^-1 against fp64 LAPACK."""
+    rng = np.random.default_rng(31)
+    n, p, m = 3000, 512, 300
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    for t in range(1, n):
+        X[t] = 0.6 * X[t - 1] + 0.8 * X[t]
+    for j in range(1, p):
+        X[:, j] = 0.5 * X[:, j - 1] + 0.87 * X[:, j]
+    G = X.T.astype(np.float64) @ X.astype(np.float64)
+    Gd = ops.upload_matrix(G.astype(np.float32))
+    lam = np.linalg.eigvalsh(G)
+    lmax = float(ops.lambda_max(Gd).cpu()[0])
+    assert abs(lmax - lam[-1]) <= 2e-6 * lam[-1], (lmax, lam[-1])
+    # clustered top eigenvalues (white-noise design): the Ritz value still lands within 1e-4
+    Wn = rng.standard_normal((4000, 256)).astype(np.float32)
+    Gw = Wn.T.astype(np.float64) @ Wn.astype(np.float64)
+    lw = float(ops.lambda_max(ops.upload_matrix(Gw.astype(np.float32))).cpu()[0])
+    assert abs(lw - np.linalg.eigvalsh(Gw)[-1]) <= 1e-4 * lw
+    P = rng.standard_normal((m, p)).astype(np.float32)
+    Pc = P - P.mean(0)
+    alphas = np.logspace(-1, 8, 20)
+    a2 = [(a ** 2) * lmax for a in alphas]
+    rows_pad = 512
+    st = ops.inverse_stack(ops.split(Gd), ops.upload_matrix(Pc), m, rows_pad, lmax, a2)
+    got = _mat(ops, st).astype(np.float64).reshape(20, rows_pad, p)
+    assert not got[:, m:].any()
+    G32 = Gd and ops.download_matrix(Gd).astype(np.float64)
+    for j, s in enumerate(a2):
+        exact = np.linalg.solve(G32 + s * np.eye(p), Pc.astype(np.float64).T).T
+        err = np.abs(got[j, :m] - exact).max() / np.abs(exact).max()
+        assert err < 5e-6, (j, alphas[j], err)
+
+
+def test_fit_predict_eig_solver_matches_reference_golden(ops):
+    """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
+    very small alphas; the default golden tests above exercise the GEMM-only route."""
+    import litcoder_core_b200 as L
+
+    g = load_golden("fit_predict.npz")
+    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    random.seed(7)
+    m, w, va = L.NestedCVModel("ridge_regression").fit_predict(X[:400], Y[:400], folding_type="chunked", n_outer_folds=4,
+                                                               n_inner_folds=3, chunk_length=10, alphas=alphas,
+                                                               inner_solver="eig")
+    ref_va, ref_r = g["cv_default__best_alphas"], g["cv_default__m__correlations"]
+    same = np.isclose(va, ref_va, rtol=1e-6)
+    assert same.mean() >= 0.9
+    assert np.abs(np.asarray(m["correlations"])[same] - ref_r[same]).max() < 3e-5

@@ -346,3 +346,26 @@ def test_dual_form_matches_oracle_on_fake_ops(N, p, label):
     same2 = np.isclose(a, a2)
     assert same2.mean() > 0.85
     np.testing.assert_allclose(np.asarray(m["correlations"])[same2], np.asarray(m2["correlations"])[same2], atol=5e-5)
+
+
+@pytest.mark.parametrize("name", ["tt_default", "cv_default"])
+def test_inner_solvers_agree_on_fake_ops(name):
+    """The GEMM-only inner solver and the eigendecomposition route compute the same validation scores."""
+    ops_c, ops_e = FakeOps(), FakeOps()
+    g = load_golden("fit_predict.npz")
+    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    kw = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
+    if name.startswith("tt"):
+        kw.update(X_test=X[400:], y_test=Y[400:])
+    random.seed(7)
+    mc, wc, ac = NestedCVModel("ridge_regression", ops=ops_c).fit_predict(X[:400], Y[:400], inner_solver="chebyshev", **kw)
+    random.seed(7)
+    me, we, ae = NestedCVModel("ridge_regression", ops=ops_e).fit_predict(X[:400], Y[:400], inner_solver="eig", **kw)
+    n_outer = 1 if name.startswith("tt") else 4
+    assert getattr(ops_c, "solver_calls", 0) == 3 * n_outer and ops_c.eig_calls == n_outer
+    assert getattr(ops_e, "solver_calls", 0) == 0 and ops_e.eig_calls == 4 * n_outer
+    same = np.isclose(ac, ae)
+    assert same.mean() > 0.95
+    np.testing.assert_allclose(np.asarray(mc["correlations"])[same], np.asarray(me["correlations"])[same], atol=1e-5)
+    with pytest.raises(ValueError, match="Unknown inner_solver"):
+        NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(X[:400], Y[:400], inner_solver="qr", **kw)
