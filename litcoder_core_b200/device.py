@@ -536,7 +536,7 @@ class DeviceOps:
         return out
 
     @staticmethod
-    def chebyshev_plan(lam_max: float, a2: float, tol: float = 2e-7, safety: float = 1.02):
+    def chebyshev_plan(lam_max: float, a2: float, tol: float = 1e-6, safety: float = 1.02):
         """Scalar schedule of the Chebyshev iteration for (G + a2 I) with spec(G) in [0, safety * lam_max]:
         list of (c1, c2) per step (d = c1 d + c2 r), after Saad, Iterative Methods, alg. 12.1."""
         u = safety * lam_max

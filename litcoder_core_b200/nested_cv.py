@@ -20,6 +20,7 @@ There is no CPU fallback: ``use_gpu=False`` is accepted for signature compatibil
 from __future__ import annotations
 
 import logging
+import os
 import time
 from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
@@ -261,6 +262,8 @@ class NestedCVModel:
                           use_corr=use_corr, normalize_features=normalize_features,
                           normalize_targets=normalize_targets, singcutoff=singcutoff, n_outer_folds=n_outer_folds,
                           inner_solver=inner_solver)
+        if inner_solver == "auto":
+            inner_solver = cfg.inner_solver = os.environ.get("LIT_INNER_SOLVER", "auto")  # development override
         if inner_solver not in ("auto", "eig", "chebyshev"):
             raise ValueError(f"Unknown inner_solver: {inner_solver}")
 

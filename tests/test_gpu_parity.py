@@ -257,6 +257,7 @@ def test_ridge_corr_and_weights_match_reference_golden(ops, name):
             cfg = RidgeConfig(alphas=alphas, normalpha=normalpha, use_corr=use_corr, singcutoff=1e-10)
             sp = eng.stage_plans([plan], cfg)[0]
             outer, inners = eng._design_side(Xd, sp, cfg)
+            eng._finish_design([(Xd, inners)], cfg)
             corr, _ = eng._inner_scores(Xd, Yd, sp, outer, inners, ops.upload_vector(np.asarray(alphas), "f64"),
                                         len(alphas), cfg)
             eng._eig_ready(outer)
