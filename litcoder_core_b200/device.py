@@ -553,56 +553,93 @@ class DeviceOps:
             rho = rho_new
         return plan
 
-    def inverse_stack(self, Gs: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
-                      series_ratio: float = 60.0) -> Mat:
-        """Alpha-stacked M_a = P_c (G + a^2 I)^-1 as a split pair of shape [len(a2_list) * rows_pad][p]
-        (rows >= n_rows of every block are zero), without an eigendecomposition:
-        Chebyshev iteration per alpha with a^2 < series_ratio * lam_max, truncated Neumann series in the
-        shared powers P_c G^q (q <= 3) for the others.  Gs: split pair of G (p x p); Pc: fp32 (n_rows x p)."""
-        p = Gs.rows
-        A = len(a2_list)
-        out = self.empty(A * rows_pad, p, split=True)
-        s = _vp(self.stream)
-        ld = Pc.ld
+    @staticmethod
+    def solver_partition(lam_max: float, a2_list, series_ratio: float = 60.0):
+        """Which alphas are solved by Chebyshev iteration and which by the Neumann series (a^2 >= ratio * lam_max)."""
         series = [j for j, a2 in enumerate(a2_list) if a2 >= series_ratio * lam_max]
-        cheb = [j for j in range(A) if j not in series]
+        cheb = [j for j in range(len(a2_list)) if j not in series]
+        return cheb, series
+
+    def solver_block_rows(self, n_rows: int, lam_max: float, a2_list, series_ratio: float = 60.0) -> int:
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        return (len(cheb) + (3 if series else 0)) * n_rows
+
+    def _view_rows(self, m: Mat, r0: int, rows: int) -> Mat:
+        return Mat(m.hi[r0:r0 + rows], m.lo[r0:r0 + rows] if m.lo is not None else None, rows, m.cols, ld=m.ld)
+
+    def solve_blocks(self, Gs: Mat, Pc: Mat, n_rows: int, lam_max: float, a2_list, series_ratio: float = 60.0) -> Mat:
+        """The expensive, alpha-specific part of P_c (G + a^2 I)^-1 as ONE compact fp32 matrix
+        [(n_cheb + 3) * n_rows][p]: the Chebyshev solutions of the small alphas followed by P_c G^q, q = 1..3
+        (the shared powers of the Neumann series).  This is what a rank broadcasts for a fold it owns
+        (130 MB at config 2 instead of the 755 MB alpha stack).  Gs: split pair of G (p x p); Pc: fp32 (n_rows x p)."""
+        p = Gs.rows
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        n_q = 3 if series else 0
+        block = self.zeros((len(cheb) + n_q) * n_rows, p)
+        s = _vp(self.stream)
+        ld = block.ld
         if cheb:
-            d, x, t, r = (self.empty(n_rows, p, ld=ld) for _ in range(4))
+            d, t, r = (self.empty(n_rows, p, ld=ld) for _ in range(3))
             dsp = self.empty(n_rows, p, split=True, ld=ld)
-            for j in cheb:
+            for i, j in enumerate(cheb):
                 a2 = float(a2_list[j])
                 plan = self.chebyshev_plan(lam_max, a2)
+                x = self._view_rows(block, i * n_rows, n_rows)
                 src = Pc
                 for k, (c1, c2) in enumerate(plan):
                     check(self.lib.lit_cheb_update(_vp(d.hi.data_ptr()), _vp(src.hi.data_ptr()), _vp(x.hi.data_ptr()),
-                                                   _vp(t.hi.data_ptr()), _vp(dsp.hi.data_ptr()), _vp(dsp.lo.data_ptr()), ld,
-                                                   n_rows, p, c1, c2, a2, int(k == 0), s), "cheb_update")
+                                                   _vp(t.hi.data_ptr()), _vp(dsp.hi.data_ptr()), _vp(dsp.lo.data_ptr()),
+                                                   ld, n_rows, p, c1, c2, a2, int(k == 0), s), "cheb_update")
                     self.launches += 1
+                    if k == 0 and src.ld != ld:
+                        raise ValueError("solve_blocks: Pc must share the block's pitch")
                     if k + 1 < len(plan):
                         self.gemm(dsp, Gs, alpha=-1.0, Cin=t, beta=1.0, out=r)  # r = t - d G
                         src = r
-                off = j * rows_pad * out.ld * 4
-                check(self.lib.lit_gather_rows_f32(_vp(x.hi.data_ptr()), ld, _vp(0), n_rows, p,
-                                                   _vp(out.hi.data_ptr() + off), _vp(out.lo.data_ptr() + off), out.ld,
-                                                   rows_pad, s), "gather_rows")
-                self.launches += 1
         if series:
-            Q = [self.split(Pc)]
-            for _ in range(3):
-                Q.append(self.gemm(Q[-1], Gs, split_out=True, ld_out=ld))
-            hi = (C.c_void_p * 4)(*[q.hi.data_ptr() for q in Q])
-            lo = (C.c_void_p * 4)(*[q.lo.data_ptr() for q in Q])
+            Q = self.split(Pc)
+            for q in range(3):
+                Q = self.gemm(Q, Gs, split_out=True, ld_out=ld)
+                self.axpy(1.0, Q, self._view_rows(block, (len(cheb) + q) * n_rows, n_rows))
+        return block
+
+    def assemble_stack(self, block: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
+                       series_ratio: float = 60.0) -> Mat:
+        """Alpha-stacked M_a = P_c (G + a^2 I)^-1 as a split pair [len(a2_list) * rows_pad][p] (pad rows zero) from
+        the compact block of solve_blocks: copies of the Chebyshev solutions, Neumann-series combinations
+        sum_q (-1)^q a^-2(q+1) P_c G^q for the large alphas."""
+        p = block.cols
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        out = self.empty(len(a2_list) * rows_pad, p, split=True)
+        s = _vp(self.stream)
+        for i, j in enumerate(cheb):
+            off = j * rows_pad * out.ld * 4
+            check(self.lib.lit_gather_rows_f32(_vp(block.hi.data_ptr() + i * n_rows * block.ld * 4), block.ld, _vp(0),
+                                               n_rows, p, _vp(out.hi.data_ptr() + off), _vp(out.lo.data_ptr() + off),
+                                               out.ld, rows_pad, s), "gather_rows")
+            self.launches += 1
+        if series:
+            if Pc.ld != block.ld:
+                raise ValueError("assemble_stack: Pc must share the block's pitch")
+            base = block.hi.data_ptr() + len(cheb) * n_rows * block.ld * 4
+            hi = (C.c_void_p * 4)(Pc.hi.data_ptr(), *[base + q * n_rows * block.ld * 4 for q in range(3)])
             coef = np.zeros((len(series), 4), dtype=np.float64)
             for g, j in enumerate(series):
                 a2 = float(a2_list[j])
                 coef[g] = [(-1.0) ** q / a2 ** (q + 1) for q in range(4)]
             d_coef = self.upload_vector(coef.reshape(-1), "f64")
             d_slots = self.upload_vector(np.asarray(series), "i32")
-            check(self.lib.lit_poly_combine(C.cast(hi, _vp), C.cast(lo, _vp), 4, ld, n_rows, rows_pad, p,
+            check(self.lib.lit_poly_combine(C.cast(hi, _vp), _vp(0), 4, block.ld, n_rows, rows_pad, p,
                                             _vp(d_coef.data_ptr()), _vp(d_slots.data_ptr()), len(series),
                                             _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld, s), "poly_combine")
             self.launches += 1
         return out
+
+    def inverse_stack(self, Gs: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
+                      series_ratio: float = 60.0) -> Mat:
+        """solve_blocks + assemble_stack on one rank."""
+        block = self.solve_blocks(Gs, Pc, n_rows, lam_max, a2_list, series_ratio)
+        return self.assemble_stack(block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio)
 
     # ------------------------------------------------------------------ ridge kernels
     def build_alpha_stack(self, L: Mat, n_rows: int, rows_pad: int, lam, alphas_dev, n_alphas: int, normalpha: bool,

@@ -223,23 +223,47 @@ class RidgeCVEngine:
             return bool(cfg.normalpha and len(cfg.alphas) and min(cfg.alphas) >= 0.05)
         return False
 
-    def _solve_stack(self, X, d, alphas, cfg: RidgeConfig):
-        """Alpha-stacked P_c (G + a^2 I)^-1 of a GEMM-only fold (owner rank): (A * rows_pad x p) split pair."""
+    def _scaled_alphas_sq(self, lam_max: float, alphas, cfg: RidgeConfig):
+        s0 = np.sqrt(np.float32(lam_max)) if cfg.normalpha else 1.0  # S[0] as the reference's fp32 scalar
+        return [(float(a) * float(s0)) ** 2 for a in alphas]
+
+    def _centred_val_design(self, X, d):
         ops = self.ops
         n_va = len(d["val_rows"])
-        rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
+        pm, _ = ops.col_stats(X, d["val"], n_va, ddof=0)
+        return ops.gather_normalize(X, d["val"], n_va, pm, None, 2, EPS)  # (n_v x p) fp32
+
+    def _solve_blocks(self, X, d, alphas, cfg: RidgeConfig):
+        """Owner rank: the compact solution block of a GEMM-only fold (see DeviceOps.solve_blocks)."""
+        ops = self.ops
         lam_max = float(d["lmax"])
         if not (lam_max > 0.0) or not np.isfinite(lam_max):
             raise FloatingPointError("inner-fold Gram has no positive eigenvalue (degenerate design)")
-        s0 = np.sqrt(np.float32(lam_max)) if cfg.normalpha else 1.0  # S[0] as the reference's fp32 scalar
-        a2 = [(float(a) * float(s0)) ** 2 for a in alphas]
+        a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
         if min(a2) * 1e4 < lam_max:
             raise ValueError("inner_solver='chebyshev' needs alpha^2 >= 1e-4 * lambda_max; use inner_solver='eig'")
-        pm, _ = ops.col_stats(X, d["val"], n_va, ddof=0)
-        Pc = ops.gather_normalize(X, d["val"], n_va, pm, None, 2, EPS)  # centred validation design (n_v x p)
-        Lst = ops.inverse_stack(ops.split(d["G"]), Pc, n_va, rows_pad, lam_max, a2)
+        block = ops.solve_blocks(ops.split(d["G"]), self._centred_val_design(X, d), len(d["val_rows"]), lam_max, a2)
         d["G"] = None
-        return Lst
+        return block
+
+    def _stack_from_blocks(self, X, d, n_alphas: int, rows_pad: int, alphas, cfg: RidgeConfig):
+        """Every rank: alpha stack of a GEMM-only fold from the owner's solution block (broadcast if needed)."""
+        ops, comm = self.ops, self.comm
+        n_va = len(d["val_rows"])
+        block = d.pop("block", None)
+        if d["owner"] == comm.rank and block is None:
+            block = self._solve_blocks(X, d, alphas, cfg)
+        if comm.world > 1:
+            lm = np.array([d["lmax"] if d["owner"] == comm.rank else 0.0], dtype=np.float64)
+            lam_max = float(comm.all_reduce_sum(lm)[0])
+            a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
+            if block is None:
+                block = ops.zeros(ops.solver_block_rows(n_va, lam_max, a2), X.cols)
+            comm.broadcast_inplace(ops.planes(block), src=d["owner"])
+        else:
+            lam_max = float(d["lmax"])
+            a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
+        return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2)
 
     def _finish_design(self, groups, cfg: RidgeConfig) -> None:
         """After the design side of every plan is queued: read the Lanczos lambda_max of all GEMM-only folds back
@@ -255,7 +279,7 @@ class RidgeCVEngine:
             d["lmax_dev"] = None
         if self.comm.world > 1:
             for X, d in mine:
-                d["Lst"] = self._solve_stack(X, d, cfg.alphas, cfg)
+                d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
 
     def _next_eig_owner(self) -> int:
         owner = self._eig_jobs % self.comm.world
@@ -316,13 +340,7 @@ class RidgeCVEngine:
                 if d["cheb"]:
                     # GEMM-only fold: pred_a^T = C^T [P_c (G + a^2 I)^-1]^T, no rotation into an eigenbasis
                     Zt = Ct
-                    Lst = d.pop("Lst", None)
-                    if d["owner"] == self.comm.rank and Lst is None:
-                        Lst = self._solve_stack(X, d, cfg.alphas, cfg)
-                    if self.comm.world > 1:
-                        if Lst is None:
-                            Lst = ops.empty(n_alphas * rows_pad, X.cols, split=True)
-                        self.comm.broadcast_inplace(ops.planes(Lst), src=d["owner"])
+                    Lst = self._stack_from_blocks(X, d, n_alphas, rows_pad, cfg.alphas, cfg)
                     L = None
                 else:
                     Vt, _, lam = self._eig_ready(d)

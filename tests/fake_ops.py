@@ -209,16 +209,30 @@ class FakeOps:
         a = G.a.astype(np.float64)
         return np.array([np.linalg.eigvalsh(0.5 * (a + a.T))[-1]])
 
-    def inverse_stack(self, Gs, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
+    def solve_blocks(self, Gs, Pc, n_rows, lam_max, a2_list, series_ratio=60.0):
+        """Compact per-fold solution block (here simply every alpha's exact solution, stacked)."""
         assert Gs.is_split
         p = Gs.rows
         G = Gs.a.astype(np.float64)
-        out = np.zeros((len(a2_list) * rows_pad, p), dtype=F32)
+        out = np.zeros((len(a2_list) * n_rows, p), dtype=F32)
         for j, a2 in enumerate(a2_list):
             M = np.linalg.solve(G + float(a2) * np.eye(p), Pc.a[:n_rows].astype(np.float64).T).T
-            out[j * rows_pad:j * rows_pad + n_rows] = M.astype(F32)
+            out[j * n_rows:(j + 1) * n_rows] = M.astype(F32)
         self.solver_calls = getattr(self, "solver_calls", 0) + 1
+        return FMat(out)
+
+    def assemble_stack(self, block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
+        out = np.zeros((len(a2_list) * rows_pad, block.cols), dtype=F32)
+        for j in range(len(a2_list)):
+            out[j * rows_pad:j * rows_pad + n_rows] = block.a[j * n_rows:(j + 1) * n_rows]
         return FMat(out, split=True)
+
+    def solver_block_rows(self, n_rows, lam_max, a2_list, series_ratio=60.0):
+        return len(a2_list) * n_rows
+
+    def inverse_stack(self, Gs, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
+        return self.assemble_stack(self.solve_blocks(Gs, Pc, n_rows, lam_max, a2_list), Pc, n_rows, rows_pad, lam_max,
+                                   a2_list)
 
     # ------------------------------------------------------------------ ridge kernels
     @staticmethod
