@@ -316,8 +316,10 @@ extern "C" int lit_poly_combine(const float* const* src_hi, const float* const* 
                                 long rows_pad, long cols, const double* coef, const int32_t* slots, int n_groups,
                                 float* out_hi, float* out_lo, long ld_out, void* stream) {
   LIT_REQUIRE(n_src >= 1 && n_src <= 4 && n_groups >= 0, "poly_combine: 1..4 sources");
-  LIT_REQUIRE(rows >= 0 && rows_pad >= rows && cols % 4 == 0 && ld_src % 4 == 0 && ld_out % 4 == 0,
-              "poly_combine: extents must be multiples of 4 floats");
+  // columns are processed four at a time; a ragged width is rounded up into the (never read) pitch padding
+  cols = (cols + 3) / 4 * 4;
+  LIT_REQUIRE(rows >= 0 && rows_pad >= rows && ld_src % 4 == 0 && ld_out % 4 == 0 && cols <= ld_src && cols <= ld_out,
+              "poly_combine: pitches must be multiples of 4 floats and cover the width rounded up to 4");
   if (n_groups == 0 || rows_pad == 0 || cols == 0) return LIT_OK;
   PolySources ps;
   for (int i = 0; i < 4; ++i) {

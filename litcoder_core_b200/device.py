@@ -278,15 +278,19 @@ class DeviceOps:
         rows, cols = tensor.shape
         ld = tensor.stride(0) if rows > 1 else max(cols, 1)
         if ld % 4 or tensor.data_ptr() % 16:
-            raise ValueError("row pitch must be a multiple of 4 floats and the base 16-byte aligned")
+            # TMA and the float4 kernels need a 16-byte aligned base and pitch: re-pitch on the device
+            out = self.empty(rows, cols)
+            check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr()), out.ld * 4, _vp(tensor.data_ptr()), ld * 4, cols * 4,
+                                         rows, 3, _vp(self.stream)), "memcpy_2d(D2D)")
+            return out
         view = tensor.as_strided((rows, ld), (ld, 1)) if ld != cols else tensor
         return Mat(view, None, rows, cols)
 
     def wrap_view(self, tensor, c0: int, c1: int) -> Mat:
         """Columns [c0, c1) of a resident row-major float32 CUDA matrix as a Mat (no copy)."""
+        if c0 % 4 or tensor.stride(0) % 4 or tensor.data_ptr() % 16:
+            return self.wrap(tensor[:, c0:c1].contiguous())
         full = self.wrap(tensor)
-        if c0 % 4:
-            raise ValueError("column block must start on a multiple of 4 columns (16-byte alignment)")
         return Mat(tensor[:, c0:c1], None, full.rows, c1 - c0, ld=full.ld)
 
     def raw(self, x):

@@ -536,3 +536,69 @@ def test_fit_predict_eig_solver_matches_reference_golden(ops):
     same = np.isclose(va, ref_va, rtol=1e-6)
     assert same.mean() >= 0.9
     assert np.abs(np.asarray(m["correlations"])[same] - ref_r[same]).max() < 3e-5
+
+
+@pytest.mark.parametrize("N,p,V,kw", [
+    (101, 7, 13, dict(n_outer_folds=3, n_inner_folds=3, chunk_length=5)),                      # ragged everything
+    (120, 5, 1, dict(n_outer_folds=3, n_inner_folds=3, chunk_length=10, single_alpha=True)),   # one voxel
+    (90, 1, 9, dict(n_outer_folds=3, n_inner_folds=2, folding_type="kfold")),                  # one feature
+    (200, 33, 130, dict(n_outer_folds=4, n_inner_folds=3, folding_type="timeseries")),         # inner train is a prefix
+    (160, 12, 40, dict(n_outer_folds=4, n_inner_folds=4, folding_type="group")),               # group folds
+    (150, 9, 21, dict(n_outer_folds=3, n_inner_folds=3, folding_type="chunked_trimmed", chunk_length=15)),
+    (140, 10, 17, dict(n_outer_folds=3, n_inner_folds=3, folding_type="kfold_trimmed", normalize_features=True)),
+    (60, 100, 12, dict(n_outer_folds=3, n_inner_folds=3, folding_type="chunked_contiguous", chunk_length=4)),  # p > n
+])
+def test_ragged_shapes_and_fold_types_match_oracle(ops, N, p, V, kw):
+    """Odd sizes (nothing a multiple of a tile), single voxel / feature, every folding type."""
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(N * 1000 + p)
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Y = (X[:, : min(p, 4)] @ rng.standard_normal((min(p, 4), V)) * 0.6 + rng.standard_normal((N, V))).astype(np.float32)
+    kw = dict(kw, alphas=np.logspace(-1, 3, 7))
+    if kw.get("folding_type") == "group":
+        kw["groups"] = np.repeat(np.arange(16), 10)[:N]
+    random.seed(4)
+    np.random.seed(4)
+    m, w, a = L.fit_nested_cv(features=X, targets=Y, **kw)
+    random.seed(4)
+    np.random.seed(4)
+    mo, wo, ao = O.fit_predict(X, Y, **kw)
+    assert w.shape == (p, V) and a.shape == (V,) and len(m["correlations"]) == V
+    same = np.isclose(a, ao, rtol=1e-6)
+    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
+    if p == 1:
+        # one feature: the prediction is a multiple of x for every alpha, so all alphas tie exactly and the
+        # selection is rounding noise in both implementations -- but r does not depend on it
+        assert np.abs(r - ro).max() < 1e-4
+    else:
+        assert same.mean() >= 0.75, same.mean()
+    assert np.abs(r[same] - ro[same]).max() < 1e-4
+    assert np.abs(w[:, same] - wo[:, same]).max() <= 2e-4 * max(np.abs(wo).max(), 1e-6)
+    assert set(m) == set(mo)
+
+
+def test_input_validation_and_dtypes(ops):
+    import torch
+
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(8)
+    X = rng.standard_normal((100, 6))  # float64 in, as NumPy pipelines produce
+    Y = rng.standard_normal((100, 10))
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=5, alphas=[0.5, 5.0, 50.0])
+    random.seed(0)
+    m64, w64, a64 = L.fit_nested_cv(features=X, targets=Y, **kw)
+    random.seed(0)
+    m32, w32, a32 = L.fit_nested_cv(features=X.astype(np.float32), targets=Y.astype(np.float32), **kw)
+    np.testing.assert_array_equal(w64, w32)  # float64 input is converted exactly like torch.tensor(x, dtype=float32)
+    random.seed(0)
+    mt, wt, at = L.fit_nested_cv(features=torch.from_numpy(X.astype(np.float32)).cuda(),
+                                 targets=torch.from_numpy(Y.astype(np.float32)).cuda(), **kw)
+    np.testing.assert_array_equal(wt, w32)  # resident CUDA tensors: same result, no H2D
+    with pytest.raises(ValueError, match="same number of rows"):
+        L.fit_nested_cv(features=X, targets=Y[:50], **kw)
+    with pytest.raises(ValueError, match="Unknown folding type"):
+        L.fit_nested_cv(features=X, targets=Y, folding_type="nope")
+    with pytest.raises(ValueError, match="Groups must be provided"):
+        L.fit_nested_cv(features=X, targets=Y, X_test=X, y_test=Y, folding_type="group")
