@@ -571,8 +571,8 @@ def test_ragged_shapes_and_fold_types_match_oracle(ops, N, p, V, kw):
         # one feature: the prediction is a multiple of x for every alpha, so all alphas tie exactly and the
         # selection is rounding noise in both implementations -- but r does not depend on it
         assert np.abs(r - ro).max() < 1e-4
-    else:
-        assert same.mean() >= 0.75, same.mean()
+        return
+    assert same.mean() >= 0.75, same.mean()
     assert np.abs(r[same] - ro[same]).max() < 1e-4
     assert np.abs(w[:, same] - wo[:, same]).max() <= 2e-4 * max(np.abs(wo).max(), 1e-6)
     assert set(m) == set(mo)
