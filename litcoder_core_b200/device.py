@@ -125,6 +125,7 @@ class DeviceOps:
         # (3.3 s per config-2 fit with 1 worker, 3.7 s with 2 or 3: they contend for the SMs the GEMMs leave)
         self.eig_workers = int(os.environ.get("LIT_EIG_WORKERS", "1"))
         self._eig_workers: List[object] = []
+        self._copy_stream = None
         self._eig_jobs = None
         self._eig_lock = threading.Lock()
         self.eig_pending = 0  # decompositions queued or running
@@ -267,6 +268,27 @@ class DeviceOps:
                                          cols * 4, cols * 4, nr, 3, s), "memcpy_2d(D2D)")
             self.launches += 1
         return out
+
+    @contextlib.contextmanager
+    def copy_stream(self):
+        """Run the enclosed uploads on a dedicated copy stream (ordered after the work already queued on the
+        current stream); yields a ticket whose `done` event the consumer stream must wait on (wait_copy)."""
+        t = self.torch
+        if self._copy_stream is None:
+            self._copy_stream = t.cuda.Stream(device=self.device)
+        ready = t.cuda.Event()
+        ready.record()
+        self._copy_stream.wait_event(ready)
+        ticket = _EigTicket()
+        with t.cuda.stream(self._copy_stream):
+            yield ticket
+            ticket.done = t.cuda.Event()
+            ticket.done.record()
+        ticket.issued.set()
+
+    def wait_copy(self, ticket) -> None:
+        if ticket is not None and ticket.done is not None:
+            self.torch.cuda.current_stream(self.device).wait_event(ticket.done)
 
     def wrap(self, tensor) -> Mat:
         """Adopt a resident torch CUDA float32 matrix (no copy) -- inputs already in HBM."""

@@ -497,7 +497,7 @@ class RidgeCVEngine:
     # drivers
     # ------------------------------------------------------------------------------------------
     def fit_shard(self, X, Y, plans: List[FoldPlan], cfg: RidgeConfig, X_test=None, Y_test=None,
-                  n_vox_total: Optional[int] = None) -> ShardResult:
+                  n_vox_total: Optional[int] = None, y_ready=None) -> ShardResult:
         """Run every outer fold on this rank's voxel shard.
 
         X (N x p) and Y (N x V_r) are device matrices.  In train/test mode there is one plan whose
@@ -520,6 +520,7 @@ class RidgeCVEngine:
             Xs, Xts = self._normalised(X, Xte_src, sp["train_rows"], sp["train"], cfg.normalize_features, same_source)
             prepared.append((Xs, Xts) + self._design_side(Xs, sp, cfg))
         self._finish_design([(pr[0], pr[3]) for pr in prepared], cfg)
+        ops.wait_copy(y_ready)  # the responses may still be in flight on the copy stream: first use is below
         for plan, sp in zip(plans, staged):
             Xs, Xts, outer, inners = prepared.pop(0)
             Ys, Yts = self._normalised(Y, Yte_src, sp["train_rows"], sp["train"], cfg.normalize_targets, same_source)

@@ -276,13 +276,16 @@ class NestedCVModel:
         ops.reset_counters()
         with ops.timed("h2d"):
             X = self._to_device(ops, features)
-            Y = self._to_device(ops, targets, c0, c1)
             Xt = self._to_device(ops, X_test) if train_test_mode else None
+        # The design side (Grams, lambda_max, eigendecompositions) needs X only: the responses -- 97 % of the
+        # input bytes -- travel on a copy stream meanwhile and are awaited right before their first use.
+        with ops.copy_stream() as y_ready:
+            Y = self._to_device(ops, targets, c0, c1)
             Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
 
         engine = RidgeCVEngine(ops, comm)
         with ops.timed("fit"):
-            res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox)
+            res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox, y_ready=y_ready)
         ops.check_eig()
 
         # ---- per-voxel vectors back to the host, gathered over ranks ----

@@ -60,6 +60,13 @@ class FakeOps:
     def synchronize(self):
         pass
 
+    @contextlib.contextmanager
+    def copy_stream(self):
+        yield None
+
+    def wait_copy(self, ticket):
+        pass
+
     def check_eig(self):
         assert self.pending == 0, "an eigendecomposition ticket was never waited on"
 
