@@ -111,10 +111,12 @@ __global__ void lanczos_step_kernel(const float* __restrict__ y, const float* __
   }
 }
 
-// Largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[1..m)) by Sturm bisection (fp64).
+// Largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[1..m)) by Sturm multisection (fp64):
+// one warp evaluates 32 trial points per round (5 bits per round instead of 1).
 __global__ void tridiag_lmax_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int m,
                                     float* __restrict__ out_f32, double* __restrict__ out_f64) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   // an (almost) invariant subspace ends the recurrence early: keep the leading block
   double scale = 0.0;
   for (int i = 0; i < m; ++i) scale = fmax(scale, fabs(alpha[i]));
@@ -131,8 +133,8 @@ __global__ void tridiag_lmax_kernel(const double* __restrict__ alpha, const doub
     hi = fmax(hi, alpha[i] + r);
   }
   const double tiny = 1e-300 + 1e-30 * fmax(fabs(lo), fabs(hi));
-  for (int it = 0; it < 100; ++it) {
-    const double x = 0.5 * (lo + hi);
+  for (int it = 0; it < 14; ++it) {  // 33^14 > 2^70 subdivisions of the Gershgorin interval
+    const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
     int below = 0;  // number of eigenvalues smaller than x
     double q = alpha[0] - x;
     if (fabs(q) < tiny) q = -tiny;
@@ -142,14 +144,20 @@ __global__ void tridiag_lmax_kernel(const double* __restrict__ alpha, const doub
       if (fabs(q) < tiny) q = -tiny;
       if (q < 0.0) ++below;
     }
-    if (below >= mm)
-      hi = x;  // every eigenvalue is below x
-    else
-      lo = x;
+    // lambda_max lies between the last point with an eigenvalue at or above it and the first point above all
+    const unsigned above_all = __ballot_sync(0xffffffffu, below >= mm);
+    const int first = above_all ? __ffs(above_all) - 1 : 32;
+    const double step = (hi - lo) / 33.0;
+    const double new_lo = lo + step * (double)first;       // point index first-1 (or lo itself)
+    const double new_hi = first < 32 ? lo + step * (double)(first + 1) : hi;
+    lo = new_lo;
+    hi = new_hi;
   }
   const double lam = 0.5 * (lo + hi);
-  if (out_f32) *out_f32 = (float)lam;
-  if (out_f64) *out_f64 = lam;
+  if (lane == 0) {
+    if (out_f32) *out_f32 = (float)lam;
+    if (out_f64) *out_f64 = lam;
+  }
 }
 
 // Chebyshev step on row-matrices (rows x cols):
