@@ -605,23 +605,35 @@ class DeviceOps:
         s = _vp(self.stream)
         ld = block.ld
         if cheb:
-            d, t, r = (self.empty(n_rows, p, ld=ld) for _ in range(3))
-            dsp = self.empty(n_rows, p, split=True, ld=ld)
-            for i, j in enumerate(cheb):
-                a2 = float(a2_list[j])
-                plan = self.chebyshev_plan(lam_max, a2)
-                x = self._view_rows(block, i * n_rows, n_rows)
-                src = Pc
-                for k, (c1, c2) in enumerate(plan):
-                    check(self.lib.lit_cheb_update(_vp(d.hi.data_ptr()), _vp(src.hi.data_ptr()), _vp(x.hi.data_ptr()),
-                                                   _vp(t.hi.data_ptr()), _vp(dsp.hi.data_ptr()), _vp(dsp.lo.data_ptr()),
-                                                   ld, n_rows, p, c1, c2, a2, int(k == 0), s), "cheb_update")
+            # The systems of all Chebyshev alphas advance together: one update launch per still-active system
+            # (own scalars) and ONE stacked GEMM r = t - d G per step over the rows of the active systems.
+            # cheb is in alpha order = descending step count, so the active systems are always a row prefix.
+            plans = [self.chebyshev_plan(lam_max, float(a2_list[j])) for j in cheb]
+            order = sorted(range(len(cheb)), key=lambda i: -len(plans[i]))  # work-buffer slot -> system
+            nc = len(cheb)
+            d, t, r = (self.empty(nc * n_rows, p, ld=ld) for _ in range(3))
+            dsp = self.empty(nc * n_rows, p, split=True, ld=ld)
+            if Pc.ld != ld:
+                raise ValueError("solve_blocks: Pc must share the block's pitch")
+            blk = n_rows * ld * 4  # bytes per system in every buffer
+            for k in range(len(plans[order[0]])):
+                n_active = sum(1 for i in order if k < len(plans[i]))  # a prefix of the slots
+                for slot in range(n_active):
+                    i = order[slot]
+                    c1, c2 = plans[i][k]
+                    src = Pc.hi.data_ptr() if k == 0 else r.hi.data_ptr() + slot * blk
+                    check(self.lib.lit_cheb_update(_vp(d.hi.data_ptr() + slot * blk), _vp(src),
+                                                   _vp(block.hi.data_ptr() + i * blk), _vp(t.hi.data_ptr() + slot * blk),
+                                                   _vp(dsp.hi.data_ptr() + slot * blk), _vp(dsp.lo.data_ptr() + slot * blk),
+                                                   ld, n_rows, p, c1, c2, float(a2_list[cheb[i]]), int(k == 0), s),
+                          "cheb_update")
                     self.launches += 1
-                    if k == 0 and src.ld != ld:
-                        raise ValueError("solve_blocks: Pc must share the block's pitch")
-                    if k + 1 < len(plan):
-                        self.gemm(dsp, Gs, alpha=-1.0, Cin=t, beta=1.0, out=r)  # r = t - d G
-                        src = r
+                # systems whose plan ends at this step do not need their residual any more
+                n_need = sum(1 for i in order if k + 1 < len(plans[i]))
+                if n_need:
+                    rows = n_need * n_rows
+                    self.gemm(self._view_rows(dsp, 0, rows), Gs, alpha=-1.0, Cin=self._view_rows(t, 0, rows), beta=1.0,
+                              out=self._view_rows(r, 0, rows))  # r = t - d G
         if series:
             Q = self.split(Pc)
             for q in range(3):

@@ -253,33 +253,36 @@ class RidgeCVEngine:
         block = d.pop("block", None)
         if d["owner"] == comm.rank and block is None:
             block = self._solve_blocks(X, d, alphas, cfg)
+        lam_max = float(d["lmax"])
+        a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
         if comm.world > 1:
-            lm = np.array([d["lmax"] if d["owner"] == comm.rank else 0.0], dtype=np.float64)
-            lam_max = float(comm.all_reduce_sum(lm)[0])
-            a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
             if block is None:
                 block = ops.zeros(ops.solver_block_rows(n_va, lam_max, a2), X.cols)
             comm.broadcast_inplace(ops.planes(block), src=d["owner"])
-        else:
-            lam_max = float(d["lmax"])
-            a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
         return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2)
 
     def _finish_design(self, groups, cfg: RidgeConfig) -> None:
         """After the design side of every plan is queued: read the Lanczos lambda_max of all GEMM-only folds back
-        in ONE synchronisation, and -- with several ranks -- solve this rank's folds right away so that no rank
-        waits for another one's solve when the fold is consumed.  groups: list of (X, inners)."""
-        ops = self.ops
-        mine = [(X, d) for X, inners in groups for d in inners if d.get("cheb") and d["owner"] == self.comm.rank]
-        if not mine:
+        in ONE synchronisation (and, with several ranks, exchange them in ONE all-reduce), then -- with several
+        ranks -- solve this rank's folds right away so that no rank waits for another one's solve when the fold
+        is consumed.  groups: list of (X, inners)."""
+        ops, comm = self.ops, self.comm
+        jobs = [(X, d) for X, inners in groups for d in inners if d.get("cheb")]
+        if not jobs:
             return
-        vals = [float(ops.download(d["lmax_dev"])[0]) for _, d in mine]
-        for (X, d), v in zip(mine, vals):
-            d["lmax"] = v
-            d["lmax_dev"] = None
-        if self.comm.world > 1:
-            for X, d in mine:
-                d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
+        vals = np.zeros(len(jobs), dtype=np.float64)
+        for i, (_, d) in enumerate(jobs):
+            if d["owner"] == comm.rank:
+                vals[i] = float(ops.download(d["lmax_dev"])[0])
+                d["lmax_dev"] = None
+        if comm.world > 1:
+            vals = comm.all_reduce_sum(vals)
+        for (X, d), v in zip(jobs, vals):
+            d["lmax"] = float(v)
+        if comm.world > 1:
+            for X, d in jobs:
+                if d["owner"] == comm.rank:
+                    d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
 
     def _next_eig_owner(self) -> int:
         owner = self._eig_jobs % self.comm.world
