@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LITRIDGE_ABI_VERSION 1
+#define LITRIDGE_ABI_VERSION 2
 
 const char* lit_last_error(void);
 int lit_abi_version(void);
@@ -74,6 +74,19 @@ int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda, const flo
 int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo,
                             long ldb, int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy,
                             float* dot_part, float* ssq_part, long ld_part, int variant, void* stream);
+
+/* The same fused GEMM on fp16 split pairs (kind::f16 MMAs: 16 values of K per instruction, twice the TF32 rate,
+ * half the operand bytes).  A_* / B_* are fp16 planes written by lit_split_f16 (pitches lda / ldb in fp16
+ * elements, multiples of 8); the partial sums are those of the SCALED predictions
+ * sA[v] * sB[g] * pred -- lit_corr_finalize_scaled undoes the scales.  Same reference lines as above. */
+int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+                           int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy, float* dot_part,
+                           float* ssq_part, long ld_part, int variant, void* stream);
+/* fp16 split pair of x = src_hi (+ src_lo when non-NULL):  out_hi = fp16(s x), out_lo = fp16(s x - out_hi) with one
+ * power-of-two scale s per group of rows_per_group consecutive rows, chosen so that the group's largest magnitude
+ * lands in [2^14, 2^15).  inv_scale[g] = 1/s.  scratch: 8 bytes per group.  ld_out in fp16 elements. */
+int lit_split_f16(const float* src_hi, const float* src_lo, long ld_src, long rows, long cols, long rows_per_group,
+                  void* out_hi, void* out_lo, long ld_out, float* inv_scale, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / conversion (bandwidth-bound streaming kernels)
@@ -163,6 +176,12 @@ int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, lon
 int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group, int n_groups,
                       long n_vox, long n_rows, float eps, int accumulate, int metric, const float* resp_std,
                       float* corr, long ld_corr, void* stream);
+/* lit_corr_finalize on the partial sums of lit_gemm_f16x3_nt_corr: dot and ssq are first multiplied by
+ * inv_row[v] * inv_group[g] and its square (either vector may be NULL = all ones). */
+int lit_corr_finalize_scaled(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group,
+                             int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                             const float* resp_std, const float* inv_row, const float* inv_group, float* corr,
+                             long ld_corr, void* stream);
 /* best[v] = first argmax_a mean[a][v], mean = corr_sum / n_folds (nested_cv.py:391-393,408-411);
  * alpha_out[v] = (float)alphas[best[v]].  col_sums (n_alphas doubles, may be NULL) receives
  * sum_v mean[a][v] for the single_alpha rule (nested_cv.py:396-400). */

@@ -70,16 +70,20 @@ struct GemmParams {
   long ld_part;
 };
 
-template <int BN_, int CG_>
+// F16_ = 0: operands are fp32 planes holding TF32 values (kind::tf32, 8 values of K per MMA);
+// F16_ = 1: operands are fp16 planes (kind::f16, 16 values of K per MMA, twice the TF32 rate).  A k-block is one
+// 128-byte swizzle span in both cases, so tiles, descriptors and the K offsets inside a span are byte-identical.
+template <int BN_, int CG_, int F16_ = 0>
 struct GemmShape {
   static constexpr int BM = 128;  // accumulator rows per CTA (= TMEM lanes)
   static constexpr int BN = BN_;  // accumulator columns
-  static constexpr int BK = 32;   // fp32 per k-block = one 128-byte swizzle span
+  static constexpr int ELEM = F16_ ? 2 : 4;
+  static constexpr int BK = 128 / ELEM;  // operand values per k-block = one 128-byte swizzle span
   static constexpr int CG = CG_;  // CTAs cooperating on one MMA (cta_group)
-  static constexpr int UMMA_K = 8;
+  static constexpr int UMMA_K = 32 / ELEM;
   static constexpr int B_ROWS = BN / CG;  // rows of B staged by each CTA
-  static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = B_ROWS * BK * 4;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = B_ROWS * 128;
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
   static constexpr int SMEM_BUDGET = 227 * 1024 - 2048;  // tiles; barriers + alignment slack live in the rest
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
@@ -104,12 +108,12 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   nt = r / gm;
 }
 
-template <int BN, int CG, int EPI>
-__global__ void __launch_bounds__(GemmShape<BN, CG>::THREADS, 1)
+template <int BN, int CG, int EPI, int F16 = 0>
+__global__ void __launch_bounds__(GemmShape<BN, CG, F16>::THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                    const GemmParams p) {
-  using S = GemmShape<BN, CG>;
+  using S = GemmShape<BN, CG, F16>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment (same offset in both CTAs of a pair).
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
@@ -194,7 +198,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     } else if (warp == 1) {
       // ======================= MMA issuer =======================
       if (lane == 0 && cta_rank == 0) {
-        constexpr uint32_t idesc = ptx::umma_idesc_tf32(S::BM * CG, BN);
+        constexpr uint32_t idesc = F16 ? ptx::umma_idesc_f16(S::BM * CG, BN) : ptx::umma_idesc_tf32(S::BM * CG, BN);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t cc = 0;  // running chunk counter: TMEM buffer = cc & 1
@@ -213,14 +217,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
               const uint32_t b_hi = st + 2 * S::A_BYTES, b_lo = b_hi + S::B_BYTES;
 #pragma unroll
               for (int ks = 0; ks < S::BK / S::UMMA_K; ++ks) {
-                const uint32_t koff = ks * S::UMMA_K * 4;  // bytes along K inside the swizzle span
+                const uint32_t koff = ks * S::UMMA_K * S::ELEM;  // bytes along K inside the swizzle span (32 per step)
                 const uint64_t dah = ptx::umma_desc_k_sw128(a_hi + koff);
                 const uint64_t dal = ptx::umma_desc_k_sw128(a_lo + koff);
                 const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + koff);
                 const uint64_t dbl = ptx::umma_desc_k_sw128(b_lo + koff);
-                ptx::umma_tf32<CG>(d_tmem, dal, dbh, idesc, (uint32_t)((kb != kb0) | (ks != 0)));
-                ptx::umma_tf32<CG>(d_tmem, dah, dbl, idesc, 1u);
-                ptx::umma_tf32<CG>(d_tmem, dah, dbh, idesc, 1u);
+                ptx::umma_split<CG, F16>(d_tmem, dal, dbh, idesc, (uint32_t)((kb != kb0) | (ks != 0)));
+                ptx::umma_split<CG, F16>(d_tmem, dah, dbl, idesc, 1u);
+                ptx::umma_split<CG, F16>(d_tmem, dah, dbh, idesc, 1u);
               }
               if constexpr (CG == 1)
                 ptx::umma_commit(&empty_bar[stage]);
@@ -387,20 +391,22 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // Tensor map of a row-major [rows][k] fp32 matrix (row pitch ld floats); box = box_rows x 32 floats.
-static int make_operand_map(CUtensorMap* tm, const float* base, long rows, long k, long ld, int box_rows) {
+static int make_operand_map(CUtensorMap* tm, const void* base, long rows, long k, long ld, int box_rows, int f16 = 0) {
   auto enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
     return LIT_ERR_CUDA;
   }
   LIT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "GEMM operand base must be 16-byte aligned");
-  LIT_REQUIRE(ld % 4 == 0 && ld >= k, "GEMM operand pitch must be a multiple of 4 floats and >= K (ld=%ld K=%ld)", ld,
-              k);
+  const int elem = f16 ? 2 : 4;
+  LIT_REQUIRE((ld * elem) % 16 == 0 && ld >= k, "GEMM operand pitch must be a multiple of 16 bytes and >= K (ld=%ld K=%ld)",
+              ld, k);
   cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                   dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -438,27 +444,27 @@ static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it 
   return e ? atoi(e) : 0;
 }();
 
-template <int BN, int CG, int EPI>
-static int launch_gemm(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo, long ldb,
+template <int BN, int CG, int EPI, int F16 = 0>
+static int launch_gemm(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
                        GemmParams p, cudaStream_t stream) {
-  using S = GemmShape<BN, CG>;
+  using S = GemmShape<BN, CG, F16>;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   int rc;
-  if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM))) return rc;
-  if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM))) return rc;
-  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS))) return rc;
-  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS))) return rc;
+  if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM, F16))) return rc;
+  if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM, F16))) return rc;
+  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS, F16))) return rc;
+  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS, F16))) return rc;
 
   p.num_m_tiles = (p.M + S::BM * CG - 1) / (S::BM * CG);
   p.num_n_tiles = (p.N + BN - 1) / BN;
   p.num_k_blocks = (p.K + S::BK - 1) / S::BK;
   if (p.num_k_blocks < 1) p.num_k_blocks = 1;  // K == 0 still zero-initialises the accumulator via OOB fill
   if (p.group_m <= 0) p.group_m = group_m_default(CG);
-  if (p.kc_blocks <= 0) p.kc_blocks = kc_blocks_default();
+  if (p.kc_blocks <= 0) p.kc_blocks = kc_blocks_default();  // 4 k-blocks: K = 128 (tf32) / 256 (fp16), 48 accumulations either way
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles == 0) return LIT_OK;
 
-  auto kfn = gemm_tf32x3_kernel<BN, CG, EPI>;
+  auto kfn = gemm_tf32x3_kernel<BN, CG, EPI, F16>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     LIT_CUDA_CHECK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES));
@@ -558,6 +564,42 @@ extern "C" int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, lon
       return launch_gemm<256, 1, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     case LIT_GEMM_2CTA_N256:
       return launch_gemm<256, 2, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    default:
+      set_error("unknown corr-GEMM variant %d", variant);
+      return LIT_ERR_INVALID;
+  }
+}
+
+// Same fused prediction + correlation GEMM with fp16 split pairs (see lit_split_f16): hi = fp16(s x),
+// lo = fp16(s x - hi) with a power-of-two scale s per row (A) / per alpha group (B), three kind::f16 MMAs per
+// k-step.  The 11-bit significands make the products as exact as 3xTF32, at twice the tensor-core rate and half
+// the operand bytes.  The partial sums are those of the SCALED predictions; lit_corr_finalize /
+// lit_pearson_finalize take the scale vectors to undo it.
+extern "C" int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
+                                      long ldb, int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy,
+                                      float* dot_part, float* ssq_part, long ld_part, int variant, void* stream) {
+  LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0, "negative extent");
+  LIT_REQUIRE(rows_per_group % 256 == 0, "rows_per_group must be padded to a multiple of 256 (got %d)",
+              rows_per_group);
+  LIT_REQUIRE(ld_part >= M && ldy >= M, "partial / response pitch smaller than M");
+  if (M == 0 || n_groups == 0 || rows_per_group == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = n_groups * rows_per_group;
+  p.K = K;
+  p.Yz = Yz;
+  p.ldy = ldy;
+  p.tiles_per_group = rows_per_group / 256;
+  p.dot_part = dot_part;
+  p.ssq_part = ssq_part;
+  p.ld_part = ld_part;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
+  switch (variant) {
+    case LIT_GEMM_1CTA_N256:
+      return launch_gemm<256, 1, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    case LIT_GEMM_2CTA_N256:
+      return launch_gemm<256, 2, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     default:
       set_error("unknown corr-GEMM variant %d", variant);
       return LIT_ERR_INVALID;

@@ -152,6 +152,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Same for kind::f16 with fp16 operands (A/B format 0 = f16), fp32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------
 // tcgen05: MMA issue / commit / TMEM load
 // ----------------------------------------------------------------------------
@@ -178,6 +184,37 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+template <int kCtaGroup>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if constexpr (kCtaGroup == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+template <int kCtaGroup, int kF16>
+__device__ __forceinline__ void umma_split(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if constexpr (kF16)
+    umma_f16<kCtaGroup>(tmem_d, desc_a, desc_b, idesc, accumulate);
+  else
+    umma_tf32<kCtaGroup>(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
 // Make the mbarrier track completion of all tcgen05 ops issued so far by this thread.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

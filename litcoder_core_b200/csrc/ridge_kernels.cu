@@ -308,6 +308,7 @@ __device__ __forceinline__ float nan_to_num(float x) {
 __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const float* __restrict__ ssq_part,
                                      long ld_part, int tiles_per_group, int n_groups, long n_vox, long n_rows, float eps,
                                      int accumulate, int metric, const float* __restrict__ resp_std,
+                                     const float* __restrict__ inv_row, const float* __restrict__ inv_group,
                                      float* __restrict__ corr, long ld_corr) {
   const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vox) return;
@@ -320,12 +321,18 @@ __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const f
     const float sd = resp_std[v];
     qvar = sd * sd;
   }
+  const float ir = inv_row ? inv_row[v] : 1.f;
   for (int g = 0; g < n_groups; ++g) {
     float d = 0.f, q = 0.f;
     for (int t = 0; t < tiles_per_group; ++t) {
       const long o = (long)(g * tiles_per_group + t) * ld_part + v;
       d += dot_part[o];
       q += ssq_part[o];
+    }
+    if (inv_row || inv_group) {  // fp16 split pairs: undo the power-of-two operand scales (exact)
+      const float is = ir * (inv_group ? inv_group[g] : 1.f);
+      d *= is;
+      q = q * is * is;
     }
     float c;
     if (metric == 0) {
@@ -505,8 +512,23 @@ extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, l
   LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize: the R^2 metric needs the response std");
   if (n_vox == 0 || n_groups == 0) return LIT_OK;
   corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
-      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, corr,
-      ld_corr);
+      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, nullptr,
+      nullptr, corr, ld_corr);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_corr_finalize_scaled(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
+                                        int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                        const float* resp_std, const float* inv_row, const float* inv_group,
+                                        float* corr, long ld_corr, void* stream) {
+  LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
+  LIT_REQUIRE(metric >= 0 && metric <= 3, "corr_finalize: metric must be 0..3");
+  LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize: the R^2 metric needs the response std");
+  if (n_vox == 0 || n_groups == 0) return LIT_OK;
+  corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
+      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, inv_row,
+      inv_group, corr, ld_corr);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

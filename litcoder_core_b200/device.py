@@ -51,13 +51,26 @@ class Mat:
         return f"Mat({self.rows}x{self.cols}, ld={self.ld}, split={self.is_split})"
 
 
+class MatF16:
+    """fp16 split pair of a matrix (lit_split_f16): hi = fp16(s x), lo = fp16(s x - hi) with one power-of-two
+    scale per group of `rows_per_group` rows; `inv_scale[g]` = 1/s.  Pitch `ld` in fp16 elements."""
+
+    __slots__ = ("hi", "lo", "rows", "cols", "ld", "rows_per_group", "inv_scale")
+
+    def __init__(self, hi, lo, rows: int, cols: int, ld: int, rows_per_group: int, inv_scale):
+        self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
+        self.rows_per_group, self.inv_scale = rows_per_group, inv_scale
+
+
 class Partials:
-    """Per-tile partial sums written by the fused correlation epilogue."""
+    """Per-tile partial sums written by the fused correlation epilogue.  inv_row / inv_group: the operand
+    scales to undo when the GEMM ran on fp16 split pairs (None for the 3xTF32 form)."""
 
-    __slots__ = ("dot", "ssq", "n_tiles", "ld")
+    __slots__ = ("dot", "ssq", "n_tiles", "ld", "inv_row", "inv_group")
 
-    def __init__(self, dot, ssq, n_tiles: int, ld: int):
+    def __init__(self, dot, ssq, n_tiles: int, ld: int, inv_row=None, inv_group=None):
         self.dot, self.ssq, self.n_tiles, self.ld = dot, ssq, n_tiles, ld
+        self.inv_row, self.inv_group = inv_row, inv_group
 
 
 class _EigTicket:
@@ -447,8 +460,31 @@ class DeviceOps:
             _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr() if out.is_split else 0), out.ld, self.gemm_variant,
             _vp(self.stream)), "gemm_tf32x3_nt")
 
-    def gemm_corr(self, A: Mat, B: Mat, n_groups: int, rows_per_group: int, Yz: Mat) -> Partials:
-        """Fused prediction + per-voxel reduction (see lit_gemm_tf32x3_nt_corr)."""
+    def split_f16(self, src: Mat, rows_per_group: int = 1) -> MatF16:
+        """fp16 split pair of `src` (fp32 or 3xTF32 split pair) with one scale per `rows_per_group` rows."""
+        t = self.torch
+        rows, cols = src.rows, src.cols
+        ld = round_up(max(cols, 1), 64)
+        n_groups = -(-max(rows, 1) // rows_per_group)
+        hi = t.empty((max(rows, 1), ld), dtype=t.float16, device=self.device)
+        lo = t.empty((max(rows, 1), ld), dtype=t.float16, device=self.device)
+        inv = self.vec(n_groups)
+        scratch = self.vec(2 * n_groups)
+        with self.timed("split_f16"):
+            check(self.lib.lit_split_f16(
+                _vp(src.hi.data_ptr()), _vp(src.lo.data_ptr() if src.is_split else 0), src.ld, rows, cols, rows_per_group,
+                _vp(hi.data_ptr()), _vp(lo.data_ptr()), ld, _vp(inv.data_ptr()), _vp(scratch.data_ptr()),
+                _vp(self.stream)), "split_f16")
+        self.launches += 3
+        return MatF16(hi, lo, rows, cols, ld, rows_per_group, inv)
+
+    def gemm_corr(self, A: Mat, B: Mat, n_groups: int, rows_per_group: int, Yz: Mat,
+                  precision: str = "tf32x3") -> Partials:
+        """Fused prediction + per-voxel reduction (see lit_gemm_tf32x3_nt_corr / lit_gemm_f16x3_nt_corr).
+        precision "f16x3": the operands are first re-split into scaled fp16 pairs (one scale per voxel row of A,
+        one per alpha group of B); corr_finalize undoes the scales."""
+        if precision not in ("tf32x3", "f16x3"):
+            raise ValueError(f"gemm_corr: unknown precision {precision!r}")
         if rows_per_group % self.TILE_N or B.rows != n_groups * rows_per_group or Yz.rows != rows_per_group:
             raise ValueError("gemm_corr: stacked design / response rows must be padded to the tile size")
         if Yz.cols != A.rows or A.cols != B.cols:
@@ -462,19 +498,24 @@ class DeviceOps:
         variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256, _lib.GEMM_2CTA_N256) \
             else _lib.GEMM_AUTO
         flops = 2.0 * M * (n_groups * rows_per_group) * K
+        inv_row = inv_group = None
+        fn, what = self.lib.lit_gemm_tf32x3_nt_corr, "gemm_tf32x3_nt_corr"
+        if precision == "f16x3":
+            A, B = self.split_f16(A, 1), self.split_f16(B, rows_per_group)
+            inv_row, inv_group = A.inv_scale, B.inv_scale
+            fn, what = self.lib.lit_gemm_f16x3_nt_corr, "gemm_f16x3_nt_corr"
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         self._timed.setdefault("gemm_corr", []).append((e0, e1))
         self._corr_log.append((e0, e1, flops))
         self._apply_sm_limit()
         e0.record()
-        check(self.lib.lit_gemm_tf32x3_nt_corr(
-            _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
-            n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
-            variant, _vp(self.stream)), "gemm_tf32x3_nt_corr")
+        check(fn(_vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
+                 n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
+                 variant, _vp(self.stream)), what)
         e1.record()
         self.launches += 1
         self.gemm_flops += flops
-        return Partials(dot, ssq, n_tiles, ld)
+        return Partials(dot, ssq, n_tiles, ld, inv_row, inv_group)
 
     # ------------------------------------------------------------------ eigendecomposition
     def syevd(self, G: Mat, lam=None):
@@ -704,10 +745,12 @@ class DeviceOps:
 
     def corr_finalize(self, parts: Partials, tiles_per_group: int, n_groups: int, n_vox: int, n_rows: int, eps: float,
                       corr: Mat, accumulate: bool, metric: int = 0, resp_std=None) -> None:
-        check(self.lib.lit_corr_finalize(_vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld,
-                                         tiles_per_group, n_groups, n_vox, n_rows, eps, int(accumulate), metric,
-                                         _vp(resp_std.data_ptr() if resp_std is not None else 0),
-                                         _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize")
+        ir, ig = getattr(parts, "inv_row", None), getattr(parts, "inv_group", None)
+        check(self.lib.lit_corr_finalize_scaled(
+            _vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld, tiles_per_group, n_groups, n_vox, n_rows,
+            eps, int(accumulate), metric, _vp(resp_std.data_ptr() if resp_std is not None else 0),
+            _vp(ir.data_ptr() if ir is not None else 0), _vp(ig.data_ptr() if ig is not None else 0),
+            _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize")
         self.launches += 1
 
     def argmax_alpha(self, corr_sum: Mat, n_folds: int, alphas_dev, want_sums: bool):

@@ -60,6 +60,9 @@ class RidgeConfig:
     # inner-fold solver: "eig" (syevd of every inner Gram), "chebyshev" (GEMM-only, no inner eigendecomposition),
     # "auto" = chebyshev for primal folds when alphas are normalised and the smallest is >= 0.05 (kappa <= 401)
     inner_solver: str = "auto"
+    # operand format of the fused inner-CV prediction + correlation GEMM: "tf32x3" or "f16x3" (scaled fp16 split
+    # pairs, lit_split_f16: same product accuracy, twice the tensor-core rate)
+    corr_precision: str = "f16x3"
 
 
 @dataclass
@@ -357,7 +360,7 @@ class RidgeCVEngine:
             del Pv, L
             mean, std = ops.col_stats(Y, d["val"], n_va, ddof=1)
             Yz = ops.gather_normalize(Y, d["val"], n_va, mean, std, 0 if cfg.use_corr else 2, EPS, rows_out=rows_pad)
-            parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz)
+            parts = ops.gemm_corr(Zt, Lst, n_alphas, rows_pad, Yz, precision=cfg.corr_precision)
             ops.corr_finalize(parts, rows_pad // ops.PART_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
                               accumulate=(i > 0), metric=metric, resp_std=std)
             del Zt, Lst, Yz, parts

@@ -213,6 +213,7 @@ class NestedCVModel:
         gather_weights: bool = True,
         device_outputs: bool = False,
         inner_solver: str = "auto",
+        corr_precision: str = "auto",
     ) -> Tuple[Dict[str, Union[float, List[float], List[bool]]], np.ndarray, np.ndarray]:
         """Fit with nested CV (or inner CV + a given test set), per-voxel or single alpha, FDR correction.
 
@@ -223,6 +224,9 @@ class NestedCVModel:
         ``inner_solver`` (extension): "eig" decomposes every inner-fold Gram with cuSOLVER syevd; "chebyshev"
         solves the inner folds with GEMMs only (Lanczos lambda_max + Chebyshev iteration / Neumann series);
         "auto" picks chebyshev when alphas are normalised and >= 0.05, else eig.
+        ``corr_precision`` (extension): operand format of the fused inner-CV prediction + correlation GEMM:
+        "tf32x3" (3xTF32 split pairs) or "f16x3" (scaled fp16 split pairs: same 2^-22 product accuracy, twice the
+        tensor-core rate); "auto" = "f16x3".
         """
         t_start = time.perf_counter()
         if alphas is None:
@@ -266,6 +270,11 @@ class NestedCVModel:
             inner_solver = cfg.inner_solver = os.environ.get("LIT_INNER_SOLVER", "auto")  # development override
         if inner_solver not in ("auto", "eig", "chebyshev"):
             raise ValueError(f"Unknown inner_solver: {inner_solver}")
+        if corr_precision == "auto":
+            corr_precision = os.environ.get("LIT_CORR_PRECISION", "f16x3")  # development override
+        if corr_precision not in ("tf32x3", "f16x3"):
+            raise ValueError(f"Unknown corr_precision: {corr_precision}")
+        cfg.corr_precision = corr_precision
 
         # ---- H2D: X replicated, this rank's voxel block of Y (nested_cv.py:99-100) ----
         ops = self._get_ops()

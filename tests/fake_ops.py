@@ -166,11 +166,35 @@ class FakeOps:
         self.gemm_flops += 2.0 * A.rows * B.rows * A.cols
         return FMat(d.astype(F32), split_out)
 
-    def gemm_corr(self, A, B, n_groups, rows_per_group, Yz):
+    @staticmethod
+    def _f16_pair_value(a, rows_per_group):
+        """What lit_split_f16 keeps of `a`: hi = fp16(s a), lo = fp16(s a - hi), one power-of-two scale per row
+        group with the group maximum in [2^14, 2^15); returns (hi + lo) / s as float64."""
+        a = np.asarray(a, dtype=F32)
+        n_groups = -(-a.shape[0] // rows_per_group)
+        out = np.empty(a.shape, dtype=np.float64)
+        for g in range(n_groups):
+            blk = a[g * rows_per_group:(g + 1) * rows_per_group]
+            m = float(np.abs(blk).max()) if blk.size else 0.0
+            s = F32(1.0)
+            if m > 0 and np.isfinite(m):
+                s = F32(np.ldexp(1.0, int(np.clip(15 - np.frexp(F32(m))[1], -100, 100))))
+            y = (blk * s).astype(F32)
+            with np.errstate(over="ignore"):
+                hi = y.astype(np.float16)
+                lo = (y - hi.astype(F32)).astype(np.float16)
+            out[g * rows_per_group:(g + 1) * rows_per_group] = (hi.astype(np.float64) + lo.astype(np.float64)) / float(s)
+        return out
+
+    def gemm_corr(self, A, B, n_groups, rows_per_group, Yz, precision="tf32x3"):
         assert A.is_split and B.is_split
         assert rows_per_group % self.TILE_N == 0 and B.rows == n_groups * rows_per_group
         assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
-        acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][group*R + t]
+        assert precision in ("tf32x3", "f16x3")
+        if precision == "f16x3":
+            acc = (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, rows_per_group).T).astype(F32)
+        else:
+            acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][group*R + t]
         tpg = rows_per_group // self.PART_N
         dot = np.zeros((n_groups * tpg, A.rows), dtype=F32)
         ssq = np.zeros_like(dot)

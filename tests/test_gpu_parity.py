@@ -602,3 +602,87 @@ def test_input_validation_and_dtypes(ops):
         L.fit_nested_cv(features=X, targets=Y, folding_type="nope")
     with pytest.raises(ValueError, match="Groups must be provided"):
         L.fit_nested_cv(features=X, targets=Y, X_test=X, y_test=Y, folding_type="group")
+
+
+def test_split_f16_is_bit_exact(ops):
+    """lit_split_f16 against its NumPy restatement (tests/fake_ops.py): scales, hi and lo planes bit for bit,
+    for fp32 and split-pair sources, ragged widths, wide dynamic range, zero rows."""
+    from fake_ops import FakeOps
+    rng = np.random.default_rng(11)
+    for rows, cols, rpg in [(300, 77, 1), (512, 3072, 256), (1000, 130, 1), (64, 8, 64)]:
+        a = (rng.standard_normal((rows, cols)) * np.exp(rng.uniform(-12, 12, (rows, 1)))).astype(np.float32)
+        a[:, : cols // 3] *= np.float32(1e-6)  # columns far below the row maximum (subnormal hi / lo)
+        a[5 % rows] = 0.0
+        for split in (False, True):
+            src = _split(ops, a) if split else ops.upload_matrix(a)
+            f = ops.split_f16(src, rpg)
+            hi = f.hi.cpu().numpy()[:rows, :cols].astype(np.float64)
+            lo = f.lo.cpu().numpy()[:rows, :cols].astype(np.float64)
+            inv = f.inv_scale.cpu().numpy()[: -(-rows // rpg)].astype(np.float64)
+            x = _mat(ops, src) if split else a.astype(np.float64)  # what the kernel reads (hi + lo of the TF32 pair)
+            want = FakeOps._f16_pair_value(x.astype(np.float32), rpg)
+            got = (hi + lo) * np.repeat(inv, rpg)[:rows, None]
+            np.testing.assert_array_equal(got, want)
+            gmax = np.array([np.abs(x[g * rpg:(g + 1) * rpg]).max() for g in range(len(inv))])
+            nz = gmax > 0
+            assert np.all(gmax[nz] / inv[nz] < 2.0 ** 15) and np.all(gmax[nz] / inv[nz] >= 2.0 ** 14)
+            assert np.all(inv[~nz] == 1.0)
+            # 2^-22 of the element or 2^-40 of the group maximum, whichever is larger
+            tol = np.maximum(np.abs(x) * 2.0 ** -21, np.repeat(gmax, rpg)[:rows, None] * 2.0 ** -39)
+            assert np.all(np.abs(got - x) <= tol)
+
+
+def test_gemm_corr_f16x3_matches_fp64(ops):
+    """The fp16-split form of the fused GEMM: partial sums (after undoing the scales) against fp64, at the
+    accuracy of the 3xTF32 form, for badly scaled rows and long K."""
+    rng = np.random.default_rng(6)
+    for M, G, R, K, variant in [(300, 3, 256, 64, 1), (1000, 4, 512, 200, 3), (130, 1, 2048, 96, 3),
+                                (515, 5, 256, 3072, 3)]:
+        A = (rng.standard_normal((M, K)) * np.exp(rng.uniform(-8, 8, (M, 1)))).astype(np.float32)
+        B = (rng.standard_normal((G * R, K)) * np.repeat(10.0 ** rng.uniform(-4, 4, G), R)[:, None]).astype(np.float32)
+        Yz = rng.standard_normal((R, M)).astype(np.float32)
+        old = ops.gemm_variant
+        ops.gemm_variant = variant
+        try:
+            parts = ops.gemm_corr(_split(ops, A), _split(ops, B), G, R, ops.upload_matrix(Yz), precision="f16x3")
+            ref = ops.gemm_corr(_split(ops, A), _split(ops, B), G, R, ops.upload_matrix(Yz), precision="tf32x3")
+        finally:
+            ops.gemm_variant = old
+        ir = parts.inv_row.cpu().numpy()[:M].astype(np.float64)
+        ig = parts.inv_group.cpu().numpy()[:G].astype(np.float64)
+        sc = ig[:, None] * ir[None, :]
+        dot = parts.dot.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1) * sc
+        ssq = parts.ssq.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1) * sc * sc
+        dot_t = ref.dot.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1)
+        ssq_t = ref.ssq.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1)
+        acc = A.astype(np.float64) @ B.astype(np.float64).T
+        for g in range(G):
+            blk = acc[:, g * R:(g + 1) * R]
+            want_d, want_q = (blk * Yz.T).sum(1), (blk * blk).sum(1)
+            scale_d = np.sqrt(want_q * R)  # |dot| <= ||pred|| ||y||
+            assert np.abs(dot[g] - want_d).max() <= 3e-5 * np.abs(scale_d).max()
+            np.testing.assert_allclose(dot[g] / scale_d, want_d / scale_d, atol=2e-5)
+            np.testing.assert_allclose(ssq[g], want_q, rtol=2e-5)
+            # no worse than twice the 3xTF32 form (+ fp32 summation noise)
+            e16 = np.abs(ssq[g] / want_q - 1).max()
+            e32 = np.abs(ssq_t[g] / want_q - 1).max()
+            assert e16 <= 2 * e32 + 2e-6, (e16, e32)
+
+
+def test_corr_precisions_agree_on_fit(ops):
+    """Whole fit with the fused GEMM in both operand formats: same alphas (up to near-ties), same r."""
+    from litcoder_core_b200 import NestedCVModel
+
+    rng = np.random.default_rng(21)
+    X, Y = _synthetic(rng, 600, 96, 700)
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 4, 8))
+    out = {}
+    for prec in ("tf32x3", "f16x3"):
+        random.seed(3)
+        m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision=prec, **kw)
+        out[prec] = (np.asarray(m["correlations"]), w, np.asarray(a))
+    same = out["tf32x3"][2] == out["f16x3"][2]
+    assert same.mean() > 0.97, same.mean()
+    assert np.abs(out["tf32x3"][0][same] - out["f16x3"][0][same]).max() < 2e-5
+    with pytest.raises(ValueError, match="Unknown corr_precision"):
+        NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision="bf16", **kw)
