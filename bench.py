@@ -310,16 +310,36 @@ def run_b200(args):
         flops = statistics.mean(fl for _, fl in big)
         achieved = flops / avg_ms / 1e9  # TFLOP/s, algorithmic 2*M*N*K
         peak = peaks["bf16_tflops_sustained"]
-        traffic = None  # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel and shape
-        tpath = os.path.join(ROOT, "profiles", "corr_gemm_traffic.json")
+        prec = model.last_stats.get("corr_precision", "tf32x3")
+        f16 = prec == "f16x3"
+        # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel and shape
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "corr_gemm_f16x3_traffic.json" if f16 else "corr_gemm_traffic.json")
         if os.path.exists(tpath) and world == 1 and not args.voxels and args.workload.startswith("config2"):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = os.path.relpath(tpath, ROOT)
+        if f16:
+            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR,F16> via lit_gemm_f16x3_nt_corr"
+            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 kind::f16 MMAs per "
+                    "product on scaled fp16 hi/lo pairs (same 2^-22 product accuracy as 3xTF32); fp16 runs at the "
+                    "bf16 rate, so the ceiling of the method is peak/3 and the tensor pipe itself sustains 3x this figure")
+            pipe = {"executed_f16_tflops": 3 * achieved, "f16_dense_peak": peak, "frac": 3 * achieved / peak}
+        else:
+            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR> via lit_gemm_tf32x3_nt_corr"
+            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 TF32 MMAs per "
+                    "product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the tensor pipe "
+                    "itself sustains 3x this figure against a TF32 dense rate of about peak/2")
+            pipe = {"executed_tf32_tflops": 3 * achieved, "tf32_dense_peak_est": peak / 2,
+                    "frac": 3 * achieved / (peak / 2)}
         line = {
             "metric": METRIC, "value": units / (ms_value / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulation)", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f32 (split-precision tensor-core products: %s in the fused prediction GEMM, 3xTF32 elsewhere; "
+                     "fp32 accumulation)" % ("fp16 hi/lo pairs x3" if f16 else "3xTF32"),
+            "data": "synthetic",
             "config": {"workload": args.workload, "TRs": N, "features": p, "voxels": V, "alphas": A,
                        "folds": f"{Ko}x{Ki} chunked({chunk})", "parallelism": f"voxel-sharded x{world}",
                        "l2": "inputs (3.6 GB of responses) exceed the 126 MB L2; no flush needed"},
@@ -329,16 +349,13 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": "gemm_tf32x3_kernel<256,2,EPI_CORR> (alpha-stacked predictions + fused per-voxel correlation)",
+                "kernel": kname + " (alpha-stacked predictions + fused per-voxel correlation)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": f"{peaks['source']} cuBLAS bf16 dense, sustained (kernel timed inside a long step)",
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "traffic_source": traffic_src,
                 "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
-                "note": ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 TF32 MMAs per "
-                         "product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the tensor pipe "
-                         "itself sustains 3x this figure against a TF32 dense rate of about peak/2"),
-                "tensor_pipe": {"executed_tf32_tflops": 3 * achieved, "tf32_dense_peak_est": peak / 2,
-                                "frac": 3 * achieved / (peak / 2)},
+                "note": note, "tensor_pipe": pipe,
             },
             "phases_ms": {k: round(v, 2) for k, v in sorted(phase.items())},
             "e2e_phases_ms": {k: round(v, 2) for k, v in sorted(e2e_phase.items())},

@@ -236,6 +236,14 @@ int lit_fisher_combine(const double* p, long ld_p, int n_folds, long n_vox, int 
  * (circpad: index mod nt).  dtype_in: 0 = f32, 1 = f64.  out is [nt][ndelays*ndim] f64, pitch ld_out. */
 int lit_fir_make_delayed(const void* stim, int dtype_in, long nt, long ndim, long ld_stim, const int32_t* delays,
                          int ndelays, int circpad, double* out, long ld_out, void* stream);
+/* FIR delay stacking fused with the trainers' per-story structuring (trainer.py:203-209,236-239,250-253;
+ * encoding/utils.py:23-29): rows [row_start, row_stop) of the delayed matrix of one story, column z-scored with the
+ * population std over those rows (a zero-std column is centred only), NaN -> 0, written as fp32 to out
+ * [row_stop - row_start][ndelays*ndim] (pitch ld_out) -- typically a row block of the design matrix X.
+ * zscore = 0 copies the trimmed delayed rows unchanged (concatenated mode, trainer.py:264-282). */
+int lit_fir_zscore_rows(const void* stim, int dtype_in, long nt, long ndim, long ld_stim, const int32_t* delays,
+                        int ndelays, int circpad, long row_start, long row_stop, int zscore, float* out, long ld_out,
+                        void* stream);
 /* Lanczos resampling (interpdata.py:45-63,87-126): out = W * data, W[i][j] = lanczos((tr_i - t_j) * cutoff),
  * cutoff = cutoff_mult / mean(diff(tr_times)) computed by the caller.  rectify -> out is [n_tr][2*ndim]
  * (negative part | positive part).  lo/hi (n_tr + 1 int32, or NULL) bound the contributing samples of

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "lit_bh_fdr": [_vp, _l, _d, _vp, _vp, _vp, _vp, _sz, _vp],
     "lit_fisher_combine": [_vp, _l, _i, _l, _i, _vp, _vp],
     "lit_fir_make_delayed": [_vp, _i, _l, _l, _l, _vp, _i, _i, _vp, _l, _vp],
+    "lit_fir_zscore_rows": [_vp, _i, _l, _l, _l, _vp, _i, _i, _l, _l, _i, _vp, _l, _vp],
     "lit_lanczos_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _d, _d, _i, _vp, _vp, _vp, _l, _vp],
     "lit_lanczos_lambda_max": [_vp, _l, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "lit_cheb_update": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _l, _f, _f, _f, _i, _vp],

@@ -262,6 +262,78 @@ __global__ void gabor_kernel(const T* __restrict__ data, long n_samples, long nd
   if (active) out[i * ld_out + pair] = sqrt(re * re + im * im);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused FIR delay stacking + per-story trim + column z-score + nan_to_num, written as fp32 straight into the
+// rows of the design matrix that fit_predict consumes (the float64 delayed matrix never exists):
+//   trainer.py:203-209 (apply_fir_delays), :236-239 / :250-253 (zs of the trimmed story, nan_to_num),
+//   encoding/utils.py:23-29 (zs: population std; a zero-std column is centred only).
+// Column (delay i, feature c) of the delayed matrix is feature c shifted by delays[i], so its statistics over
+// the trimmed rows [row_start, row_stop) are those of stim[row_start - d .. row_stop - d) with zero fill.
+// Block = 32 columns x 8 row slices; fp64 moments about the column's first value (a constant column gets an
+// exact zero std), three passes over the (L2-resident) story.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ double fir_value(const T* __restrict__ stim, long nt, long ld_stim, long t, long d, long c,
+                                            int circpad) {
+  long ts = t - d;
+  bool valid = ts >= 0 && ts < nt;
+  if (!valid && circpad && nt > 0) {
+    ts = (d < nt && -d < nt) ? ((ts % nt) + nt) % nt : t;
+    valid = true;
+  }
+  return valid ? (double)stim[ts * ld_stim + c] : 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fir_zscore_kernel(const T* __restrict__ stim, long nt, long ndim, long ld_stim, const int32_t* __restrict__ delays,
+                  int ndelays, int circpad, long row_start, long row_stop, int zscore, float* __restrict__ out,
+                  long ld_out) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long j = (long)blockIdx.x * 32 + tx;  // output column = delay * ndim + feature
+  const bool col_ok = j < ndim * ndelays;
+  const long c = col_ok ? j % ndim : 0;
+  const long d = col_ok ? (long)delays[j / ndim] : 0;
+  const long n = row_stop - row_start;
+  double mean = 0.0, inv_std = 1.0;
+  if (zscore) {
+    const double shift = col_ok ? fir_value(stim, nt, ld_stim, row_start, d, c, circpad) : 0.0;
+    double acc = 0.0;
+    if (col_ok)
+      for (long t = row_start + ty; t < row_stop; t += 8) acc += fir_value(stim, nt, ld_stim, t, d, c, circpad) - shift;
+    red[ty][tx] = acc;
+    __syncthreads();
+    acc = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc += red[y][tx];
+    mean = shift + acc / (double)n;
+    __syncthreads();
+    double ssq = 0.0;
+    if (col_ok)
+      for (long t = row_start + ty; t < row_stop; t += 8) {
+        const double e = fir_value(stim, nt, ld_stim, t, d, c, circpad) - mean;
+        ssq += e * e;
+      }
+    red[ty][tx] = ssq;
+    __syncthreads();
+    ssq = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) ssq += red[y][tx];
+    const double sd = sqrt(ssq / (double)n);
+    inv_std = (sd != 0.0) ? 1.0 / sd : 1.0;  // NaN std: `s != 0` holds in the reference too -> NaN column -> 0
+  }
+  if (!col_ok) return;
+  for (long t = row_start + ty; t < row_stop; t += 8) {
+    double v = fir_value(stim, nt, ld_stim, t, d, c, circpad);
+    if (zscore) {
+      v = (v - mean) * inv_std;
+      if (isnan(v)) v = 0.0;  // np.nan_to_num; +-inf become +-DBL_MAX there, i.e. +-inf again once cast to fp32
+    }
+    out[(t - row_start) * ld_out + j] = (float)v;
+  }
+}
+
 }  // namespace lit
 
 using namespace lit;
@@ -386,6 +458,28 @@ extern "C" int lit_gabor_downsample(const void* data, int dtype_in, long n_sampl
   else
     gabor_kernel<double, 256><<<grid, block, 0, s>>>((const double*)data, n_samples, ndim, ld_data, data_times,
                                                      tr_times, freqs, n_freq, sigma, out, ld_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_fir_zscore_rows(const void* stim, int dtype_in, long nt, long ndim, long ld_stim,
+                                   const int32_t* delays, int ndelays, int circpad, long row_start, long row_stop,
+                                   int zscore, float* out, long ld_out, void* stream) {
+  LIT_REQUIRE(nt >= 0 && ndim >= 0 && ndelays >= 0, "fir_zscore: negative extent");
+  LIT_REQUIRE(ld_stim >= ndim && ld_out >= ndim * ndelays, "fir_zscore: pitch too small");
+  LIT_REQUIRE(dtype_in == 0 || dtype_in == 1, "fir_zscore: dtype_in must be 0 (f32) or 1 (f64)");
+  LIT_REQUIRE(row_start >= 0 && row_stop <= nt && row_start <= row_stop, "fir_zscore: trimmed rows [%ld, %ld) outside [0, %ld)",
+              row_start, row_stop, nt);
+  const long ncols = ndim * ndelays;
+  if (ncols == 0 || row_stop == row_start) return LIT_OK;
+  const unsigned grid = (unsigned)((ncols + 31) / 32);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype_in == 0)
+    fir_zscore_kernel<float><<<grid, 256, 0, s>>>((const float*)stim, nt, ndim, ld_stim, delays, ndelays, circpad,
+                                                  row_start, row_stop, zscore, out, ld_out);
+  else
+    fir_zscore_kernel<double><<<grid, 256, 0, s>>>((const double*)stim, nt, ndim, ld_stim, delays, ndelays, circpad,
+                                                   row_start, row_stop, zscore, out, ld_out);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

@@ -412,9 +412,12 @@ class DeviceOps:
         return mean, std
 
     def gather_normalize(self, src: Mat, idx, n: int, mean, std, mode: int, eps: float,
-                         rows_out: Optional[int] = None, split: bool = False) -> Mat:
+                         rows_out: Optional[int] = None, split: bool = False, out: Optional[Mat] = None) -> Mat:
         rows_out = n if rows_out is None else rows_out
-        out = self.empty(rows_out, src.cols, split=split)
+        if out is None:
+            out = self.empty(rows_out, src.cols, split=split)
+        elif out.rows != rows_out or out.cols != src.cols or out.is_split != split:
+            raise ValueError("gather_normalize: destination does not match")
         check(self.lib.lit_gather_normalize_rows(
             _vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr() if idx is not None else 0), n, src.cols,
             _vp(mean.data_ptr()), _vp(std.data_ptr() if std is not None else 0), mode, eps, _vp(out.hi.data_ptr()),
@@ -826,6 +829,43 @@ class DeviceOps:
         self.launches += 1
         t.from_numpy(out_h).copy_(d_out)
         return out_h
+
+    def row_view(self, m: Mat, r0: int, rows: int) -> Mat:
+        """Rows [r0, r0 + rows) of a Mat as a Mat sharing its storage."""
+        if r0 < 0 or rows < 0 or r0 + rows > m.rows:
+            raise ValueError("row_view: rows outside the matrix")
+        return self._view_rows(m, r0, rows)
+
+    def upload_into(self, host: np.ndarray, out: Mat) -> None:
+        """H2D of a 2-D float32 / float64 host block into the rows of `out` (float64 is converted on the device)."""
+        host = np.asarray(host)
+        if host.shape != (out.rows, out.cols):
+            raise ValueError("upload_into: shape mismatch")
+        if out.rows == 0 or out.cols == 0:
+            return
+        tmp = self.upload_matrix(host)
+        check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr()), out.ld * 4, _vp(tmp.hi.data_ptr()), tmp.ld * 4,
+                                     out.cols * 4, out.rows, 3, _vp(self.stream)), "memcpy_2d(D2D)")
+
+    def fir_zscore_rows(self, stim: np.ndarray, delays, circpad: bool, row_start: int, row_stop: int, zscore: bool,
+                        out: Mat) -> None:
+        """Rows [row_start, row_stop) of FIR.make_delayed(stim, delays), z-scored per column over those rows
+        (population std; zero-std columns centred only; NaN -> 0) when `zscore`, written as fp32 into `out`
+        (lit_fir_zscore_rows: trainer.py:203-209,236-239 fused; the float64 delayed matrix is never formed)."""
+        stim, d_stim, dt = self._feature_in(stim)
+        nt, ndim = stim.shape
+        nd = len(delays)
+        if out.rows != row_stop - row_start or out.cols != nd * ndim:
+            raise ValueError("fir_zscore_rows: destination does not match")
+        d_del = self.upload_vector(np.asarray(delays, dtype=np.int64), "i32")
+        check(self.lib.lit_fir_zscore_rows(_vp(d_stim.data_ptr()), dt, nt, ndim, ndim, _vp(d_del.data_ptr()), nd,
+                                           int(bool(circpad)), row_start, row_stop, int(bool(zscore)),
+                                           _vp(out.hi.data_ptr()), out.ld, _vp(self.stream)), "fir_zscore_rows")
+        self.launches += 1
+
+    def as_tensor(self, m: Mat):
+        """The logical [rows][cols] block of a Mat as a torch CUDA tensor (a view; no copy)."""
+        return m.hi[: m.rows, : m.cols]
 
     def _feature_in(self, data: np.ndarray):
         data = np.ascontiguousarray(data)

@@ -341,7 +341,7 @@ class NestedCVModel:
         self.last_timings["wall_ms"] = (time.perf_counter() - t_start) * 1e3
         self.last_timings["host_weights_ms"] = t_w
         self.last_timings["host_stats_metrics_ms"] = (t_stats_end - t_s0) * 1e3
-        self.last_stats = {"launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
+        self.last_stats = {"corr_precision": cfg.corr_precision, "launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
                            "world": comm.world, "voxels_this_rank": c1 - c0,
                            "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0)}
         if hasattr(ops, "corr_launches"):

@@ -348,6 +348,41 @@ def zs(v: np.ndarray) -> np.ndarray:
     return m
 
 
+# ----------------------------------------------------------------------------------------------
+# the trainers' data structuring between FIR and fit_predict  (encoding/trainer.py:203-282)
+# ----------------------------------------------------------------------------------------------
+def apply_fir_delays(features: dict, delays: Sequence[int]) -> dict:
+    """trainer.py:203-209: FIR.make_delayed per story (insertion order kept)."""
+    return {story: fir_make_delayed(feat, delays) for story, feat in features.items()}
+
+
+def create_train_test_split(features: dict, brain_data: dict, trimming_config: dict) -> dict:
+    """trainer.py:223-262 (LeBel style): the last story is the test set; per story: trim, zs; the stimulus
+    side additionally goes through nan_to_num after the vstack."""
+    stories = list(features.keys())
+    train, test = stories[:-1], stories[-1:]
+    g = trimming_config.get
+
+    def side(names, prefix):
+        fs, fe = g(f"{prefix}_features_start", 0), g(f"{prefix}_features_end", None)
+        ts, te = g(f"{prefix}_targets_start", 0), g(f"{prefix}_targets_end", None)
+        X = np.nan_to_num(np.vstack([zs(features[s][fs:fe]) for s in names]))
+        Y = np.vstack([zs(brain_data[s][ts:te]) for s in names])
+        return X, Y
+
+    X_train, Y_train = side(train, "train")
+    X_test, Y_test = side(test, "test")
+    return {"Rstim": X_train, "Rresp": Y_train, "Pstim": X_test, "Presp": Y_test}
+
+
+def create_concatenated_data(features: dict, brain_data: dict, story_order: Sequence[str], trimming_config: dict) -> dict:
+    """trainer.py:264-282 (LPP / Narratives style): concatenate the stories, then trim ONCE; no z-scoring."""
+    g = trimming_config.get
+    X = np.concatenate([features[s] for s in story_order], axis=0)
+    Y = np.concatenate([brain_data[s] for s in story_order], axis=0)
+    return {"X": X[g("features_start", 0):g("features_end", None)], "Y": Y[g("targets_start", 0):g("targets_end", None)]}
+
+
 def find_best_alphas(X, Y, splits, alphas, single_alpha=False, normalpha=False, use_corr=True,
                      singcutoff=1e-10, return_corrs=False):
     """nested_cv._find_best_alphas (:334-415)."""

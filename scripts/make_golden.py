@@ -349,10 +349,64 @@ def extra_golden():
     print("downsample_extra.npz written")
 
 
+def structure_golden():
+    """The trainers' data structuring between FIR and fit_predict (encoding/trainer.py:203-282): apply_fir_delays,
+    _create_train_test_split (per-story trim -> zs -> nan_to_num -> vstack) and _create_concatenated_data, called as
+    unbound methods of the unmodified AbstractTrainer on a stand-in `self` that only carries the attributes they read."""
+    import_reference()
+    for n in ("encoding.plotting", "encoding.plotting.plotting_utils"):  # matplotlib / nilearn loggers: not executed
+        _stub(n, BrainPlotter=object, TensorBoardLogger=object, WandBLogger=object)
+    from encoding.trainer import AbstractTrainer
+
+    rng = np.random.default_rng(77)
+    stories = ["s0", "s1", "s2", "s3"]
+    delays = [1, 2, 3, 4]
+    D, V = 5, 7
+    n_full = {"s0": 75, "s1": 68, "s2": 90, "s3": 120}
+    out = {"stories": np.asarray(stories), "delays": np.asarray(delays)}
+    feats, brain = {}, {}
+    for s in stories:
+        f = np.cumsum(rng.standard_normal((n_full[s], D)), axis=0) * 0.3 + rng.standard_normal((n_full[s], D))
+        feats[s] = f  # float64, as the Lanczos downsampler returns
+        b = rng.standard_normal((n_full[s] - 15, V)).astype(np.float32) * 2 + 1
+        brain[s] = b
+    feats["s1"][:, 2] = 0.75          # constant feature: centred only (std == 0)
+    feats["s2"][20, 4] = np.nan       # NaN feature -> whole delayed columns NaN after zs -> nan_to_num -> 0
+    brain["s0"][:, 3] = -2.0          # constant voxel in one story
+    brain["s3"] = brain["s3"].astype(np.float64)  # mixed dtypes across stories (vstack promotes)
+    for s in stories:
+        out[f"feat__{s}"], out[f"brain__{s}"] = feats[s], brain[s]
+    cfg_tt = {"train_features_start": 10, "train_features_end": -5, "train_targets_start": 0, "train_targets_end": None,
+              "test_features_start": 50, "test_features_end": -5, "test_targets_start": 40, "test_targets_end": None}
+    cfg_cc = {"features_start": 14, "features_end": -9, "targets_start": 14, "targets_end": -9}
+    me = types.SimpleNamespace(fir_delays=delays, trimming_config=cfg_tt, stories_to_process=stories)
+    with quiet():
+        delayed = AbstractTrainer.apply_fir_delays(me, {s: feats[s] for s in stories})
+        tt = AbstractTrainer._create_train_test_split(me, delayed, {s: brain[s] for s in stories})
+        me.trimming_config = cfg_cc
+        # concatenated mode: brain data and features have the same per-story length
+        brain_cc = {s: np.vstack([brain[s], brain[s][:15]]) for s in stories}
+        cc = AbstractTrainer._create_concatenated_data(me, delayed, brain_cc)
+    for k, v in tt.items():
+        out[f"tt__{k}"] = v
+    for k, v in cc.items():
+        out[f"cc__{k}"] = v
+    for k, v in cfg_tt.items():
+        out[f"cfg_tt__{k}"] = np.asarray(np.nan if v is None else v, dtype=np.float64)
+    for k, v in cfg_cc.items():
+        out[f"cfg_cc__{k}"] = np.asarray(np.nan if v is None else v, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "structure.npz"), **out)
+    print("structure.npz written", {k: (v.shape, v.dtype) for k, v in list(tt.items()) + list(cc.items())})
+
+
 if __name__ == "__main__":
-    if "--extra-only" in sys.argv:
-        os.makedirs(OUT, exist_ok=True)
+    os.makedirs(OUT, exist_ok=True)
+    if "--structure-only" in sys.argv:
+        structure_golden()
+    elif "--extra-only" in sys.argv:
         extra_golden()
+        structure_golden()
     else:
         main()
         extra_golden()
+        structure_golden()

@@ -139,7 +139,51 @@ class FakeOps:
         var = ((r64 - mean) ** 2).sum(0) / (n - ddof) if n - ddof > 0 else np.full(src.cols, np.nan)
         return mean.astype(F32), np.sqrt(var).astype(F32)
 
-    def gather_normalize(self, src, idx, n, mean, std, mode, eps, rows_out=None, split=False):
+    def row_view(self, m, r0, rows):
+        assert 0 <= r0 and r0 + rows <= m.rows
+        v = FMat.__new__(FMat)
+        v.a, v.is_split = m.a[r0:r0 + rows], m.is_split
+        return v
+
+    def upload_into(self, host, out):
+        host = np.asarray(host)
+        assert host.shape == (out.rows, out.cols)
+        self.h2d_bytes += host.nbytes
+        out.a[...] = host.astype(F32)
+
+    def fir_zscore_rows(self, stim, delays, circpad, row_start, row_stop, zscore, out):
+        """NumPy restatement of lit_fir_zscore_rows (fp64 moments, fp32 output)."""
+        stim = np.asarray(stim, dtype=np.float64)
+        nt, ndim = stim.shape
+        blocks = []
+        for d in delays:
+            b = np.zeros((nt, ndim))
+            if circpad and abs(d) < nt:
+                b = np.roll(stim, d, axis=0)
+            elif circpad:
+                b = stim.copy()
+            elif d >= 0:
+                b[d:] = stim[:nt - d] if d < nt else 0
+            else:
+                b[:d] = stim[-d:] if -d < nt else 0
+            blocks.append(b)
+        x = np.hstack(blocks)[row_start:row_stop]
+        assert out.rows == x.shape[0] and out.cols == x.shape[1]
+        if zscore:
+            with np.errstate(invalid="ignore", divide="ignore"):
+                shift = x[:1]
+                mean = shift + (x - shift).mean(0)
+                sd = np.sqrt(((x - mean) ** 2).mean(0))
+                x = (x - mean) * np.where(sd != 0, 1.0 / sd, 1.0)
+            x = np.where(np.isnan(x), 0.0, x)
+        with np.errstate(over="ignore"):
+            out.a[...] = x.astype(F32)
+        self.launches += 1
+
+    def as_tensor(self, m):
+        return m.a
+
+    def gather_normalize(self, src, idx, n, mean, std, mode, eps, rows_out=None, split=False, out=None):
         rows_out = n if rows_out is None else rows_out
         rows = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
         x = rows - mean[None, :].astype(F32)
@@ -151,6 +195,11 @@ class FakeOps:
                 x = x * sc[None, :]
             elif mode == 3:
                 x = x * np.where(std != 0, F32(1) / std, F32(1)).astype(F32)[None, :]
+        if out is not None:
+            assert out.rows == rows_out and out.cols == src.cols
+            out.a[...] = 0
+            out.a[:n] = x
+            return out
         out = np.zeros((rows_out, src.cols), dtype=F32)
         out[:n] = x
         return FMat(out, split)

@@ -686,3 +686,52 @@ def test_corr_precisions_agree_on_fit(ops):
     assert np.abs(out["tf32x3"][0][same] - out["f16x3"][0][same]).max() < 2e-5
     with pytest.raises(ValueError, match="Unknown corr_precision"):
         NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision="bf16", **kw)
+
+
+def test_structure_kernels_match_reference_trainer(ops):
+    """lit_fir_zscore_rows + the response-side z-scoring against the unmodified trainer's outputs
+    (tests/golden/structure.npz), then the resident outputs straight into fit_predict."""
+    import torch
+
+    import litcoder_core_b200 as L
+
+    g = load_golden("structure.npz")
+    stories = [str(x) for x in g["stories"]]
+    feats = {s: g[f"feat__{s}"] for s in stories}
+    brain = {s: g[f"brain__{s}"] for s in stories}
+    delays = [int(d) for d in g["delays"]]
+
+    def cfg(prefix):
+        out = {}
+        for k in g.files:
+            if k.startswith(prefix):
+                v = float(g[k])
+                out[k[len(prefix):]] = None if np.isnan(v) else int(v)
+        return out
+
+    tt = L.create_train_test_split(feats, brain, cfg("cfg_tt__"), fir_delays=delays)
+    for k in ("Rstim", "Rresp", "Pstim", "Presp"):
+        want = g[f"tt__{k}"]
+        assert tt[k].dtype == np.float32 and tt[k].shape == want.shape
+        np.testing.assert_allclose(tt[k], want.astype(np.float32), rtol=1e-5, atol=2e-6)
+    f32 = {s: feats[s].astype(np.float32) for s in stories}  # float32 features take the other kernel instantiation
+    tt32 = L.create_train_test_split(f32, brain, cfg("cfg_tt__"), fir_delays=delays)
+    np.testing.assert_allclose(tt32["Rstim"], g["tt__Rstim"].astype(np.float32), rtol=1e-4, atol=1e-4)
+    brain_cc = {s: np.vstack([brain[s], brain[s][:15]]) for s in stories}
+    cc = L.create_concatenated_data(feats, brain_cc, stories, cfg("cfg_cc__"), fir_delays=delays)
+    np.testing.assert_array_equal(cc["X"], g["cc__X"].astype(np.float32))
+    np.testing.assert_array_equal(cc["Y"], g["cc__Y"].astype(np.float32))
+    # circular padding and negative delays go through the same index rule as lit_fir_make_delayed
+    for dl, circ in (([-2, 0, 3], False), ([1, -1, 80], True)):
+        got = L.create_concatenated_data({"a": feats["s0"]}, {"a": brain["s0"]}, ["a"], {}, fir_delays=dl, circpad=circ)
+        np.testing.assert_array_equal(got["X"], O.fir_make_delayed(feats["s0"], dl, circ).astype(np.float32))
+    # resident outputs feed fit_predict without a host round trip
+    dev = L.create_train_test_split(feats, brain, cfg("cfg_tt__"), fir_delays=delays, device_outputs=True)
+    assert all(isinstance(v, torch.Tensor) and v.is_cuda for v in dev.values())
+    kw = dict(n_inner_folds=3, chunk_length=10, alphas=np.logspace(0, 3, 4))
+    random.seed(1)
+    m1, w1, a1 = L.fit_nested_cv(features=dev["Rstim"], targets=dev["Rresp"], X_test=dev["Pstim"], y_test=dev["Presp"], **kw)
+    random.seed(1)
+    m2, w2, a2 = L.fit_nested_cv(features=tt["Rstim"], targets=tt["Rresp"], X_test=tt["Pstim"], y_test=tt["Presp"], **kw)
+    np.testing.assert_array_equal(w1, w2)
+    np.testing.assert_array_equal(a1, a2)

@@ -369,3 +369,58 @@ def test_inner_solvers_agree_on_fake_ops(name):
     np.testing.assert_allclose(np.asarray(mc["correlations"])[same], np.asarray(me["correlations"])[same], atol=1e-5)
     with pytest.raises(ValueError, match="Unknown inner_solver"):
         NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(X[:400], Y[:400], inner_solver="qr", **kw)
+
+
+def _structure_golden():
+    g = load_golden("structure.npz")
+    stories = [str(x) for x in g["stories"]]
+    feats = {s: g[f"feat__{s}"] for s in stories}
+    brain = {s: g[f"brain__{s}"] for s in stories}
+
+    def cfg(prefix):
+        out = {}
+        for k in g.files:
+            if k.startswith(prefix):
+                v = float(g[k])
+                out[k[len(prefix):]] = None if np.isnan(v) else int(v)
+        return out
+
+    return g, stories, feats, brain, [int(d) for d in g["delays"]], cfg("cfg_tt__"), cfg("cfg_cc__")
+
+
+def test_structure_train_test_split_matches_reference_trainer():
+    """create_train_test_split (FIR fused) on the NumPy stand-in against the unmodified trainer's outputs."""
+    from litcoder_core_b200.structure import create_train_test_split
+
+    g, stories, feats, brain, delays, cfg_tt, _ = _structure_golden()
+    out = create_train_test_split(feats, brain, cfg_tt, fir_delays=delays, ops=FakeOps())
+    for k in ("Rstim", "Rresp", "Pstim", "Presp"):
+        want = g[f"tt__{k}"]
+        assert out[k].dtype == np.float32 and out[k].shape == want.shape
+        np.testing.assert_allclose(out[k], want.astype(np.float32), rtol=2e-6, atol=2e-6)
+    # already-delayed input (fir_delays=None) gives the same matrices
+    delayed = {s: O.fir_make_delayed(feats[s], delays) for s in stories}
+    out2 = create_train_test_split(delayed, brain, cfg_tt, ops=FakeOps())
+    np.testing.assert_array_equal(out2["Rstim"], out["Rstim"])
+    np.testing.assert_array_equal(out2["Pstim"], out["Pstim"])
+    # the NaN feature of story s2 is scrubbed: its delayed columns are all zero in that story's rows
+    assert not np.isnan(out["Rstim"]).any()
+    with pytest.raises(ValueError, match="at least one training story"):
+        create_train_test_split({"a": feats["s0"]}, {"a": brain["s0"]}, cfg_tt, ops=FakeOps())
+
+
+def test_structure_concatenated_matches_reference_trainer():
+    from litcoder_core_b200.structure import create_concatenated_data
+
+    g, stories, feats, brain, delays, _, cfg_cc = _structure_golden()
+    brain_cc = {s: np.vstack([brain[s], brain[s][:15]]) for s in stories}
+    out = create_concatenated_data(feats, brain_cc, stories, cfg_cc, fir_delays=delays, ops=FakeOps())
+    with np.errstate(invalid="ignore"):
+        np.testing.assert_array_equal(out["X"], g["cc__X"].astype(np.float32))  # copies: exact (NaN kept)
+        np.testing.assert_array_equal(out["Y"], g["cc__Y"].astype(np.float32))
+    # a window that starts inside the second story and ends inside the third
+    cfg = {"features_start": 80, "features_end": 200, "targets_start": 80, "targets_end": 200}
+    out = create_concatenated_data(feats, brain_cc, stories, cfg, fir_delays=delays, ops=FakeOps())
+    want = np.concatenate([O.fir_make_delayed(feats[s], delays) for s in stories])[80:200]
+    np.testing.assert_array_equal(out["X"], want.astype(np.float32))
+    np.testing.assert_array_equal(out["Y"], np.concatenate([brain_cc[s] for s in stories])[80:200].astype(np.float32))

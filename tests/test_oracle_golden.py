@@ -251,3 +251,34 @@ def test_fit_predict_matches_reference(name):
     assert w.shape == wref.shape and w.dtype == wref.dtype
     err = np.abs(w[:, same] - wref[:, same]).max() / np.abs(wref).max()
     assert err < 1e-4, (name, err)
+
+
+def _structure_inputs():
+    g = load_golden("structure.npz")
+    stories = [str(x) for x in g["stories"]]
+    feats = {s: g[f"feat__{s}"] for s in stories}
+    brain = {s: g[f"brain__{s}"] for s in stories}
+
+    def cfg(prefix):
+        out = {}
+        for k in g.files:
+            if k.startswith(prefix):
+                v = float(g[k])
+                out[k[len(prefix):]] = None if np.isnan(v) else int(v)
+        return out
+
+    return g, stories, feats, brain, [int(d) for d in g["delays"]], cfg("cfg_tt__"), cfg("cfg_cc__")
+
+
+def test_structure_data_matches_reference():
+    """apply_fir_delays + _create_train_test_split / _create_concatenated_data of the unmodified trainer."""
+    g, stories, feats, brain, delays, cfg_tt, cfg_cc = _structure_inputs()
+    delayed = O.apply_fir_delays(feats, delays)
+    tt = O.create_train_test_split(delayed, brain, cfg_tt)
+    for k in ("Rstim", "Rresp", "Pstim", "Presp"):
+        assert tt[k].dtype == g[f"tt__{k}"].dtype and tt[k].shape == g[f"tt__{k}"].shape
+        np.testing.assert_array_equal(tt[k], g[f"tt__{k}"])
+    brain_cc = {s: np.vstack([brain[s], brain[s][:15]]) for s in stories}
+    cc = O.create_concatenated_data(delayed, brain_cc, stories, cfg_cc)
+    for k in ("X", "Y"):
+        np.testing.assert_array_equal(cc[k], g[f"cc__{k}"])
