@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LITRIDGE_ABI_VERSION 2
+#define LITRIDGE_ABI_VERSION 3
 
 const char* lit_last_error(void);
 int lit_abi_version(void);
@@ -82,9 +82,21 @@ int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, cons
 int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
                            int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy, float* dot_part,
                            float* ssq_part, long ld_part, int variant, void* stream);
+/* The fused GEMM over a stack whose last n_series_tiles tiles (256 rows each) are SERIES tiles written by
+ * lit_series_stack: 64 time points x the 4 terms Q_q of the Neumann series of (G + a^2 I)^-1.  For those tiles the
+ * epilogue emits, per part of 32 time points and voxel, 14 sums into series_part[part*14 + j][ld_part]:
+ * j = 0..3: sum_t T_q[t] Yz[t][v];  j = 4..13: sum_t T_q[t] T_q'[t] for (q,q') = 00 01 02 03 11 12 13 22 23 33,
+ * T_q = Q_q A[v]^T.  Every alpha of the series is then a 4-term combination (lit_corr_finalize_series) instead of
+ * its own block of stacked rows: 16 of the 20 BASELINE alphas cost 4 row blocks.  The first n_groups *
+ * rows_per_group rows are ordinary alpha groups (dot_part / ssq_part as in lit_gemm_tf32x3_nt_corr).
+ * precision: 0 = 3xTF32 split pairs (float planes), 1 = fp16 split pairs (lit_split_f16). */
+int lit_gemm_corr_series(int precision, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
+                         long ldb, int M, int n_groups, int rows_per_group, int n_series_tiles, int K, const float* Yz,
+                         long ldy, float* dot_part, float* ssq_part, float* series_part, long ld_part, int variant,
+                         void* stream);
 /* fp16 split pair of x = src_hi (+ src_lo when non-NULL):  out_hi = fp16(s x), out_lo = fp16(s x - out_hi) with one
- * power-of-two scale s per group of rows_per_group consecutive rows, chosen so that the group's largest magnitude
- * lands in [2^14, 2^15).  inv_scale[g] = 1/s.  scratch: 8 bytes per group.  ld_out in fp16 elements. */
+ * power-of-two scale s per group of rows_per_group consecutive rows (1 for the voxel rows of A, 256 = one N tile
+ * for the stacked design B), chosen so that the group's largest magnitude lands in [2^14, 2^15).  inv_scale[g] = 1/s.  scratch: 8 bytes per group.  ld_out in fp16 elements. */
 int lit_split_f16(const float* src_hi, const float* src_lo, long ld_src, long rows, long cols, long rows_per_group,
                   void* out_hi, void* out_lo, long ld_out, float* inv_scale, void* scratch, void* stream);
 
@@ -176,11 +188,21 @@ int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, long ld_z, lon
 int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group, int n_groups,
                       long n_vox, long n_rows, float eps, int accumulate, int metric, const float* resp_std,
                       float* corr, long ld_corr, void* stream);
-/* lit_corr_finalize on the partial sums of lit_gemm_f16x3_nt_corr: dot and ssq are first multiplied by
- * inv_row[v] * inv_group[g] and its square (either vector may be NULL = all ones). */
+/* lit_corr_finalize with the operand scales of lit_gemm_f16x3_nt_corr undone and an optional slot map: the partial
+ * sums of part P (128 stacked rows) are multiplied by inv_row[v] * inv_tile[P / 2] (and its square) before they are
+ * added (either vector may be NULL = ones; lit_split_f16 with rows_per_group = 256 writes inv_tile); group g is
+ * written to corr row slots[g] (NULL: row g). */
 int lit_corr_finalize_scaled(const float* dot_part, const float* ssq_part, long ld_part, int parts_per_group,
                              int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
-                             const float* resp_std, const float* inv_row, const float* inv_group, float* corr,
+                             const float* resp_std, const float* inv_row, const float* inv_tile, const int32_t* slots,
+                             float* corr, long ld_corr, void* stream);
+/* Scores of the alphas served by the truncated Neumann series from the 14 per-voxel sums of the series tiles of
+ * lit_gemm_corr_series: prediction_a[t] = sum_q coef[a*4+q] T_q[t], so dot_a = sum_q coef_q D_q and
+ * ssq_a = sum_{q,q'} coef_q coef_q' S_qq' (fp64), then the lit_corr_finalize formula; alpha a goes to corr row
+ * slots[a].  n_parts = 2 * n_series_tiles; inv_tile indexes the SERIES tiles (NULL = ones). */
+int lit_corr_finalize_series(const float* series_part, long ld_part, int n_parts, long n_vox, long n_rows, float eps,
+                             int accumulate, int metric, const float* resp_std, const float* inv_row,
+                             const float* inv_tile, const double* coef, const int32_t* slots, int n_alphas, float* corr,
                              long ld_corr, void* stream);
 /* best[v] = first argmax_a mean[a][v], mean = corr_sum / n_folds (nested_cv.py:391-393,408-411);
  * alpha_out[v] = (float)alphas[best[v]].  col_sums (n_alphas doubles, may be NULL) receives
@@ -209,6 +231,11 @@ int lit_cheb_update(float* d, const float* r, float* x, float* t, float* d_hi, f
 int lit_poly_combine(const float* const* src_hi, const float* const* src_lo, int n_src, long ld_src, long rows,
                      long rows_pad, long cols, const double* coef, const int32_t* slots, int n_groups, float* out_hi,
                      float* out_lo, long ld_out, void* stream);
+/* Series tiles of the alpha stack: out row tile*256 + half*128 + q*32 + i = scale[q] * (src_hi[q] + src_lo[q])[t],
+ * t = tile*64 + half*32 + i (zero for t >= rows), as a split pair; q = 0..3.  src_hi / src_lo: HOST arrays of 4
+ * device pointers (src_lo may be NULL or hold NULLs); scale: 4 HOST doubles (lambda_max^-q). */
+int lit_series_stack(const float* const* src_hi, const float* const* src_lo, long ld_src, long rows, long cols,
+                     const double* scale, long n_tiles, float* out_hi, float* out_lo, long ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test statistics (nested_cv.py:418-477, statsmodels fdrcorrection)

@@ -68,6 +68,11 @@ struct GemmParams {
   float* dot_part;      // [2*num_n_tiles][ld_part]
   float* ssq_part;
   long ld_part;
+  // EPI_CORR, series tiles (N tiles >= series_tile0): the 256 columns of a tile are 64 time points x 4 series
+  // terms, laid out [half][q][32 time points]; every epilogue thread then holds T_q[t] for q = 0..3 and 32 time
+  // points and emits the 4 sums T_q y and the 10 sums T_q T_q' (q <= q') into series_part[part*14 + j][ld_part].
+  int series_tile0;
+  float* series_part;
 };
 
 // F16_ = 0: operands are fp32 planes holding TF32 values (kind::tf32, 8 values of K per MMA);
@@ -340,7 +345,40 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         }
       } else {
         // Fused per-voxel reduction: rows = voxels, columns = time points of one alpha group.
-        if (row_ok) {
+        if (row_ok && nt >= p.series_tile0) {
+          if constexpr (COLS == 128) {
+            const long part = (long)(nt - p.series_tile0) * 2 + half;
+            const float* ycol = p.Yz + row + part * 32 * p.ldy;  // time points part*32 .. part*32 + 31
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = __ldg(ycol + (long)i * p.ldy);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            float s00 = 0.f, s01 = 0.f, s02 = 0.f, s03 = 0.f, s11 = 0.f, s12 = 0.f, s13 = 0.f, s22 = 0.f, s23 = 0.f,
+                  s33 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float a0 = acc[i], a1 = acc[32 + i], a2 = acc[64 + i], a3 = acc[96 + i];
+              d0 = fmaf(a0, y[i], d0);
+              d1 = fmaf(a1, y[i], d1);
+              d2 = fmaf(a2, y[i], d2);
+              d3 = fmaf(a3, y[i], d3);
+              s00 = fmaf(a0, a0, s00);
+              s01 = fmaf(a0, a1, s01);
+              s02 = fmaf(a0, a2, s02);
+              s03 = fmaf(a0, a3, s03);
+              s11 = fmaf(a1, a1, s11);
+              s12 = fmaf(a1, a2, s12);
+              s13 = fmaf(a1, a3, s13);
+              s22 = fmaf(a2, a2, s22);
+              s23 = fmaf(a2, a3, s23);
+              s33 = fmaf(a3, a3, s33);
+            }
+            float* o = p.series_part + part * 14 * p.ld_part + row;
+            const float vals[14] = {d0, d1, d2, d3, s00, s01, s02, s03, s11, s12, s13, s22, s23, s33};
+#pragma unroll
+            for (int j = 0; j < 14; ++j) o[(long)j * p.ld_part] = vals[j];
+          }
+        } else if (row_ok) {
           float dot = 0.f, ssq = 0.f;
           const long t_base = (long)(nt % p.tiles_per_group) * BN + half * COLS;
           const float* ycol = p.Yz + row + t_base * p.ldy;
@@ -538,70 +576,71 @@ extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda
   }
 }
 
-extern "C" int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
-                                       const float* B_lo, long ldb, int M, int n_groups, int rows_per_group, int K,
-                                       const float* Yz, long ldy, float* dot_part, float* ssq_part, long ld_part,
-                                       int variant, void* stream) {
-  LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0, "negative extent");
+// Shared body of the fused prediction + correlation entry points.  f16 = 0: 3xTF32 split pairs; 1: fp16 split pairs.
+static int corr_gemm(int f16, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+                     int M, int n_groups, int rows_per_group, int n_series_tiles, int K, const float* Yz, long ldy,
+                     float* dot_part, float* ssq_part, float* series_part, long ld_part, int variant, void* stream) {
+  LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0 && n_series_tiles >= 0, "negative extent");
   LIT_REQUIRE(rows_per_group % 256 == 0, "rows_per_group must be padded to a multiple of 256 (got %d)",
               rows_per_group);
   LIT_REQUIRE(ld_part >= M && ldy >= M, "partial / response pitch smaller than M");
-  if (M == 0 || n_groups == 0 || rows_per_group == 0) return LIT_OK;
+  LIT_REQUIRE(n_series_tiles == 0 || series_part, "series tiles need the series_part output");
+  const long n_plain = (long)n_groups * rows_per_group;
+  if (M == 0 || n_plain + n_series_tiles == 0) return LIT_OK;
   GemmParams p = {};
   p.M = M;
-  p.N = n_groups * rows_per_group;
+  p.N = (int)(n_plain + 256L * n_series_tiles);
   p.K = K;
   p.Yz = Yz;
   p.ldy = ldy;
-  p.tiles_per_group = rows_per_group / 256;
+  p.tiles_per_group = rows_per_group >= 256 ? rows_per_group / 256 : 1;
   p.dot_part = dot_part;
   p.ssq_part = ssq_part;
   p.ld_part = ld_part;
+  p.series_tile0 = (int)(n_plain / 256);
+  p.series_part = series_part;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
   switch (variant) {
     case LIT_GEMM_1CTA_N256:
-      return launch_gemm<256, 1, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+      return f16 ? launch_gemm<256, 1, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s)
+                 : launch_gemm<256, 1, EPI_CORR, 0>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     case LIT_GEMM_2CTA_N256:
-      return launch_gemm<256, 2, EPI_CORR>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+      return f16 ? launch_gemm<256, 2, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s)
+                 : launch_gemm<256, 2, EPI_CORR, 0>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     default:
       set_error("unknown corr-GEMM variant %d", variant);
       return LIT_ERR_INVALID;
   }
 }
 
+extern "C" int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
+                                       const float* B_lo, long ldb, int M, int n_groups, int rows_per_group, int K,
+                                       const float* Yz, long ldy, float* dot_part, float* ssq_part, long ld_part,
+                                       int variant, void* stream) {
+  return corr_gemm(0, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, n_groups, rows_per_group, 0, K, Yz, ldy, dot_part, ssq_part,
+                   nullptr, ld_part, variant, stream);
+}
+
 // Same fused prediction + correlation GEMM with fp16 split pairs (see lit_split_f16): hi = fp16(s x),
-// lo = fp16(s x - hi) with a power-of-two scale s per row (A) / per alpha group (B), three kind::f16 MMAs per
+// lo = fp16(s x - hi) with a power-of-two scale s per row (A) / per 256-row tile (B), three kind::f16 MMAs per
 // k-step.  The 11-bit significands make the products as exact as 3xTF32, at twice the tensor-core rate and half
-// the operand bytes.  The partial sums are those of the SCALED predictions; lit_corr_finalize /
-// lit_pearson_finalize take the scale vectors to undo it.
+// the operand bytes.  The partial sums are those of the SCALED predictions; lit_corr_finalize_scaled /
+// lit_corr_finalize_series take the scale vectors to undo it.
 extern "C" int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
                                       long ldb, int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy,
                                       float* dot_part, float* ssq_part, long ld_part, int variant, void* stream) {
-  LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0, "negative extent");
-  LIT_REQUIRE(rows_per_group % 256 == 0, "rows_per_group must be padded to a multiple of 256 (got %d)",
-              rows_per_group);
-  LIT_REQUIRE(ld_part >= M && ldy >= M, "partial / response pitch smaller than M");
-  if (M == 0 || n_groups == 0 || rows_per_group == 0) return LIT_OK;
-  GemmParams p = {};
-  p.M = M;
-  p.N = n_groups * rows_per_group;
-  p.K = K;
-  p.Yz = Yz;
-  p.ldy = ldy;
-  p.tiles_per_group = rows_per_group / 256;
-  p.dot_part = dot_part;
-  p.ssq_part = ssq_part;
-  p.ld_part = ld_part;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
-  switch (variant) {
-    case LIT_GEMM_1CTA_N256:
-      return launch_gemm<256, 1, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
-    case LIT_GEMM_2CTA_N256:
-      return launch_gemm<256, 2, EPI_CORR, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
-    default:
-      set_error("unknown corr-GEMM variant %d", variant);
-      return LIT_ERR_INVALID;
-  }
+  return corr_gemm(1, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, n_groups, rows_per_group, 0, K, Yz, ldy, dot_part, ssq_part,
+                   nullptr, ld_part, variant, stream);
+}
+
+// The fused GEMM over a stack whose last n_series_tiles tiles carry the four terms of the Neumann series
+// (see GemmParams::series_tile0 and lit_series_stack): precision 0 = 3xTF32 pairs, 1 = fp16 pairs.
+extern "C" int lit_gemm_corr_series(int precision, const void* A_hi, const void* A_lo, long lda, const void* B_hi,
+                                    const void* B_lo, long ldb, int M, int n_groups, int rows_per_group,
+                                    int n_series_tiles, int K, const float* Yz, long ldy, float* dot_part,
+                                    float* ssq_part, float* series_part, long ld_part, int variant, void* stream) {
+  LIT_REQUIRE(precision == 0 || precision == 1, "corr_series: precision must be 0 (tf32x3) or 1 (f16x3)");
+  return corr_gemm(precision, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, n_groups, rows_per_group, n_series_tiles, K, Yz, ldy,
+                   dot_part, ssq_part, series_part, ld_part, variant, stream);
 }

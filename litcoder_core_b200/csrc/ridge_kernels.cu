@@ -305,11 +305,28 @@ __device__ __forceinline__ float nan_to_num(float x) {
 // metric 0: correlation (Yz z-scored).  metric 1: signed sqrt of R^2 (Yz centred only, resp_std = unbiased
 // std of the validation responses): Rsq = 1 - var(Q - pred)/var(Q) with
 // sum (q_c - p_c)^2 = (n-1) var(Q) - 2 dot + ssq   (ridge_regression.py:126-130).
+__device__ __forceinline__ float inner_score(float d, float q, int metric, bool raw, float qvar, float inv_n,
+                                             float inv_nm1, float nm1, float eps) {
+  float c;
+  if (metric == 0) {
+    const float sd = sqrtf(q * inv_nm1);
+    c = (d * inv_n) / (sd + eps);
+  } else {
+    const float resvar = (qvar * nm1 - 2.f * d + q) * inv_nm1;
+    const float rsq = 1.f - resvar / qvar;
+    c = sqrtf(fabsf(rsq)) * (rsq > 0.f ? 1.f : (rsq < 0.f ? -1.f : 0.f));
+    if (isnan(rsq)) c = rsq;
+  }
+  return raw ? c : nan_to_num(c);
+}
+
+// inv_row[v] / inv_tile[N tile]: power-of-two operand scales of the fp16-split GEMM to undo (NULL = ones); a tile
+// is 256 stacked rows = 2 parts.
 __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const float* __restrict__ ssq_part,
                                      long ld_part, int tiles_per_group, int n_groups, long n_vox, long n_rows, float eps,
                                      int accumulate, int metric, const float* __restrict__ resp_std,
-                                     const float* __restrict__ inv_row, const float* __restrict__ inv_group,
-                                     float* __restrict__ corr, long ld_corr) {
+                                     const float* __restrict__ inv_row, const float* __restrict__ inv_tile,
+                                     const int32_t* __restrict__ slots, float* __restrict__ corr, long ld_corr) {
   const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_vox) return;
   const float inv_n = 1.f / (float)n_rows;
@@ -325,27 +342,64 @@ __global__ void corr_finalize_kernel(const float* __restrict__ dot_part, const f
   for (int g = 0; g < n_groups; ++g) {
     float d = 0.f, q = 0.f;
     for (int t = 0; t < tiles_per_group; ++t) {
-      const long o = (long)(g * tiles_per_group + t) * ld_part + v;
-      d += dot_part[o];
-      q += ssq_part[o];
+      const long part = (long)g * tiles_per_group + t;
+      const long o = part * ld_part + v;
+      if (inv_row || inv_tile) {  // fp16 split pairs: undo the power-of-two operand scales (exact)
+        const float is = ir * (inv_tile ? inv_tile[part >> 1] : 1.f);
+        d += dot_part[o] * is;
+        q += ssq_part[o] * is * is;
+      } else {
+        d += dot_part[o];
+        q += ssq_part[o];
+      }
     }
-    if (inv_row || inv_group) {  // fp16 split pairs: undo the power-of-two operand scales (exact)
-      const float is = ir * (inv_group ? inv_group[g] : 1.f);
-      d *= is;
-      q = q * is * is;
-    }
-    float c;
-    if (metric == 0) {
-      const float sd = sqrtf(q * inv_nm1);
-      c = (d * inv_n) / (sd + eps);
-    } else {
-      const float resvar = (qvar * (float)(n_rows - 1) - 2.f * d + q) * inv_nm1;
-      const float rsq = 1.f - resvar / qvar;
-      c = sqrtf(fabsf(rsq)) * (rsq > 0.f ? 1.f : (rsq < 0.f ? -1.f : 0.f));
-      if (isnan(rsq)) c = rsq;
-    }
-    if (!raw) c = nan_to_num(c);
-    float* dst = corr + (long)g * ld_corr + v;
+    const float c = inner_score(d, q, metric, raw, qvar, inv_n, inv_nm1, (float)(n_rows - 1), eps);
+    float* dst = corr + (long)(slots ? slots[g] : g) * ld_corr + v;
+    *dst = accumulate ? *dst + c : c;
+  }
+}
+
+// Scores of the alphas served by the Neumann series, from the 14 per-voxel sums of the series tiles
+// (lit_gemm_corr_series): with T_q[t] = Q_q[t] . c_v the prediction for alpha a is  sum_q coef[a][q] T_q[t], so
+//   dot_a = sum_q coef_q D_q,   ssq_a = sum_{q,q'} coef_q coef_q' S_qq'
+// (D_q = sum_t T_q y, S_qq' = sum_t T_q T_q'), combined in fp64 and scored like every other alpha.
+// series_part[part*14 + j]: j = 0..3 -> D_q; 4..13 -> S_00 S_01 S_02 S_03 S_11 S_12 S_13 S_22 S_23 S_33.
+__global__ void corr_finalize_series_kernel(const float* __restrict__ series_part, long ld_part, int n_parts,
+                                            long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                            const float* __restrict__ resp_std, const float* __restrict__ inv_row,
+                                            const float* __restrict__ inv_tile /* of the series tiles */,
+                                            const double* __restrict__ coef /* [n_alphas][4] */,
+                                            const int32_t* __restrict__ slots, int n_alphas,
+                                            float* __restrict__ corr, long ld_corr) {
+  const long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_vox) return;
+  const float inv_n = 1.f / (float)n_rows;
+  const float inv_nm1 = 1.f / (float)(n_rows - 1);
+  const bool raw = (metric & 2) != 0;
+  metric &= 1;
+  float qvar = 0.f;
+  if (metric == 1) {
+    const float sd = resp_std[v];
+    qvar = sd * sd;
+  }
+  const double ir = inv_row ? (double)inv_row[v] : 1.0;
+  double sum[14];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) sum[j] = 0.0;
+  for (int part = 0; part < n_parts; ++part) {
+    const double is = ir * (inv_tile ? (double)inv_tile[part >> 1] : 1.0);
+    const float* src = series_part + (long)part * 14 * ld_part + v;
+#pragma unroll
+    for (int j = 0; j < 14; ++j) sum[j] += (double)src[(long)j * ld_part] * (j < 4 ? is : is * is);
+  }
+  for (int a = 0; a < n_alphas; ++a) {
+    const double c0 = coef[a * 4], c1 = coef[a * 4 + 1], c2 = coef[a * 4 + 2], c3 = coef[a * 4 + 3];
+    const double d = c0 * sum[0] + c1 * sum[1] + c2 * sum[2] + c3 * sum[3];
+    const double q = c0 * c0 * sum[4] + c1 * c1 * sum[8] + c2 * c2 * sum[11] + c3 * c3 * sum[13] +
+                     2.0 * (c0 * c1 * sum[5] + c0 * c2 * sum[6] + c0 * c3 * sum[7] + c1 * c2 * sum[9] +
+                            c1 * c3 * sum[10] + c2 * c3 * sum[12]);
+    const float c = inner_score((float)d, (float)q, metric, raw, qvar, inv_n, inv_nm1, (float)(n_rows - 1), eps);
+    float* dst = corr + (long)slots[a] * ld_corr + v;
     *dst = accumulate ? *dst + c : c;
   }
 }
@@ -504,31 +558,48 @@ extern "C" int lit_scale_rows_by_alpha(const float* Z_hi, const float* Z_lo, lon
   return LIT_OK;
 }
 
-extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
-                                 int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
-                                 const float* resp_std, float* corr, long ld_corr, void* stream) {
-  LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
-  LIT_REQUIRE(metric >= 0 && metric <= 3, "corr_finalize: metric must be 0..3");
-  LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize: the R^2 metric needs the response std");
-  if (n_vox == 0 || n_groups == 0) return LIT_OK;
-  corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
-      dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, nullptr,
-      nullptr, corr, ld_corr);
-  LIT_LAUNCH_CHECK();
-  return LIT_OK;
-}
-
-extern "C" int lit_corr_finalize_scaled(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
-                                        int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
-                                        const float* resp_std, const float* inv_row, const float* inv_group,
-                                        float* corr, long ld_corr, void* stream) {
+static int corr_finalize_common(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
+                                int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                const float* resp_std, const float* inv_row, const float* inv_tile, const int32_t* slots,
+                                float* corr, long ld_corr, void* stream) {
   LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize: pitch smaller than n_vox");
   LIT_REQUIRE(metric >= 0 && metric <= 3, "corr_finalize: metric must be 0..3");
   LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize: the R^2 metric needs the response std");
   if (n_vox == 0 || n_groups == 0) return LIT_OK;
   corr_finalize_kernel<<<blocks_for(n_vox, 256), 256, 0, (cudaStream_t)stream>>>(
       dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate, metric, resp_std, inv_row,
-      inv_group, corr, ld_corr);
+      inv_tile, slots, corr, ld_corr);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_corr_finalize(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
+                                 int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                 const float* resp_std, float* corr, long ld_corr, void* stream) {
+  return corr_finalize_common(dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate,
+                              metric, resp_std, nullptr, nullptr, nullptr, corr, ld_corr, stream);
+}
+
+extern "C" int lit_corr_finalize_scaled(const float* dot_part, const float* ssq_part, long ld_part, int tiles_per_group,
+                                        int n_groups, long n_vox, long n_rows, float eps, int accumulate, int metric,
+                                        const float* resp_std, const float* inv_row, const float* inv_tile,
+                                        const int32_t* slots, float* corr, long ld_corr, void* stream) {
+  return corr_finalize_common(dot_part, ssq_part, ld_part, tiles_per_group, n_groups, n_vox, n_rows, eps, accumulate,
+                              metric, resp_std, inv_row, inv_tile, slots, corr, ld_corr, stream);
+}
+
+extern "C" int lit_corr_finalize_series(const float* series_part, long ld_part, int n_parts, long n_vox, long n_rows,
+                                        float eps, int accumulate, int metric, const float* resp_std,
+                                        const float* inv_row, const float* inv_tile, const double* coef,
+                                        const int32_t* slots, int n_alphas, float* corr, long ld_corr, void* stream) {
+  LIT_REQUIRE(ld_part >= n_vox && ld_corr >= n_vox, "corr_finalize_series: pitch smaller than n_vox");
+  LIT_REQUIRE(metric >= 0 && metric <= 3, "corr_finalize_series: metric must be 0..3");
+  LIT_REQUIRE((metric & 1) == 0 || resp_std, "corr_finalize_series: the R^2 metric needs the response std");
+  LIT_REQUIRE(n_alphas == 0 || (coef && slots), "corr_finalize_series: coefficients / slots missing");
+  if (n_vox == 0 || n_alphas == 0) return LIT_OK;
+  corr_finalize_series_kernel<<<blocks_for(n_vox, 128), 128, 0, (cudaStream_t)stream>>>(
+      series_part, ld_part, n_parts, n_vox, n_rows, eps, accumulate, metric, resp_std, inv_row, inv_tile, coef, slots,
+      n_alphas, corr, ld_corr);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

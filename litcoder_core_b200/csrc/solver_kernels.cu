@@ -263,6 +263,41 @@ __global__ void poly_combine_kernel(PolySources src, int n_src, long ld_src, lon
   }
 }
 
+// Series tiles of the alpha stack (lit_gemm_corr_series): the four terms Q_q = scale[q] * (src_hi[q] + src_lo[q])
+// (Q_0 = P_c, Q_q = P_c G^q / lambda_max^q) of the Neumann series, interleaved so that one 256-row tile holds
+// 64 time points x 4 terms:  out row = tile*256 + half*128 + q*32 + i  <->  time point t = tile*64 + half*32 + i.
+// Rows with t >= rows are zero.  Written as a 3xTF32 split pair.
+__global__ void series_stack_kernel(PolySources src, long ld_src, long rows, long cols, double s0, double s1, double s2,
+                                    double s3, long n_tiles, float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                    long ld_out) {
+  const long c = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const double sc[4] = {s0, s1, s2, s3};
+  for (long orow = blockIdx.y; orow < n_tiles * 256; orow += gridDim.y) {
+    const long tile = orow >> 8;
+    const int r = (int)(orow & 255);
+    const int q = (r & 127) >> 5;
+    const long t = tile * 64 + (r >> 7) * 32 + (r & 31);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < rows) {
+      v = *reinterpret_cast<const float4*>(src.hi[q] + t * ld_src + c);
+      if (src.lo[q]) {
+        const float4 w = *reinterpret_cast<const float4*>(src.lo[q] + t * ld_src + c);
+        v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+      }
+      const double f = sc[q];
+      v.x = (float)(f * (double)v.x), v.y = (float)(f * (double)v.y);
+      v.z = (float)(f * (double)v.z), v.w = (float)(f * (double)v.w);
+    }
+    float4 h, l;
+    h.x = ptx::to_tf32(v.x), h.y = ptx::to_tf32(v.y), h.z = ptx::to_tf32(v.z), h.w = ptx::to_tf32(v.w);
+    l.x = ptx::to_tf32(v.x - h.x), l.y = ptx::to_tf32(v.y - h.y);
+    l.z = ptx::to_tf32(v.z - h.z), l.w = ptx::to_tf32(v.w - h.w);
+    *reinterpret_cast<float4*>(out_hi + orow * ld_out + c) = h;
+    *reinterpret_cast<float4*>(out_lo + orow * ld_out + c) = l;
+  }
+}
+
 }  // namespace lit
 
 using namespace lit;
@@ -346,6 +381,34 @@ extern "C" int lit_poly_combine(const float* const* src_hi, const float* const* 
   poly_combine_kernel<<<dim3(gx, (unsigned)gy), block, 0, (cudaStream_t)stream>>>(ps, n_src, ld_src, rows, rows_pad, cols,
                                                                                    coef, slots, n_groups, out_hi, out_lo,
                                                                                    ld_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_series_stack(const float* const* src_hi, const float* const* src_lo, long ld_src, long rows, long cols,
+                                const double* scale /* 4 host doubles */, long n_tiles, float* out_hi, float* out_lo,
+                                long ld_out, void* stream) {
+  cols = (cols + 3) / 4 * 4;
+  LIT_REQUIRE(rows >= 0 && n_tiles >= 0 && rows <= n_tiles * 64, "series_stack: %ld rows do not fit %ld tiles", rows,
+              n_tiles);
+  LIT_REQUIRE(ld_src % 4 == 0 && ld_out % 4 == 0 && cols <= ld_src && cols <= ld_out,
+              "series_stack: pitches must be multiples of 4 floats and cover the width rounded up to 4");
+  if (n_tiles == 0 || cols == 0) return LIT_OK;
+  PolySources ps;
+  for (int i = 0; i < 4; ++i) {
+    ps.hi[i] = src_hi[i];
+    ps.lo[i] = src_lo ? src_lo[i] : nullptr;
+    LIT_REQUIRE(ps.hi[i] && aligned16(ps.hi[i]) && (!ps.lo[i] || aligned16(ps.lo[i])), "series_stack: source alignment");
+  }
+  LIT_REQUIRE(aligned16(out_hi) && aligned16(out_lo), "series_stack: output alignment");
+  const int block = 128;
+  const int gx = (int)((cols / 4 + block - 1) / block);
+  long gy = n_tiles * 256;
+  const long want = ((long)sm_count() * 16 + gx - 1) / gx;
+  if (gy > want) gy = want;
+  if (gy > 65535) gy = 65535;
+  series_stack_kernel<<<dim3(gx, (unsigned)gy), block, 0, (cudaStream_t)stream>>>(
+      ps, ld_src, rows, cols, scale[0], scale[1], scale[2], scale[3], n_tiles, out_hi, out_lo, ld_out);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

@@ -62,15 +62,28 @@ class MatF16:
         self.rows_per_group, self.inv_scale = rows_per_group, inv_scale
 
 
+class SeriesStack:
+    """Alpha stack of a GEMM-only fold in its compact form: `n_cheb` ordinary groups of `rows_pad` rows (the
+    Chebyshev solutions, group i -> alpha slot_cheb[i]) followed by `n_tiles` series tiles (lit_series_stack) that
+    serve the alphas slot_series with the 4-term combinations `coef` (n_series x 4, float64)."""
+
+    __slots__ = ("mat", "n_cheb", "rows_pad", "n_tiles", "slot_cheb", "slot_series", "coef")
+
+    def __init__(self, mat, n_cheb, rows_pad, n_tiles, slot_cheb, slot_series, coef):
+        self.mat, self.n_cheb, self.rows_pad, self.n_tiles = mat, n_cheb, rows_pad, n_tiles
+        self.slot_cheb, self.slot_series, self.coef = slot_cheb, slot_series, coef
+
+
 class Partials:
-    """Per-tile partial sums written by the fused correlation epilogue.  inv_row / inv_group: the operand
-    scales to undo when the GEMM ran on fp16 split pairs (None for the 3xTF32 form)."""
+    """Per-tile partial sums written by the fused correlation epilogue.  inv_row / inv_tile: the operand
+    scales to undo when the GEMM ran on fp16 split pairs (None for the 3xTF32 form).  series / stack: the
+    14-sum partials of the series tiles and the SeriesStack they belong to (compact stacks only)."""
 
-    __slots__ = ("dot", "ssq", "n_tiles", "ld", "inv_row", "inv_group")
+    __slots__ = ("dot", "ssq", "n_tiles", "ld", "inv_row", "inv_tile", "series", "stack")
 
-    def __init__(self, dot, ssq, n_tiles: int, ld: int, inv_row=None, inv_group=None):
+    def __init__(self, dot, ssq, n_tiles: int, ld: int, inv_row=None, inv_tile=None, series=None, stack=None):
         self.dot, self.ssq, self.n_tiles, self.ld = dot, ssq, n_tiles, ld
-        self.inv_row, self.inv_group = inv_row, inv_group
+        self.inv_row, self.inv_tile, self.series, self.stack = inv_row, inv_tile, series, stack
 
 
 class _EigTicket:
@@ -481,44 +494,55 @@ class DeviceOps:
         self.launches += 3
         return MatF16(hi, lo, rows, cols, ld, rows_per_group, inv)
 
-    def gemm_corr(self, A: Mat, B: Mat, n_groups: int, rows_per_group: int, Yz: Mat,
+    def gemm_corr(self, A: Mat, B, n_groups: int, rows_per_group: int, Yz: Mat,
                   precision: str = "tf32x3") -> Partials:
-        """Fused prediction + per-voxel reduction (see lit_gemm_tf32x3_nt_corr / lit_gemm_f16x3_nt_corr).
+        """Fused prediction + per-voxel reduction (lit_gemm_tf32x3_nt_corr / lit_gemm_f16x3_nt_corr /
+        lit_gemm_corr_series).  B is the alpha stack: a split Mat of n_groups * rows_per_group rows, or a
+        SeriesStack (compact form; n_groups is then the number of alphas it serves).
         precision "f16x3": the operands are first re-split into scaled fp16 pairs (one scale per voxel row of A,
-        one per alpha group of B); corr_finalize undoes the scales."""
+        one per 256-row tile of B); corr_finalize undoes the scales."""
         if precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"gemm_corr: unknown precision {precision!r}")
-        if rows_per_group % self.TILE_N or B.rows != n_groups * rows_per_group or Yz.rows != rows_per_group:
+        stack = B if isinstance(B, SeriesStack) else None
+        if stack is not None:
+            if stack.rows_pad != rows_per_group or stack.n_cheb + len(stack.slot_series) != n_groups:
+                raise ValueError("gemm_corr: SeriesStack does not match the alpha count / row padding")
+            B, n_plain, n_st = stack.mat, stack.n_cheb, stack.n_tiles
+        else:
+            n_plain, n_st = n_groups, 0
+        if rows_per_group % self.TILE_N or B.rows != n_plain * rows_per_group + n_st * self.TILE_N \
+                or Yz.rows != rows_per_group:
             raise ValueError("gemm_corr: stacked design / response rows must be padded to the tile size")
         if Yz.cols != A.rows or A.cols != B.cols:
             raise ValueError("gemm_corr: shape mismatch")
         M, K = A.rows, A.cols
-        n_tiles = n_groups * rows_per_group // self.PART_N
+        n_tiles = n_plain * rows_per_group // self.PART_N
         ld = round_up(M, 32)
         t = self.torch
-        dot = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
-        ssq = t.empty((n_tiles, ld), dtype=t.float32, device=self.device)
+        dot = t.empty((max(n_tiles, 1), ld), dtype=t.float32, device=self.device)
+        ssq = t.empty((max(n_tiles, 1), ld), dtype=t.float32, device=self.device)
+        series = t.empty((2 * n_st * 14, ld), dtype=t.float32, device=self.device) if n_st else None
         variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256, _lib.GEMM_2CTA_N256) \
             else _lib.GEMM_AUTO
-        flops = 2.0 * M * (n_groups * rows_per_group) * K
-        inv_row = inv_group = None
-        fn, what = self.lib.lit_gemm_tf32x3_nt_corr, "gemm_tf32x3_nt_corr"
+        flops = 2.0 * M * B.rows * K
+        inv_row = inv_tile = None
         if precision == "f16x3":
-            A, B = self.split_f16(A, 1), self.split_f16(B, rows_per_group)
-            inv_row, inv_group = A.inv_scale, B.inv_scale
-            fn, what = self.lib.lit_gemm_f16x3_nt_corr, "gemm_f16x3_nt_corr"
+            A, B = self.split_f16(A, 1), self.split_f16(B, self.TILE_N)
+            inv_row, inv_tile = A.inv_scale, B.inv_scale
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         self._timed.setdefault("gemm_corr", []).append((e0, e1))
         self._corr_log.append((e0, e1, flops))
         self._apply_sm_limit()
         e0.record()
-        check(fn(_vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld, M,
-                 n_groups, rows_per_group, K, _vp(Yz.hi.data_ptr()), Yz.ld, _vp(dot.data_ptr()), _vp(ssq.data_ptr()), ld,
-                 variant, _vp(self.stream)), what)
+        check(self.lib.lit_gemm_corr_series(
+            int(precision == "f16x3"), _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()),
+            _vp(B.lo.data_ptr()), B.ld, M, n_plain, rows_per_group, n_st, K, _vp(Yz.hi.data_ptr()), Yz.ld,
+            _vp(dot.data_ptr()), _vp(ssq.data_ptr()), _vp(series.data_ptr() if n_st else 0), ld, variant,
+            _vp(self.stream)), "gemm_corr_series")
         e1.record()
         self.launches += 1
         self.gemm_flops += flops
-        return Partials(dot, ssq, n_tiles, ld, inv_row, inv_group)
+        return Partials(dot, ssq, n_tiles, ld, inv_row, inv_tile, series, stack)
 
     # ------------------------------------------------------------------ eigendecomposition
     def syevd(self, G: Mat, lam=None):
@@ -685,8 +709,47 @@ class DeviceOps:
                 self.axpy(1.0, Q, self._view_rows(block, (len(cheb) + q) * n_rows, n_rows))
         return block
 
+    SERIES_MIN_ALPHAS = 5  # the compact stack pays once more alphas ride the series than it has terms (4)
+
+    def assemble_series_stack(self, block: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
+                              series_ratio: float = 60.0) -> SeriesStack:
+        """Compact alpha stack from the block of solve_blocks: the Chebyshev solutions as ordinary groups, then the
+        series tiles holding Q_q = P_c G^q / lam_max^q (q = 0..3) interleaved per 64 time points; the alphas of the
+        series become 4-term combinations with coef[a][q] = (-1)^q lam_max^q / a2^(q+1)."""
+        p = block.cols
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        n_tiles = -(-n_rows // 64)
+        out = self.empty(len(cheb) * rows_pad + n_tiles * self.TILE_N, p, split=True)
+        s = _vp(self.stream)
+        for i in range(len(cheb)):
+            off = i * rows_pad * out.ld * 4
+            check(self.lib.lit_gather_rows_f32(_vp(block.hi.data_ptr() + i * n_rows * block.ld * 4), block.ld, _vp(0),
+                                               n_rows, p, _vp(out.hi.data_ptr() + off), _vp(out.lo.data_ptr() + off),
+                                               out.ld, rows_pad, s), "gather_rows")
+            self.launches += 1
+        if Pc.ld != block.ld:
+            raise ValueError("assemble_series_stack: Pc must share the block's pitch")
+        base = block.hi.data_ptr() + len(cheb) * n_rows * block.ld * 4
+        hi = (C.c_void_p * 4)(Pc.hi.data_ptr(), *[base + q * n_rows * block.ld * 4 for q in range(3)])
+        scale = (C.c_double * 4)(*[float(lam_max) ** -q for q in range(4)])
+        off = len(cheb) * rows_pad * out.ld * 4
+        check(self.lib.lit_series_stack(C.cast(hi, _vp), _vp(0), block.ld, n_rows, p, C.cast(scale, _vp), n_tiles,
+                                        _vp(out.hi.data_ptr() + off), _vp(out.lo.data_ptr() + off), out.ld, s),
+              "series_stack")
+        self.launches += 1
+        coef = np.array([[(-1.0) ** q * float(lam_max) ** q / float(a2_list[j]) ** (q + 1) for q in range(4)]
+                         for j in series], dtype=np.float64)
+        return SeriesStack(out, len(cheb), rows_pad, n_tiles, np.asarray(cheb, dtype=np.int32),
+                           np.asarray(series, dtype=np.int32), coef)
+
     def assemble_stack(self, block: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
-                       series_ratio: float = 60.0) -> Mat:
+                       series_ratio: float = 60.0, series_moments: bool = False):
+        if series_moments and len(self.solver_partition(lam_max, a2_list, series_ratio)[1]) >= self.SERIES_MIN_ALPHAS:
+            return self.assemble_series_stack(block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio)
+        return self._assemble_full_stack(block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio)
+
+    def _assemble_full_stack(self, block: Mat, Pc: Mat, n_rows: int, rows_pad: int, lam_max: float, a2_list,
+                             series_ratio: float = 60.0) -> Mat:
         """Alpha-stacked M_a = P_c (G + a^2 I)^-1 as a split pair [len(a2_list) * rows_pad][p] (pad rows zero) from
         the compact block of solve_blocks: copies of the Chebyshev solutions, Neumann-series combinations
         sum_q (-1)^q a^-2(q+1) P_c G^q for the large alphas."""
@@ -748,13 +811,32 @@ class DeviceOps:
 
     def corr_finalize(self, parts: Partials, tiles_per_group: int, n_groups: int, n_vox: int, n_rows: int, eps: float,
                       corr: Mat, accumulate: bool, metric: int = 0, resp_std=None) -> None:
-        ir, ig = getattr(parts, "inv_row", None), getattr(parts, "inv_group", None)
-        check(self.lib.lit_corr_finalize_scaled(
-            _vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld, tiles_per_group, n_groups, n_vox, n_rows,
-            eps, int(accumulate), metric, _vp(resp_std.data_ptr() if resp_std is not None else 0),
-            _vp(ir.data_ptr() if ir is not None else 0), _vp(ig.data_ptr() if ig is not None else 0),
-            _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize")
-        self.launches += 1
+        """Scores of all n_groups alphas into corr (rows = alpha slots).  A compact stack (parts.stack) is finalised
+        in two launches: its ordinary groups through their slot map, the series alphas from the 14-sum partials."""
+        ir, it = parts.inv_row, parts.inv_tile
+        st = parts.stack
+        rs = _vp(resp_std.data_ptr() if resp_std is not None else 0)
+        n_plain = n_groups if st is None else st.n_cheb
+        slots = None
+        if st is not None and n_plain:
+            slots = self.upload_vector(np.asarray(st.slot_cheb), "i32")
+        if n_plain:
+            check(self.lib.lit_corr_finalize_scaled(
+                _vp(parts.dot.data_ptr()), _vp(parts.ssq.data_ptr()), parts.ld, tiles_per_group, n_plain, n_vox, n_rows,
+                eps, int(accumulate), metric, rs, _vp(ir.data_ptr() if ir is not None else 0),
+                _vp(it.data_ptr() if it is not None else 0), _vp(slots.data_ptr() if slots is not None else 0),
+                _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize")
+            self.launches += 1
+        if st is not None and st.n_tiles:
+            coef = self.upload_vector(np.asarray(st.coef, dtype=np.float64).reshape(-1), "f64")
+            sl = self.upload_vector(np.asarray(st.slot_series), "i32")
+            tile0 = n_plain * tiles_per_group // 2  # first series tile among the stack's 256-row tiles
+            it_s = it.data_ptr() + 4 * tile0 if it is not None else 0
+            check(self.lib.lit_corr_finalize_series(
+                _vp(parts.series.data_ptr()), parts.ld, 2 * st.n_tiles, n_vox, n_rows, eps, int(accumulate), metric, rs,
+                _vp(ir.data_ptr() if ir is not None else 0), _vp(it_s), _vp(coef.data_ptr()), _vp(sl.data_ptr()),
+                len(st.slot_series), _vp(corr.hi.data_ptr()), corr.ld, _vp(self.stream)), "corr_finalize_series")
+            self.launches += 1
 
     def argmax_alpha(self, corr_sum: Mat, n_folds: int, alphas_dev, want_sums: bool):
         n_alphas, n_vox = corr_sum.rows, corr_sum.cols

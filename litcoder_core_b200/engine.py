@@ -63,6 +63,10 @@ class RidgeConfig:
     # operand format of the fused inner-CV prediction + correlation GEMM: "tf32x3" or "f16x3" (scaled fp16 split
     # pairs, lit_split_f16: same product accuracy, twice the tensor-core rate)
     corr_precision: str = "f16x3"
+    # GEMM-only folds: the alphas served by the Neumann series (a^2 >= 60 lambda_max; 16 of the 20 BASELINE alphas)
+    # share FOUR stacked row blocks P_c G^q instead of one block each; their scores are 4-term combinations of 14
+    # per-voxel sums taken in the GEMM epilogue (DeviceOps.assemble_series_stack).  2.5x fewer prediction flops.
+    series_moments: bool = True
 
 
 @dataclass
@@ -262,7 +266,8 @@ class RidgeCVEngine:
             if block is None:
                 block = ops.zeros(ops.solver_block_rows(n_va, lam_max, a2), X.cols)
             comm.broadcast_inplace(ops.planes(block), src=d["owner"])
-        return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2)
+        return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2,
+                                  series_moments=cfg.series_moments)
 
     def _finish_design(self, groups, cfg: RidgeConfig) -> None:
         """After the design side of every plan is queued: read the Lanczos lambda_max of all GEMM-only folds back

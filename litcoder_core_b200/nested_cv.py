@@ -275,6 +275,7 @@ class NestedCVModel:
         if corr_precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"Unknown corr_precision: {corr_precision}")
         cfg.corr_precision = corr_precision
+        cfg.series_moments = os.environ.get("LIT_SERIES_MOMENTS", "1") != "0"  # development override
 
         # ---- H2D: X replicated, this rank's voxel block of Y (nested_cv.py:99-100) ----
         ops = self._get_ops()

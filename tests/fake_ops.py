@@ -34,6 +34,14 @@ class FMat:
         return self.a.shape[1]
 
 
+class FakeSeriesStack:
+    """Mirror of device.SeriesStack."""
+
+    def __init__(self, mat, n_cheb, rows_pad, n_tiles, slot_cheb, slot_series, coef):
+        self.mat, self.n_cheb, self.rows_pad, self.n_tiles = mat, n_cheb, rows_pad, n_tiles
+        self.slot_cheb, self.slot_series, self.coef = slot_cheb, slot_series, coef
+
+
 class FakeOps:
     TILE_N = 256
     PART_N = 128
@@ -236,27 +244,46 @@ class FakeOps:
         return out
 
     def gemm_corr(self, A, B, n_groups, rows_per_group, Yz, precision="tf32x3"):
+        """lit_gemm_corr_series: B is a split FMat of n_groups alpha groups, or a FakeSeriesStack (compact form)."""
+        stack = B if isinstance(B, FakeSeriesStack) else None
+        n_plain, n_st = n_groups, 0
+        if stack is not None:
+            assert stack.rows_pad == rows_per_group and stack.n_cheb + len(stack.slot_series) == n_groups
+            B, n_plain, n_st = stack.mat, stack.n_cheb, stack.n_tiles
         assert A.is_split and B.is_split
-        assert rows_per_group % self.TILE_N == 0 and B.rows == n_groups * rows_per_group
+        assert rows_per_group % self.TILE_N == 0 and B.rows == n_plain * rows_per_group + n_st * self.TILE_N
         assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
         assert precision in ("tf32x3", "f16x3")
         if precision == "f16x3":
-            acc = (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, rows_per_group).T).astype(F32)
+            acc = (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, self.TILE_N).T).astype(F32)
         else:
-            acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][group*R + t]
+            acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][stacked row]
         tpg = rows_per_group // self.PART_N
-        dot = np.zeros((n_groups * tpg, A.rows), dtype=F32)
+        dot = np.zeros((max(n_plain * tpg, 1), A.rows), dtype=F32)
         ssq = np.zeros_like(dot)
-        for g in range(n_groups):
+        for g in range(n_plain):
             for t in range(tpg):
                 c0 = g * rows_per_group + t * self.PART_N
                 blk = acc[:, c0:c0 + self.PART_N].astype(np.float64)
                 yz = Yz.a[t * self.PART_N:(t + 1) * self.PART_N].astype(np.float64).T
                 dot[g * tpg + t] = (blk * yz).sum(1)
                 ssq[g * tpg + t] = (blk * blk).sum(1)
+        series = None
+        if n_st:
+            # series tiles: part = 32 time points; columns [q][32] of the 128-wide half; 14 sums per (part, voxel)
+            series = np.zeros((2 * n_st * 14, A.rows), dtype=F32)
+            pairs = [(q, r) for q in range(4) for r in range(q, 4)]
+            for part in range(2 * n_st):
+                c0 = n_plain * rows_per_group + part * self.PART_N
+                T = [acc[:, c0 + q * 32:c0 + (q + 1) * 32].astype(np.float64) for q in range(4)]
+                yz = Yz.a[part * 32:(part + 1) * 32].astype(np.float64).T
+                for q in range(4):
+                    series[part * 14 + q] = (T[q] * yz).sum(1)
+                for j, (q, r) in enumerate(pairs):
+                    series[part * 14 + 4 + j] = (T[q] * T[r]).sum(1)
         self.launches += 1
         self.gemm_flops += 2.0 * A.rows * B.rows * A.cols
-        return {"dot": dot, "ssq": ssq, "n_tiles": n_groups * tpg}
+        return {"dot": dot, "ssq": ssq, "n_tiles": n_plain * tpg, "series": series, "stack": stack}
 
     # ------------------------------------------------------------------ eig
     def syevd(self, G, lam=None):
@@ -289,26 +316,63 @@ class FakeOps:
         a = G.a.astype(np.float64)
         return np.array([np.linalg.eigvalsh(0.5 * (a + a.T))[-1]])
 
+    @staticmethod
+    def solver_partition(lam_max, a2_list, series_ratio=60.0):
+        series = [j for j, a2 in enumerate(a2_list) if a2 >= series_ratio * lam_max]
+        cheb = [j for j in range(len(a2_list)) if j not in series]
+        return cheb, series
+
+    def solver_block_rows(self, n_rows, lam_max, a2_list, series_ratio=60.0):
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        return (len(cheb) + (3 if series else 0)) * n_rows
+
     def solve_blocks(self, Gs, Pc, n_rows, lam_max, a2_list, series_ratio=60.0):
-        """Compact per-fold solution block (here simply every alpha's exact solution, stacked)."""
+        """Compact per-fold solution block in the layout of DeviceOps.solve_blocks: the solutions of the small
+        alphas (exact here; Chebyshev iteration on the device) followed by P_c G^q, q = 1..3."""
         assert Gs.is_split
         p = Gs.rows
         G = Gs.a.astype(np.float64)
-        out = np.zeros((len(a2_list) * n_rows, p), dtype=F32)
-        for j, a2 in enumerate(a2_list):
-            M = np.linalg.solve(G + float(a2) * np.eye(p), Pc.a[:n_rows].astype(np.float64).T).T
-            out[j * n_rows:(j + 1) * n_rows] = M.astype(F32)
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        out = np.zeros(((len(cheb) + (3 if series else 0)) * n_rows, p), dtype=F32)
+        P = Pc.a[:n_rows].astype(np.float64)
+        for i, j in enumerate(cheb):
+            M = np.linalg.solve(G + float(a2_list[j]) * np.eye(p), P.T).T
+            out[i * n_rows:(i + 1) * n_rows] = M.astype(F32)
+        Q = P
+        for q in range(3 if series else 0):
+            Q = (Q @ G).astype(F32).astype(np.float64)
+            out[(len(cheb) + q) * n_rows:(len(cheb) + q + 1) * n_rows] = Q
         self.solver_calls = getattr(self, "solver_calls", 0) + 1
         return FMat(out)
 
-    def assemble_stack(self, block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
-        out = np.zeros((len(a2_list) * rows_pad, block.cols), dtype=F32)
-        for j in range(len(a2_list)):
-            out[j * rows_pad:j * rows_pad + n_rows] = block.a[j * n_rows:(j + 1) * n_rows]
-        return FMat(out, split=True)
+    SERIES_MIN_ALPHAS = 5
 
-    def solver_block_rows(self, n_rows, lam_max, a2_list, series_ratio=60.0):
-        return len(a2_list) * n_rows
+    def assemble_stack(self, block, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0, series_moments=False):
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        nc = len(cheb)
+        Q = [Pc.a[:n_rows].astype(np.float64)] + [block.a[(nc + q) * n_rows:(nc + q + 1) * n_rows].astype(np.float64)
+                                                  for q in range(3 if series else 0)]
+        if series_moments and len(series) >= self.SERIES_MIN_ALPHAS:
+            # lit_series_stack: row tile*256 + half*128 + q*32 + i <-> time point tile*64 + half*32 + i
+            n_tiles = -(-n_rows // 64)
+            out = np.zeros((nc * rows_pad + n_tiles * self.TILE_N, block.cols), dtype=F32)
+            for i in range(nc):
+                out[i * rows_pad:i * rows_pad + n_rows] = block.a[i * n_rows:(i + 1) * n_rows]
+            for t in range(n_rows):
+                tile, half, i = t // 64, (t % 64) // 32, t % 32
+                for q in range(4):
+                    out[nc * rows_pad + tile * 256 + half * 128 + q * 32 + i] = Q[q][t] * float(lam_max) ** -q
+            coef = np.array([[(-1.0) ** q * float(lam_max) ** q / float(a2_list[j]) ** (q + 1) for q in range(4)]
+                             for j in series], dtype=np.float64)
+            return FakeSeriesStack(FMat(out, split=True), nc, rows_pad, n_tiles, np.asarray(cheb, dtype=np.int32),
+                                   np.asarray(series, dtype=np.int32), coef)
+        out = np.zeros((len(a2_list) * rows_pad, block.cols), dtype=F32)
+        for i, j in enumerate(cheb):
+            out[j * rows_pad:j * rows_pad + n_rows] = block.a[i * n_rows:(i + 1) * n_rows]
+        for j in series:
+            a2 = float(a2_list[j])
+            out[j * rows_pad:j * rows_pad + n_rows] = sum((-1.0) ** q * a2 ** -(q + 1) * Q[q] for q in range(4))
+        return FMat(out, split=True)
 
     def inverse_stack(self, Gs, Pc, n_rows, rows_pad, lam_max, a2_list, series_ratio=60.0):
         return self.assemble_stack(self.solve_blocks(Gs, Pc, n_rows, lam_max, a2_list), Pc, n_rows, rows_pad, lam_max,
@@ -340,22 +404,39 @@ class FakeOps:
             out = np.where(keep[None, :], Z.a / (lam[None, :] + a2[:, None]), F32(0))
         return FMat(out.astype(F32), split=True)
 
+    @staticmethod
+    def _inner_score(d, q, metric, raw, n_rows, eps, resp_std):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if metric == 0:
+                c = (d / F32(n_rows)) / (np.sqrt(q / F32(n_rows - 1)) + F32(eps))
+            else:
+                qvar = (resp_std * resp_std).astype(F32)
+                resvar = (qvar * F32(n_rows - 1) - 2 * d + q) / F32(n_rows - 1)
+                rsq = 1 - resvar / qvar
+                c = np.sqrt(np.abs(rsq)) * np.sign(rsq)
+        return c.astype(F32) if raw else np.nan_to_num(c.astype(F32))
+
     def corr_finalize(self, parts, tiles_per_group, n_groups, n_vox, n_rows, eps, corr, accumulate, metric=0,
                       resp_std=None):
         raw, metric = bool(metric & 2), metric & 1
-        for g in range(n_groups):
+        st = parts.get("stack")
+        n_plain = n_groups if st is None else st.n_cheb
+        for g in range(n_plain):
             d = parts["dot"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
             q = parts["ssq"][g * tiles_per_group:(g + 1) * tiles_per_group].sum(0, dtype=F32)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                if metric == 0:
-                    c = (d / F32(n_rows)) / (np.sqrt(q / F32(n_rows - 1)) + F32(eps))
-                else:
-                    qvar = (resp_std * resp_std).astype(F32)
-                    resvar = (qvar * F32(n_rows - 1) - 2 * d + q) / F32(n_rows - 1)
-                    rsq = 1 - resvar / qvar
-                    c = np.sqrt(np.abs(rsq)) * np.sign(rsq)
-            c = c.astype(F32) if raw else np.nan_to_num(c.astype(F32))
-            corr.a[g] = corr.a[g] + c if accumulate else c
+            c = self._inner_score(d, q, metric, raw, n_rows, eps, resp_std)
+            slot = g if st is None else int(st.slot_cheb[g])
+            corr.a[slot] = corr.a[slot] + c if accumulate else c
+        if st is not None and st.n_tiles:
+            # lit_corr_finalize_series: 4-term combinations of the 14 sums, in float64
+            S = parts["series"].astype(np.float64).reshape(2 * st.n_tiles, 14, -1).sum(0)
+            pairs = [(q, r) for q in range(4) for r in range(q, 4)]
+            for a, slot in enumerate(st.slot_series):
+                cf = st.coef[a]
+                d = sum(cf[q] * S[q] for q in range(4))
+                q2 = sum((1.0 if q == r else 2.0) * cf[q] * cf[r] * S[4 + j] for j, (q, r) in enumerate(pairs))
+                c = self._inner_score(d.astype(F32), q2.astype(F32), metric, raw, n_rows, eps, resp_std)
+                corr.a[slot] = corr.a[slot] + c if accumulate else c
 
     def argmax_alpha(self, corr_sum, n_folds, alphas_dev, want_sums):
         mean = (corr_sum.a / F32(n_folds)).astype(F32)

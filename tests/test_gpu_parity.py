@@ -649,10 +649,10 @@ def test_gemm_corr_f16x3_matches_fp64(ops):
         finally:
             ops.gemm_variant = old
         ir = parts.inv_row.cpu().numpy()[:M].astype(np.float64)
-        ig = parts.inv_group.cpu().numpy()[:G].astype(np.float64)
-        sc = ig[:, None] * ir[None, :]
-        dot = parts.dot.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1) * sc
-        ssq = parts.ssq.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1) * sc * sc
+        it = parts.inv_tile.cpu().numpy()[:G * R // 256].astype(np.float64)  # one scale per 256-row tile = 2 parts
+        sc = np.repeat(it, 2)[:, None] * ir[None, :]
+        dot = (parts.dot.cpu().numpy()[:, :M].astype(np.float64) * sc).reshape(G, R // 128, M).sum(1)
+        ssq = (parts.ssq.cpu().numpy()[:, :M].astype(np.float64) * sc * sc).reshape(G, R // 128, M).sum(1)
         dot_t = ref.dot.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1)
         ssq_t = ref.ssq.cpu().numpy()[:, :M].astype(np.float64).reshape(G, R // 128, M).sum(1)
         acc = A.astype(np.float64) @ B.astype(np.float64).T
@@ -686,6 +686,102 @@ def test_corr_precisions_agree_on_fit(ops):
     assert np.abs(out["tf32x3"][0][same] - out["f16x3"][0][same]).max() < 2e-5
     with pytest.raises(ValueError, match="Unknown corr_precision"):
         NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision="bf16", **kw)
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_series_moment_stack_matches_full_stack(ops, precision, metric):
+    """Compact alpha stack (lit_series_stack + lit_gemm_corr_series + lit_corr_finalize_series): the scores of the
+    alphas served by the Neumann series, taken as 4-term combinations of 14 per-voxel sums, against the one-block-
+    per-alpha stack and against fp64."""
+    rng = np.random.default_rng(17)
+    n, p, m, V = 1500, 200, 331, 700   # m: ragged against the 64-point series tiles and the 256-row padding
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    for j in range(1, p):
+        X[:, j] = 0.5 * X[:, j - 1] + 0.87 * X[:, j]
+    G = (X.T.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
+    lmax = float(np.linalg.eigvalsh(G.astype(np.float64))[-1])
+    P = rng.standard_normal((m, p)).astype(np.float32)
+    Pc = (P - P.mean(0)).astype(np.float32)
+    alphas = np.logspace(-1, 8, 20)
+    a2 = [float(a) ** 2 * lmax for a in alphas]
+    rows_pad = 512
+    Ct = (rng.standard_normal((V, p)) * np.exp(rng.uniform(-3, 3, (V, 1)))).astype(np.float32) * np.float32(n)
+    Yv = rng.standard_normal((m, V)).astype(np.float32)
+    Yv[:, 3] = 0.0
+    mean, sd = Yv.mean(0), Yv.std(0, ddof=1)
+    Yn = (Yv - mean) / (sd + 1e-8) if metric == 0 else Yv - mean
+    Yz = np.zeros((rows_pad, V), dtype=np.float32)
+    Yz[:m] = Yn
+    Pd = ops.upload_matrix(Pc)
+    block = ops.solve_blocks(_split(ops, G), Pd, m, lmax, a2)
+    cheb, series = ops.solver_partition(lmax, a2)
+    assert len(series) == 16 and len(cheb) == 4
+    full = ops.assemble_stack(block, Pd, m, rows_pad, lmax, a2, series_moments=False)
+    comp = ops.assemble_stack(block, Pd, m, rows_pad, lmax, a2, series_moments=True)
+    assert type(comp).__name__ == "SeriesStack" and comp.n_tiles == 6 and comp.mat.rows == 4 * rows_pad + 6 * 256
+    A, Yd = _split(ops, Ct), ops.upload_matrix(Yz)
+    std = ops.upload_vector(sd.astype(np.float32), "f32")
+    got = {}
+    for name, st in (("full", full), ("compact", comp)):
+        corr = ops.empty(20, V)
+        for rep in range(2):  # second pass accumulates
+            parts = ops.gemm_corr(A, st, 20, rows_pad, Yd, precision=precision)
+            ops.corr_finalize(parts, rows_pad // ops.PART_N, 20, V, m, 1e-8, corr, accumulate=(rep > 0), metric=metric,
+                              resp_std=std)
+        got[name] = ops.download_matrix(corr).astype(np.float64) / 2
+    # fp64 statement of the same scores
+    G64, C64 = G.astype(np.float64), Ct.astype(np.float64)
+    want = np.zeros((20, V))
+    for j, s in enumerate(a2):
+        pred = np.linalg.solve(G64 + s * np.eye(p), Pc.astype(np.float64).T).T @ C64.T  # (m x V)
+        d, q = (pred * Yn).sum(0), (pred * pred).sum(0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if metric == 0:
+                want[j] = (d / m) / (np.sqrt(q / (m - 1)) + 1e-8)
+            else:
+                qv = sd.astype(np.float64) ** 2
+                rsq = 1 - ((qv * (m - 1) - 2 * d + q) / (m - 1)) / qv
+                want[j] = np.sqrt(np.abs(rsq)) * np.sign(rsq)
+    want = np.nan_to_num(want)
+    ok = np.ones(V, dtype=bool)
+    ok[3] = False  # constant voxel: 0/0 -> documented divergence (nan_to_num of rounding noise)
+    if metric == 0:
+        assert np.abs(got["compact"] - got["full"])[:, ok].max() < 2e-5
+        assert np.abs(got["compact"] - want)[:, ok].max() < 3e-5
+    else:
+        # compare R^2 itself (the signed square root has an infinite slope at 0), relative where it is large
+        sq = {k: np.sign(v) * v ** 2 for k, v in got.items()}
+        wsq = np.sign(want) * want ** 2
+        den = np.maximum(np.abs(wsq), 1.0)
+        assert (np.abs(sq["compact"] - sq["full"]) / den)[:, ok].max() < 5e-5
+        assert (np.abs(sq["compact"] - wsq) / den)[:, ok].max() < 5e-5
+
+
+def test_series_moments_agree_on_fit(ops, monkeypatch):
+    """Whole fit on the BASELINE alpha grid (16 of 20 alphas ride the series) with and without the compact stack."""
+    from litcoder_core_b200 import NestedCVModel
+
+    rng = np.random.default_rng(23)
+    X, Y = _synthetic(rng, 700, 128, 900)
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 8, 20))
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LIT_SERIES_MOMENTS", flag)
+        for prec in ("tf32x3", "f16x3"):
+            random.seed(3)
+            m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision=prec,
+                                                                             inner_solver="chebyshev", **kw)
+            out[flag, prec] = (np.asarray(m["correlations"]), w, np.asarray(a))
+    for prec in ("tf32x3", "f16x3"):
+        same = out["0", prec][2] == out["1", prec][2]
+        assert same.mean() > 0.97, same.mean()
+        assert np.abs(out["0", prec][0][same] - out["1", prec][0][same]).max() < 2e-5
+    random.seed(3)
+    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
+    same = np.isclose(out["1", "f16x3"][2], ao)
+    assert same.mean() > 0.9, same.mean()
+    assert np.abs(out["1", "f16x3"][0][same] - np.asarray(mo["correlations"], dtype=np.float64)[same]).max() < 1e-4
 
 
 def test_structure_kernels_match_reference_trainer(ops):

@@ -371,6 +371,31 @@ def test_inner_solvers_agree_on_fake_ops(name):
         NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(X[:400], Y[:400], inner_solver="qr", **kw)
 
 
+def test_series_moments_match_full_stack_on_fake_ops(monkeypatch):
+    """GEMM-only folds: the compact stack (four series terms + 14 per-voxel sums, combined per alpha at finalize)
+    scores the alphas like the one-block-per-alpha stack; both follow the golden reference run."""
+    g = load_golden("fit_predict.npz")
+    X, Y = g["X"], g["Y"]
+    kw = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 8, 20))
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LIT_SERIES_MOMENTS", flag)
+        for prec in ("tf32x3", "f16x3"):
+            ops = FakeOps()
+            seen = []
+            orig = ops.gemm_corr
+            ops.gemm_corr = lambda *a, _o=orig, _s=seen, **k: (_s.append(type(a[1]).__name__), _o(*a, **k))[1]
+            random.seed(7)
+            m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X[:400], Y[:400], inner_solver="chebyshev",
+                                                                             corr_precision=prec, **kw)
+            out[flag, prec] = (np.asarray(m["correlations"]), np.asarray(a))
+            assert ("FakeSeriesStack" in seen) == (flag == "1")
+    for prec in ("tf32x3", "f16x3"):
+        same = out["0", prec][1] == out["1", prec][1]
+        assert same.mean() > 0.97
+        np.testing.assert_allclose(out["0", prec][0][same], out["1", prec][0][same], atol=1e-5)
+
+
 def _structure_golden():
     g = load_golden("structure.npz")
     stories = [str(x) for x in g["stories"]]
