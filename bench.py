@@ -304,7 +304,10 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        # dominant kernel: the alpha-stacked prediction GEMM with the fused correlation epilogue
+        # The two instances of the tcgen05 GEMM carry the fit: the fused prediction + correlation GEMM (few, large
+        # launches) and the store-epilogue GEMM (Grams, cross products, solver steps, weights: thousands of
+        # launches of many shapes).  `roofline` describes whichever took more time in the timed region; the other
+        # one is reported as `roofline_other`.
         big = [(ms, fl) for ms, fl in zip(corr_ms, corr_flops) if fl >= 0.5 * max(corr_flops)]
         avg_ms = statistics.mean(ms for ms, _ in big)
         flops = statistics.mean(fl for _, fl in big)
@@ -312,27 +315,64 @@ def run_b200(args):
         peak = peaks["bf16_tflops_sustained"]
         prec = model.last_stats.get("corr_precision", "tf32x3")
         f16 = prec == "f16x3"
+        compact = bool(model.last_stats.get("compact_stacks", 0))
         # DRAM bytes per launch from the committed `ncu --set full` capture of this kernel and shape
         traffic, traffic_src = None, None
-        tpath = os.path.join(ROOT, "profiles", "corr_gemm_f16x3_traffic.json" if f16 else "corr_gemm_traffic.json")
+        tname = "corr_gemm_%s%s_traffic.json" % ("compact_" if compact else "", prec)
+        if prec == "tf32x3" and not compact:
+            tname = "corr_gemm_traffic.json"
+        tpath = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tpath) and world == 1 and not args.voxels and args.workload.startswith("config2"):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             traffic_src = os.path.relpath(tpath, ROOT)
+        form = ("compact alpha stack: the solved alphas' row blocks + 4 shared Neumann-series terms, 14 per-voxel "
+                "sums per 32 time points" if compact else "one row block per alpha")
         if f16:
-            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR,F16> via lit_gemm_f16x3_nt_corr"
-            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 kind::f16 MMAs per "
-                    "product on scaled fp16 hi/lo pairs (same 2^-22 product accuracy as 3xTF32); fp16 runs at the "
-                    "bf16 rate, so the ceiling of the method is peak/3 and the tensor pipe itself sustains 3x this figure")
+            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR,F16> via lit_gemm_corr_series"
+            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K) of the launched shape (%s).  The kernel executes "
+                    "3 kind::f16 MMAs per product on scaled fp16 hi/lo pairs (same 2^-22 product accuracy as 3xTF32); "
+                    "fp16 runs at the bf16 rate, so the ceiling of the method is peak/3 and the tensor pipe itself "
+                    "sustains 3x this figure" % form)
             pipe = {"executed_f16_tflops": 3 * achieved, "f16_dense_peak": peak, "frac": 3 * achieved / peak}
         else:
-            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR> via lit_gemm_tf32x3_nt_corr"
-            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K).  The kernel executes 3 TF32 MMAs per "
-                    "product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the tensor pipe "
-                    "itself sustains 3x this figure against a TF32 dense rate of about peak/2")
+            kname = "gemm_tf32x3_kernel<256,2,EPI_CORR> via lit_gemm_corr_series"
+            note = ("achieved counts ALGORITHMIC fp32 flops (2*M*N*K) of the launched shape (%s).  The kernel executes "
+                    "3 TF32 MMAs per product (3xTF32 split precision) and TF32 runs at half the bf16 rate, so the "
+                    "tensor pipe itself sustains 3x this figure against a TF32 dense rate of about peak/2" % form)
             pipe = {"executed_tf32_tflops": 3 * achieved, "tf32_dense_peak_est": peak / 2,
                     "frac": 3 * achieved / (peak / 2)}
+        peak_src = f"{peaks['source']} cuBLAS bf16 dense, sustained (kernel timed inside a long step)"
+        roof_corr = {
+            "kernel": kname + " (alpha-stacked predictions + fused per-voxel correlation)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": traffic,
+            "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": traffic_src, "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
+            "total_ms_per_step": sum(corr_ms) / args.steps, "note": note, "tensor_pipe": pipe,
+        }
+        store_ms = phase.get("gemm", 0.0)  # per step: CUDA events around every store-epilogue GEMM launch
+        store_flops = (model.last_stats["gemm_flops"] * args.steps - sum(corr_flops)) / args.steps
+        store_n = model.last_stats.get("store_gemm_launches", 0)
+        store_ach = store_flops / store_ms / 1e9 if store_ms > 0 else 0.0
+        roof_store = {
+            "kernel": "gemm_tf32x3_kernel<256,2,EPI_STORE> via lit_gemm_tf32x3_nt (Grams, cross products Y^T X and their "
+                      "downdates, solver steps, rotations, weights: all launches of a fit together)",
+            "bound": "tensor", "achieved": store_ach, "peak": peak, "unit": "TFLOP/s", "frac": store_ach / peak,
+            "peak_source": peak_src, "traffic": None, "launch_ms": store_ms / max(store_n, 1),
+            "flops_per_launch": store_flops / max(store_n, 1), "launches_timed": store_n * args.steps,
+            "total_ms_per_step": store_ms,
+            "note": ("achieved = algorithmic 2*M*N*K summed over every launch of a fit / summed launch durations; 3 TF32 "
+                     "MMAs per product, TF32 at half the bf16 rate: ceiling of the method = peak/6.  Most launches are "
+                     "single-wave solver steps (M x 3072 x 3072 with M <= 6,000), where tile quantisation and the "
+                     "pipeline prologue weigh in; while eigendecompositions are in flight the grids are limited to "
+                     "100 SMs"),
+            "tensor_pipe": {"executed_tf32_tflops": 3 * store_ach, "tf32_dense_peak_est": peak / 2,
+                            "frac": 3 * store_ach / (peak / 2)},
+        }
+        roof_main, roof_other = (roof_corr, roof_store) if roof_corr["total_ms_per_step"] >= store_ms \
+            else (roof_store, roof_corr)
         line = {
             "metric": METRIC, "value": units / (ms_value / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value, "higher_is_better": True, "scaling": "strong",
@@ -348,15 +388,8 @@ def run_b200(args):
                     "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {
-                "kernel": kname + " (alpha-stacked predictions + fused per-voxel correlation)",
-                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": f"{peaks['source']} cuBLAS bf16 dense, sustained (kernel timed inside a long step)",
-                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "traffic_source": traffic_src,
-                "launch_ms": avg_ms, "flops_per_launch": flops, "launches_timed": len(big),
-                "note": note, "tensor_pipe": pipe,
-            },
+            "roofline": roof_main,
+            "roofline_other": roof_other,
             "phases_ms": {k: round(v, 2) for k, v in sorted(phase.items())},
             "e2e_phases_ms": {k: round(v, 2) for k, v in sorted(e2e_phase.items())},
             "result_check": {"median_r": metrics["median_score"], "n_significant": metrics["n_significant"],

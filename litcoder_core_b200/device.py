@@ -167,6 +167,8 @@ class DeviceOps:
         self.gemm_flops = 0.0  # algorithmic 2*M*N*K of the executed GEMMs (x3 tensor-core MMAs each)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.store_gemms = 0  # launches of the store-epilogue GEMM
+        self.compact_stacks = 0  # fused-GEMM launches on a compact (series) alpha stack
         self._corr_log: List[tuple] = []  # (start, stop, flops) of every fused prediction+correlation GEMM
         self._staging: List[object] = []
         self._timed: Dict[str, List[tuple]] = {}
@@ -227,7 +229,12 @@ class DeviceOps:
         a = np.ascontiguousarray(np.asarray(arr, dtype=npdt))
         out = self.vec(a.size, dtype)
         if a.size:
-            out[: a.size].copy_(t.from_numpy(a), non_blocking=False)
+            # through a page-locked staging block and an ASYNCHRONOUS copy: a pageable source would make the copy
+            # drain the stream (the host would stop running ahead of the device at every small upload).  The
+            # caching host allocator keeps the block alive until the copy has executed.
+            host = t.empty((a.size,), dtype=out.dtype, pin_memory=True)
+            host.numpy()[...] = a.reshape(-1)
+            out[: a.size].copy_(host, non_blocking=True)
             self.h2d_bytes += a.nbytes
         return out
 
@@ -466,6 +473,7 @@ class DeviceOps:
         with self.timed("gemm"):
             self._gemm_call(A, B, M, N, K, alpha, Cin, beta, out)
         self.launches += 1
+        self.store_gemms += 1
         self.gemm_flops += 2.0 * M * N * K
         return out
 
@@ -541,6 +549,7 @@ class DeviceOps:
             _vp(self.stream)), "gemm_corr_series")
         e1.record()
         self.launches += 1
+        self.compact_stacks += int(stack is not None)
         self.gemm_flops += flops
         return Partials(dot, ssq, n_tiles, ld, inv_row, inv_tile, series, stack)
 
@@ -630,13 +639,15 @@ class DeviceOps:
         return out
 
     @staticmethod
-    def chebyshev_plan(lam_max: float, a2: float, tol: float = 1e-6, safety: float = 1.02):
-        """Scalar schedule of the Chebyshev iteration for (G + a2 I) with spec(G) in [0, safety * lam_max]:
+    def chebyshev_plan_interval(lo: float, hi: float, tol: float = 1e-6):
+        """Scalar schedule of the Chebyshev iteration for a symmetric operator with spectrum in [lo, hi], lo > 0:
         list of (c1, c2) per step (d = c1 d + c2 r), after Saad, Iterative Methods, alg. 12.1."""
-        u = safety * lam_max
-        theta, delta = a2 + 0.5 * u, 0.5 * u
+        if not (0.0 < lo <= hi):
+            raise ValueError(f"chebyshev_plan_interval: need 0 < lo <= hi (got {lo}, {hi})")
+        theta = 0.5 * (hi + lo)
+        delta = max(0.5 * (hi - lo), 1e-9 * theta)
         sigma1 = theta / delta
-        kappa = (a2 + u) / a2
+        kappa = hi / lo
         rate = (np.sqrt(kappa) - 1.0) / (np.sqrt(kappa) + 1.0)
         n_steps = max(2, int(np.ceil(np.log(2.0 / tol) / -np.log(rate)))) if rate > 0 else 2
         rho = 1.0 / sigma1
@@ -646,6 +657,11 @@ class DeviceOps:
             plan.append((rho_new * rho, 2.0 * rho_new / delta))
             rho = rho_new
         return plan
+
+    @staticmethod
+    def chebyshev_plan(lam_max: float, a2: float, tol: float = 1e-6, safety: float = 1.02):
+        """Schedule for (G + a2 I) with spec(G) in [0, safety * lam_max]."""
+        return DeviceOps.chebyshev_plan_interval(a2, a2 + safety * lam_max, tol)
 
     @staticmethod
     def solver_partition(lam_max: float, a2_list, series_ratio: float = 60.0):
@@ -661,18 +677,94 @@ class DeviceOps:
     def _view_rows(self, m: Mat, r0: int, rows: int) -> Mat:
         return Mat(m.hi[r0:r0 + rows], m.lo[r0:r0 + rows] if m.lo is not None else None, rows, m.cols, ld=m.ld)
 
-    def solve_blocks(self, Gs: Mat, Pc: Mat, n_rows: int, lam_max: float, a2_list, series_ratio: float = 60.0) -> Mat:
+    def lbo_prepare(self, Pv: Mat, Vt: Mat, lam_o, a2_min: float, steps: int = 48) -> dict:
+        """Leave-block-out form of an inner fold whose validation rows R are exactly the rows removed from the
+        outer training set (G_in = G_o - X_R^T X_R) once the outer Gram's eigendecomposition G_o = V diag(lam_o) V^T
+        is known:
+            X_R (G_in + a^2 I)^-1 = (I - H_a)^-1 X_R M_a,   M_a = V diag(1/(lam_o + a^2)) V^T,  H_a = X_R M_a X_R^T
+        (Woodbury on the downdate), i.e. an |R| x |R| system with spectrum in (0, 1] instead of a p x p one with
+        condition number (lam_max + a^2)/a^2.  Queues B = X_R V (|R| x k), E = B diag(1/(lam_o + a2_min)),
+        H = E B^T for the smallest alpha and the Lanczos estimate of lambda_max(H); nothing is read back here.
+        Pv: split pair of X_R (|R| x p); Vt: split pair of the eigenvectors as rows (k x p)."""
+        B = self.gemm(Pv, Vt, split_out=True)
+        E = self._lbo_scaled(B, lam_o, a2_min)
+        H = self.gemm(E, B, split_out=True)
+        return {"B": B, "E": E, "H": H, "a2": float(a2_min), "hmax_dev": self.lambda_max(H, steps)}
+
+    def _lbo_scaled(self, B: Mat, lam_o, a2: float) -> Mat:
+        """B diag(1 / (lam_o + a2)) as a split pair (columns of non-positive eigenvalues -- numerically null
+        directions, where B vanishes -- are dropped)."""
+        alpha_v = self.vec(B.rows)
+        check(self.lib.lit_fill_f32(_vp(alpha_v.data_ptr()), alpha_v.numel(), float(np.sqrt(np.float64(a2))),
+                                    _vp(self.stream)), "fill")
+        self.launches += 1
+        return self.scale_rows_by_alpha(B, lam_o, alpha_v, False, 0.0)
+
+    @staticmethod
+    def lbo_bounds(h0: float, a2_0: float, a2: float, lam_top: float):
+        """Spectral interval [lo, 1] of I - H_a from the Lanczos estimate h0 of lambda_max(H_a0) at the smallest
+        alpha: H_a <= H_a0 (lam_top + a2_0)/(lam_top + a2) for a2 >= a2_0 (the ratio of the two diagonal scalings is
+        largest at the top eigenvalue), and I - H_a >= a2/(a2 + lam_top) always (G_R <= G_o)."""
+        hi_h = (1.06 * h0 + 0.01) * (1.001 * lam_top + a2_0) / (1.001 * lam_top + a2)
+        lo_rigorous = a2 / (a2 + 1.001 * lam_top)
+        return max(1.0 - hi_h, lo_rigorous), 1.0
+
+    def _lbo_solve(self, block: Mat, lbo: dict, cheb, a2_list, n_rows: int, tol: float = 1e-6) -> None:
+        """Rows [i * n_rows, (i+1) * n_rows) of `block` <- J (I - H_a)^-1 B D_a V^T for the i-th Chebyshev alpha
+        (J = column centring over the validation rows).  The |R| x |R| systems are solved by Chebyshev iteration on
+        the transposed unknown x = Z^T (k x |R|), so that every step is one NT GEMM r = t + d H; a handful of steps
+        each (the spectrum of I - H_a lies in [1 - lambda_max(H_a), 1])."""
+        prep, Vs, lam_o = lbo["prep"], lbo["V"], lbo["lam"]
+        B = prep["B"]
+        k = B.cols
+        s = _vp(self.stream)
+        x, dvec, t, r = (self.empty(k, n_rows) for _ in range(4))
+        dsp = self.empty(k, n_rows, split=True)
+        ld = x.ld
+        for i, j in enumerate(cheb):
+            a2 = float(a2_list[j])
+            if abs(a2 - prep["a2"]) <= 1e-12 * a2:
+                E, H = prep["E"], prep["H"]
+            else:
+                E = self._lbo_scaled(B, lam_o, a2)
+                H = self.gemm(E, B, split_out=True)
+            Ef = self.zeros(n_rows, k)
+            self.axpy(1.0, E, Ef)  # hi + lo
+            Et = self.transpose(Ef)  # right-hand side, transposed: (k x |R|)
+            if Et.ld != ld:
+                raise ValueError("lbo_solve: pitch mismatch")
+            lo, hi = self.lbo_bounds(lbo["h0"], prep["a2"], a2, lbo["lam_top"])
+            plan = self.chebyshev_plan_interval(lo, hi, tol)
+            for step, (c1, c2) in enumerate(plan):
+                src = Et if step == 0 else r
+                check(self.lib.lit_cheb_update(_vp(dvec.hi.data_ptr()), _vp(src.hi.data_ptr()), _vp(x.hi.data_ptr()),
+                                               _vp(t.hi.data_ptr()), _vp(dsp.hi.data_ptr()), _vp(dsp.lo.data_ptr()), ld,
+                                               k, n_rows, c1, c2, 1.0, int(step == 0), s), "cheb_update")
+                self.launches += 1
+                if step + 1 < len(plan):
+                    self.gemm(dsp, H, alpha=1.0, Cin=t, beta=1.0, out=r)  # r = t + d H  (operator I - H, t = r - d)
+            Z = self.transpose(x, split=True)  # (|R| x k)
+            S = self.gemm(Z, Vs)  # back to the feature basis: Z V^T  (|R| x p)
+            mean, _ = self.col_stats(S, None, n_rows, ddof=0)
+            self.gather_normalize(S, None, n_rows, mean, None, 2, 0.0, out=self._view_rows(block, i * n_rows, n_rows))
+
+    def solve_blocks(self, Gs: Mat, Pc: Mat, n_rows: int, lam_max: float, a2_list, series_ratio: float = 60.0,
+                     lbo: Optional[dict] = None) -> Mat:
         """The expensive, alpha-specific part of P_c (G + a^2 I)^-1 as ONE compact fp32 matrix
-        [(n_cheb + 3) * n_rows][p]: the Chebyshev solutions of the small alphas followed by P_c G^q, q = 1..3
+        [(n_cheb + 3) * n_rows][p]: the solutions of the small alphas followed by P_c G^q, q = 1..3
         (the shared powers of the Neumann series).  This is what a rank broadcasts for a fold it owns
-        (130 MB at config 2 instead of the 755 MB alpha stack).  Gs: split pair of G (p x p); Pc: fp32 (n_rows x p)."""
+        (130 MB at config 2 instead of the 755 MB alpha stack).  Gs: split pair of G (p x p); Pc: fp32 (n_rows x p).
+        The small alphas are solved by Chebyshev iteration on (G + a^2 I), or -- with `lbo` (lbo_prepare's dict plus
+        "V", "lam", "lam_top", "h0") -- through the leave-block-out identity on the outer eigendecomposition."""
         p = Gs.rows
         cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
         n_q = 3 if series else 0
         block = self.zeros((len(cheb) + n_q) * n_rows, p)
         s = _vp(self.stream)
         ld = block.ld
-        if cheb:
+        if cheb and lbo is not None:
+            self._lbo_solve(block, lbo, cheb, a2_list, n_rows)
+        elif cheb:
             # The systems of all Chebyshev alphas advance together: one update launch per still-active system
             # (own scalars) and ONE stacked GEMM r = t - d G per step over the rows of the active systems.
             # cheb is in alpha order = descending step count, so the active systems are always a row prefix.

@@ -67,6 +67,10 @@ class RidgeConfig:
     # share FOUR stacked row blocks P_c G^q instead of one block each; their scores are 4-term combinations of 14
     # per-voxel sums taken in the GEMM epilogue (DeviceOps.assemble_series_stack).  2.5x fewer prediction flops.
     series_moments: bool = True
+    # GEMM-only folds whose validation rows are exactly the rows removed from the outer training set (the nested
+    # chunked / k-fold layouts of the reference): solve the small alphas through the leave-block-out identity on
+    # the outer fold's eigendecomposition (DeviceOps.lbo_prepare) instead of Chebyshev iteration on the p x p Gram
+    leave_block_out: bool = True
 
 
 @dataclass
@@ -193,6 +197,9 @@ class RidgeCVEngine:
             else:
                 d["cheb"] = self._use_chebyshev(cfg)
                 need_G = mine  # the Gram is only needed by the rank that solves this fold
+                d["lbo"] = bool(d["cheb"] and cfg.leave_block_out and d["R"] is not None and G_o is not None
+                                and len(d["R_rows"]) == len(d["val_rows"])
+                                and np.array_equal(np.sort(d["R_rows"]), np.sort(d["val_rows"])))
                 if d["R"] is not None and G_o is not None:
                     XRt = ops.gather_rows_T_split(X, d["R"], len(d["R_rows"]))  # (p x |R|)
                     d.update(XRt=XRt, XtT=None,
@@ -249,9 +256,44 @@ class RidgeCVEngine:
         a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
         if min(a2) * 1e4 < lam_max:
             raise ValueError("inner_solver='chebyshev' needs alpha^2 >= 1e-4 * lambda_max; use inner_solver='eig'")
-        block = ops.solve_blocks(ops.split(d["G"]), self._centred_val_design(X, d), len(d["val_rows"]), lam_max, a2)
+        block = ops.solve_blocks(ops.split(d["G"]), self._centred_val_design(X, d), len(d["val_rows"]), lam_max, a2,
+                                 lbo=d.pop("lbo_args", None))
         d["G"] = None
         return block
+
+    def _prepare_lbo(self, X, outer, inners, cfg: RidgeConfig) -> None:
+        """Leave-block-out folds of one outer fold (see DeviceOps.lbo_prepare): make the outer eigendecomposition
+        available (every rank takes part in its broadcast), queue B / H / Lanczos for the folds this rank owns,
+        read the Lanczos values and the top outer eigenvalue back in ONE synchronisation, and -- with several
+        ranks -- solve the owned folds right away so that no rank waits for another one's solve."""
+        ops, comm = self.ops, self.comm
+        if not any(d.get("lbo") for d in inners):
+            return
+        Vt_s, Vt, lam = self._eig_ready(outer)
+        todo = []
+        for d in inners:
+            if not (d.get("lbo") and d["owner"] == comm.rank and "block" not in d):
+                continue
+            a2 = self._scaled_alphas_sq(float(d["lmax"]), cfg.alphas, cfg)
+            cheb, _ = ops.solver_partition(float(d["lmax"]), a2)
+            if not cheb:
+                continue
+            if "V_split" not in outer:
+                outer["V_split"] = ops.transpose(Vt, split=True)  # V (p x k): rows = features
+            Pv = ops.gather_rows(X, d["val"], len(d["val_rows"]), split=True)  # X_R (|R| x p)
+            d["lbo_args"] = {"prep": ops.lbo_prepare(Pv, Vt_s, lam, a2[cheb[0]]), "V": outer["V_split"], "lam": lam}
+            todo.append(d)
+        if not todo:
+            return
+        lam_top = float(np.asarray(ops.download(lam)).reshape(-1)[Vt.rows - 1])
+        for d in todo:
+            d["lbo_args"]["lam_top"] = lam_top
+            d["lbo_args"]["h0"] = float(np.asarray(ops.download(d["lbo_args"]["prep"]["hmax_dev"])).reshape(-1)[0])
+            if not (0.0 <= d["lbo_args"]["h0"] < 1.0 + 1e-3) or not (lam_top > 0.0):
+                raise FloatingPointError("leave-block-out: lambda_max(H) outside [0, 1] (degenerate design)")
+        if comm.world > 1:
+            for d in todo:
+                d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
 
     def _stack_from_blocks(self, X, d, n_alphas: int, rows_pad: int, alphas, cfg: RidgeConfig):
         """Every rank: alpha stack of a GEMM-only fold from the owner's solution block (broadcast if needed)."""
@@ -289,7 +331,7 @@ class RidgeCVEngine:
             d["lmax"] = float(v)
         if comm.world > 1:
             for X, d in jobs:
-                if d["owner"] == comm.rank:
+                if d["owner"] == comm.rank and not d.get("lbo"):  # leave-block-out folds: see _prepare_lbo
                     d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
 
     def _next_eig_owner(self) -> int:
@@ -300,12 +342,15 @@ class RidgeCVEngine:
     def _eig_ready(self, d):
         """Wait (on the main stream) for d's eigendecomposition; returns (Vt split, Vt fp32, lam)."""
         ops = self.ops
-        if d["ticket"] is not None:
-            ops.wait(d["ticket"])
-            d["ticket"] = None
-        if self.comm.world > 1:
-            self.comm.broadcast_inplace([ops.raw(d["G"]), ops.raw(d["lam"])], src=d["owner"])
-        return ops.split(d["G"]), d["G"], d["lam"]
+        if not d.get("eig_ready"):
+            if d["ticket"] is not None:
+                ops.wait(d["ticket"])
+                d["ticket"] = None
+            if self.comm.world > 1:
+                self.comm.broadcast_inplace([ops.raw(d["G"]), ops.raw(d["lam"])], src=d["owner"])
+            d["eig_ready"] = True
+            d["Vt_split"] = ops.split(d["G"])
+        return d["Vt_split"], d["G"], d["lam"]
 
     # ------------------------------------------------------------------------------------------
     # inner CV
@@ -319,6 +364,7 @@ class RidgeCVEngine:
             YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
             Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
             del YoT
+        self._prepare_lbo(X, outer, inners, cfg)
         corr_sum = ops.empty(n_alphas, Y.cols)
         metric = 0 if cfg.use_corr else 1
         for i, d in enumerate(inners):
@@ -369,7 +415,7 @@ class RidgeCVEngine:
             ops.corr_finalize(parts, rows_pad // ops.PART_N, n_alphas, Y.cols, n_va, EPS, corr_sum,
                               accumulate=(i > 0), metric=metric, resp_std=std)
             del Zt, Lst, Yz, parts
-            d["G"] = d["XRt"] = d["XtT"] = None
+            d["G"] = d["XRt"] = d["XtT"] = d["Vt_split"] = None
         return corr_sum, Ct_o
 
     def _select_alphas(self, corr_sum, n_folds: int, alphas_dev, cfg: RidgeConfig, n_vox_total: int):
@@ -407,7 +453,9 @@ class RidgeCVEngine:
             XoT = ops.gather_rows_T_split(X, sp["train"], len(sp["train_rows"]))  # (p x n_o)
             basis = ops.gemm(XoT, ops.split(G), split_out=True)  # X_tr^T U  (p x n_o)
         else:
-            basis = ops.transpose(G, split=True)  # V (p x k): rows = features
+            basis = outer.get("V_split")
+            if basis is None:
+                basis = ops.transpose(G, split=True)  # V (p x k): rows = features
         return ops.gemm(ZS, basis, split_out=True)
 
     def _outer_fit_and_score(self, X, Y, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):

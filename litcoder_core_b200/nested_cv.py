@@ -276,6 +276,7 @@ class NestedCVModel:
             raise ValueError(f"Unknown corr_precision: {corr_precision}")
         cfg.corr_precision = corr_precision
         cfg.series_moments = os.environ.get("LIT_SERIES_MOMENTS", "1") != "0"  # development override
+        cfg.leave_block_out = os.environ.get("LIT_LEAVE_BLOCK_OUT", "1") != "0"  # development override
 
         # ---- H2D: X replicated, this rank's voxel block of Y (nested_cv.py:99-100) ----
         ops = self._get_ops()
@@ -344,7 +345,9 @@ class NestedCVModel:
         self.last_timings["host_stats_metrics_ms"] = (t_stats_end - t_s0) * 1e3
         self.last_stats = {"corr_precision": cfg.corr_precision, "launches": ops.launches, "gemm_flops": ops.gemm_flops, "rank": comm.rank,
                            "world": comm.world, "voxels_this_rank": c1 - c0,
-                           "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0)}
+                           "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0),
+                           "store_gemm_launches": getattr(ops, "store_gemms", 0),
+                           "compact_stacks": getattr(ops, "compact_stacks", 0)}
         if hasattr(ops, "corr_launches"):
             log = ops.corr_launches()
             self.last_stats["corr_launch_ms"] = [ms for ms, _ in log]

@@ -326,9 +326,27 @@ class FakeOps:
         cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
         return (len(cheb) + (3 if series else 0)) * n_rows
 
-    def solve_blocks(self, Gs, Pc, n_rows, lam_max, a2_list, series_ratio=60.0):
+    def lbo_prepare(self, Pv, Vt, lam_o, a2_min, steps=48):
+        """DeviceOps.lbo_prepare: B = X_R V, E = B diag(1/(lam_o + a2)), H = E B^T, lambda_max(H)."""
+        assert Pv.is_split and Vt.is_split
+        B = (Pv.a.astype(np.float64) @ Vt.a.astype(np.float64).T).astype(F32)
+        E = self._lbo_scaled(B, lam_o, a2_min)
+        H = (E.astype(np.float64) @ B.astype(np.float64).T).astype(F32)
+        self.lbo_prepared = getattr(self, "lbo_prepared", 0) + 1
+        return {"B": FMat(B, split=True), "E": FMat(E, split=True), "H": FMat(H, split=True), "a2": float(a2_min),
+                "hmax_dev": self.lambda_max(FMat(H))}
+
+    @staticmethod
+    def _lbo_scaled(B, lam_o, a2):
+        lam = np.asarray(lam_o, dtype=F32)
+        a = F32(np.sqrt(np.float64(a2)))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(lam[None, :] > 0, B / (lam[None, :] + a * a), F32(0)).astype(F32)
+
+    def solve_blocks(self, Gs, Pc, n_rows, lam_max, a2_list, series_ratio=60.0, lbo=None):
         """Compact per-fold solution block in the layout of DeviceOps.solve_blocks: the solutions of the small
-        alphas (exact here; Chebyshev iteration on the device) followed by P_c G^q, q = 1..3."""
+        alphas (exact here; Chebyshev iteration on the device) followed by P_c G^q, q = 1..3.  With `lbo` the small
+        alphas follow the leave-block-out identity on the outer eigendecomposition (DeviceOps._lbo_solve)."""
         assert Gs.is_split
         p = Gs.rows
         G = Gs.a.astype(np.float64)
@@ -336,7 +354,18 @@ class FakeOps:
         out = np.zeros(((len(cheb) + (3 if series else 0)) * n_rows, p), dtype=F32)
         P = Pc.a[:n_rows].astype(np.float64)
         for i, j in enumerate(cheb):
-            M = np.linalg.solve(G + float(a2_list[j]) * np.eye(p), P.T).T
+            if lbo is not None:
+                assert 0.0 <= lbo["h0"] < 1.0 and lbo["lam_top"] > 0.0
+                B = lbo["prep"]["B"].a
+                E = self._lbo_scaled(B, lbo["lam"], float(a2_list[j])).astype(np.float64)
+                H = E @ B.astype(np.float64).T
+                assert np.linalg.eigvalsh(0.5 * (H + H.T))[-1] <= 1.0 - self._lbo_lo(lbo, float(a2_list[j])) + 1e-6
+                Z = np.linalg.solve(np.eye(n_rows) - H, E)
+                M = Z @ lbo["V"].a.astype(np.float64).T
+                M = M - M.mean(0)
+                self.lbo_solved = getattr(self, "lbo_solved", 0) + 1
+            else:
+                M = np.linalg.solve(G + float(a2_list[j]) * np.eye(p), P.T).T
             out[i * n_rows:(i + 1) * n_rows] = M.astype(F32)
         Q = P
         for q in range(3 if series else 0):
@@ -344,6 +373,12 @@ class FakeOps:
             out[(len(cheb) + q) * n_rows:(len(cheb) + q + 1) * n_rows] = Q
         self.solver_calls = getattr(self, "solver_calls", 0) + 1
         return FMat(out)
+
+    @staticmethod
+    def _lbo_lo(lbo, a2):
+        """Lower end of the spectral interval the device's Chebyshev iteration assumes for I - H_a."""
+        from litcoder_core_b200.device import DeviceOps
+        return DeviceOps.lbo_bounds(lbo["h0"], lbo["prep"]["a2"], a2, lbo["lam_top"])[0]
 
     SERIES_MIN_ALPHAS = 5
 

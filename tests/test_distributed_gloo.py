@@ -39,12 +39,14 @@ def _worker(rank, world, port, single_alpha, out_dir):
     try:
         X, Y = _problem()
         random.seed(11)
-        model = NestedCVModel("ridge_regression", ops=FakeOps(), comm=TorchDistComm())
+        ops = FakeOps()
+        model = NestedCVModel("ridge_regression", ops=ops, comm=TorchDistComm())
         m, w, a = model.fit_predict(X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10,
                                     alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
         assert model.last_stats["world"] == world and model.last_stats["voxels_this_rank"] in (256, 44)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
-                 p=np.asarray(m["p_values"]), sig=np.asarray(m["significant_mask"]), n_sig=m["n_significant"])
+                 p=np.asarray(m["p_values"]), sig=np.asarray(m["significant_mask"]), n_sig=m["n_significant"],
+                 lbo_solved=getattr(ops, "lbo_solved", 0), solver_calls=getattr(ops, "solver_calls", 0))
     finally:
         dist.destroy_process_group()
 
@@ -62,8 +64,12 @@ def test_two_ranks_match_single_process(tmp_path, single_alpha):
     m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(
         X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
     mp.spawn(_worker, args=(2, _free_port(), single_alpha, str(tmp_path)), nprocs=2, join=True)
+    # the 9 inner folds are leave-block-out folds, each solved once, by its owner (2 small alphas each)
+    per_rank = [np.load(tmp_path / f"rank{rank}.npz") for rank in range(2)]
+    assert sum(int(g["solver_calls"]) for g in per_rank) == 9 and all(int(g["solver_calls"]) >= 3 for g in per_rank)
+    assert sum(int(g["lbo_solved"]) for g in per_rank) == 18
     for rank in range(2):
-        g = np.load(tmp_path / f"rank{rank}.npz")
+        g = per_rank[rank]
         np.testing.assert_array_equal(g["a"], a)
         np.testing.assert_allclose(g["r"], np.asarray(m["correlations"]), atol=1e-6)
         np.testing.assert_allclose(g["w"], w, atol=1e-6 * np.abs(w).max())

@@ -784,6 +784,84 @@ def test_series_moments_agree_on_fit(ops, monkeypatch):
     assert np.abs(out["1", "f16x3"][0][same] - np.asarray(mo["correlations"], dtype=np.float64)[same]).max() < 1e-4
 
 
+def test_leave_block_out_solver_kernels(ops):
+    """Small-alpha rows of the solution block through the leave-block-out identity (lbo_prepare + the |R| x |R|
+    Chebyshev solves on the outer eigendecomposition) against fp64 LAPACK and against the direct p x p route;
+    the Lanczos-based spectral bounds must contain the true spectrum of I - H_a."""
+    from litcoder_core_b200.device import DeviceOps
+
+    rng = np.random.default_rng(41)
+    n, p, m = 3000, 512, 333
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    for t in range(1, n):
+        X[t] = 0.6 * X[t - 1] + 0.8 * X[t]
+    for j in range(1, p):
+        X[:, j] = 0.5 * X[:, j - 1] + 0.87 * X[:, j]
+    X[:, 7] = 0.0  # a numerically null direction of both Grams
+    R = np.arange(1100, 1100 + m)
+    keep = np.ones(n, dtype=bool)
+    keep[R] = False
+    X64 = X.astype(np.float64)
+    G_o, G_in = X64.T @ X64, X64[keep].T @ X64[keep]
+    lmax = float(np.linalg.eigvalsh(G_in)[-1])
+    alphas = np.logspace(-1, 8, 20)
+    a2 = [float(a) ** 2 * lmax for a in alphas]
+    cheb, series = ops.solver_partition(lmax, a2)
+    Pc = (X[R] - X[R].mean(0)).astype(np.float32)
+    Pd = ops.upload_matrix(Pc)
+    Gs = _split(ops, G_in.astype(np.float32))
+    # outer eigendecomposition on the device, as the engine has it
+    Gd = ops.upload_matrix(G_o.astype(np.float32))
+    lam = ops.syevd(Gd)
+    Vt_s = ops.split(Gd)
+    prep = ops.lbo_prepare(_split(ops, X[R]), Vt_s, lam, a2[cheb[0]])
+    h0 = float(prep["hmax_dev"].cpu()[0])
+    lam_top = float(lam.cpu()[p - 1])
+    assert abs(lam_top - np.linalg.eigvalsh(G_o)[-1]) < 1e-5 * lam_top
+    lbo = {"prep": prep, "V": ops.transpose(Gd, split=True), "lam": lam, "lam_top": lam_top, "h0": h0}
+    got = ops.download_matrix(ops.solve_blocks(Gs, Pd, m, lmax, a2, lbo=lbo)).astype(np.float64)
+    direct = ops.download_matrix(ops.solve_blocks(Gs, Pd, m, lmax, a2)).astype(np.float64)
+    assert got.shape == ((len(cheb) + 3) * m, p)
+    np.testing.assert_array_equal(got[len(cheb) * m:], direct[len(cheb) * m:])  # Neumann powers: same code
+    lam_o, V = np.linalg.eigh(G_o)
+    for i, j in enumerate(cheb):
+        exact = np.linalg.solve(G_in + a2[j] * np.eye(p), Pc.astype(np.float64).T).T
+        scale = np.abs(exact).max()
+        assert np.abs(got[i * m:(i + 1) * m] - exact).max() < 1e-5 * scale, (j, alphas[j])
+        assert np.abs(direct[i * m:(i + 1) * m] - exact).max() < 1e-5 * scale
+        B = X64[R] @ V
+        H = (B / (lam_o + a2[j])) @ B.T
+        lo, hi = DeviceOps.lbo_bounds(h0, a2[cheb[0]], a2[j], lam_top)
+        ev = np.linalg.eigvalsh(np.eye(m) - 0.5 * (H + H.T))
+        assert lo <= ev[0] and ev[-1] <= hi + 1e-9, (lo, ev[0], ev[-1])
+        assert len(DeviceOps.chebyshev_plan_interval(lo, hi)) <= 24
+
+
+def test_leave_block_out_agrees_on_fit(ops, monkeypatch):
+    """Whole fit with the small alphas solved through the leave-block-out identity and through Chebyshev iteration
+    on the p x p Gram: same alphas (up to near-ties), same r, both at the oracle."""
+    from litcoder_core_b200 import NestedCVModel
+
+    rng = np.random.default_rng(29)
+    X, Y = _synthetic(rng, 800, 160, 900)
+    kw = dict(n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 8, 20))
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LIT_LEAVE_BLOCK_OUT", flag)
+        random.seed(5)
+        m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, inner_solver="chebyshev", **kw)
+        out[flag] = (np.asarray(m["correlations"]), w, np.asarray(a))
+    same = out["0"][2] == out["1"][2]
+    assert same.mean() > 0.97, same.mean()
+    assert np.abs(out["0"][0][same] - out["1"][0][same]).max() < 2e-5
+    random.seed(5)
+    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
+    same = np.isclose(out["1"][2], ao)
+    assert same.mean() > 0.9, same.mean()
+    assert np.abs(out["1"][0][same] - np.asarray(mo["correlations"], dtype=np.float64)[same]).max() < 1e-4
+    assert np.abs(out["1"][1][:, same] - wo[:, same]).max() < 1e-4 * np.abs(wo).max()
+
+
 def test_structure_kernels_match_reference_trainer(ops):
     """lit_fir_zscore_rows + the response-side z-scoring against the unmodified trainer's outputs
     (tests/golden/structure.npz), then the resident outputs straight into fit_predict."""

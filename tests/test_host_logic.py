@@ -396,6 +396,45 @@ def test_series_moments_match_full_stack_on_fake_ops(monkeypatch):
         np.testing.assert_allclose(out["0", prec][0][same], out["1", prec][0][same], atol=1e-5)
 
 
+def test_leave_block_out_matches_chebyshev_route_on_fake_ops(monkeypatch):
+    """GEMM-only folds whose validation rows are the rows removed from the outer training set: the small alphas
+    solved through the leave-block-out identity on the outer eigendecomposition give the scores of the direct
+    p x p solves; folds that are not leave-block-out folds (timeseries layout) keep the direct route."""
+    g = load_golden("fit_predict.npz")
+    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    kw = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LIT_LEAVE_BLOCK_OUT", flag)
+        ops = FakeOps()
+        random.seed(7)
+        m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X[:400], Y[:400], inner_solver="chebyshev", **kw)
+        out[flag] = (np.asarray(m["correlations"]), w, np.asarray(a))
+        n_small = 3  # alphas below sqrt(60): solved, not served by the Neumann series
+        assert getattr(ops, "lbo_solved", 0) == (12 * n_small if flag == "1" else 0)
+        assert getattr(ops, "lbo_prepared", 0) == (12 if flag == "1" else 0)
+        assert ops.eig_calls == 4 and ops.solver_calls == 12
+    same = out["0"][2] == out["1"][2]
+    assert same.mean() > 0.97
+    np.testing.assert_allclose(out["0"][0][same], out["1"][0][same], atol=1e-5)
+    ref_va, ref_r = g["cv_default__best_alphas"], g["cv_default__m__correlations"]
+    same = np.isclose(out["1"][2], ref_va, rtol=1e-6)
+    assert same.mean() >= 0.9
+    assert np.abs(out["1"][0][same] - ref_r[same]).max() < 3e-5
+    # a fold whose validation rows are only PART of the rows removed from the outer training set is downdated but
+    # keeps the direct solve; validating on all of them makes it a leave-block-out fold
+    from fake_ops import FMat
+    from litcoder_core_b200 import engine as E
+    from litcoder_core_b200.engine import FoldPlan, RidgeCVEngine
+
+    tr_o, te = np.arange(300), np.arange(300, 400)
+    for val, n_lbo in ((np.arange(250, 300), 0), (np.arange(200, 300), 3)):
+        ops = FakeOps()
+        cfg = E.RidgeConfig(alphas=alphas, inner_solver="chebyshev", n_outer_folds=1)
+        RidgeCVEngine(ops).fit_shard(FMat(X[:400]), FMat(Y[:400]), [FoldPlan(tr_o, te, [(np.arange(200), val)])], cfg)
+        assert getattr(ops, "lbo_solved", 0) == n_lbo and ops.solver_calls == 1
+
+
 def _structure_golden():
     g = load_golden("structure.npz")
     stories = [str(x) for x in g["stories"]]
