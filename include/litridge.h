@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LITRIDGE_ABI_VERSION 3
+#define LITRIDGE_ABI_VERSION 4
 
 const char* lit_last_error(void);
 int lit_abi_version(void);
@@ -82,6 +82,13 @@ int lit_gemm_tf32x3_nt_corr(const float* A_hi, const float* A_lo, long lda, cons
 int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
                            int M, int n_groups, int rows_per_group, int K, const float* Yz, long ldy, float* dot_part,
                            float* ssq_part, long ld_part, int variant, void* stream);
+/* D = alpha * A B^T + beta * Cin with the operands as fp16 split pairs (lit_split_f16 with rows_per_group = 1 for
+ * both): inv_a[M] / inv_b[N, readable up to the next multiple of 4] are the inverse operand scales the epilogue
+ * multiplies back in (NULL = ones).  Same output options as lit_gemm_tf32x3_nt; variants 1CTA_N256 / 2CTA_N256.
+ * lda / ldb in fp16 elements (multiples of 8). */
+int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb, int M,
+                      int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D, float* D_lo, long ldd,
+                      const float* inv_a, const float* inv_b, int variant, void* stream);
 /* The fused GEMM over a stack whose last n_series_tiles tiles (256 rows each) are SERIES tiles written by
  * lit_series_stack: 64 time points x the 4 terms Q_q of the Neumann series of (G + a^2 I)^-1.  For those tiles the
  * epilogue emits, per part of 32 time points and voxel, 14 sums into series_part[part*14 + j][ld_part]:
@@ -220,6 +227,11 @@ int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_v
  * Replaces S[0] = largest singular value used by normalpha (ridge_regression.py:39,97). */
 int lit_lanczos_lambda_max(const float* G, long ld, int n, int steps, float* vec_scratch, double* scal_scratch,
                            float* lam_out_f32, double* lam_out_f64, void* stream);
+/* The same for `batch` matrices of one size at once (one launch per Lanczos step for all of them): G is a HOST
+ * array of device pointers (all n x n, pitch ld); vec_scratch: batch * 3*n floats; scal_scratch:
+ * batch * (2*steps + 4) doubles; lam_out_f64: batch doubles.  steps <= n. */
+int lit_lanczos_lambda_max_batched(const float* const* G, int batch, long ld, int n, int steps, float* vec_scratch,
+                                   double* scal_scratch, double* lam_out_f64, void* stream);
 /* One Chebyshev step on (rows x cols) row-matrices of pitch ld:
  *   d = c1*d + c2*r (also written as the split pair d_hi/d_lo),  x += d,  t = r - a2*d;
  * `first` != 0 treats d and x as zero on input.  The caller then forms r = t - d G with lit_gemm_tf32x3_nt. */

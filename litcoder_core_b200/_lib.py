@@ -11,7 +11,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblitridge.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _l, _i, _f, _d, _sz = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_double, C.c_size_t
 _psz, _pi = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
@@ -25,6 +25,7 @@ PROTOTYPES = {
     "lit_gemm_tf32x3_nt": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _f, _vp, _l, _f, _vp, _vp, _l, _i, _vp],
     "lit_gemm_tf32x3_nt_corr": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _vp, _l, _vp, _vp, _l, _i, _vp],
     "lit_gemm_f16x3_nt_corr": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _vp, _l, _vp, _vp, _l, _i, _vp],
+    "lit_gemm_f16x3_nt": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _f, _vp, _l, _f, _vp, _vp, _l, _vp, _vp, _i, _vp],
     "lit_gemm_corr_series": [_i, _vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp, _l, _i, _vp],
     "lit_split_f16": [_vp, _vp, _l, _l, _l, _l, _vp, _vp, _l, _vp, _vp, _vp],
     "lit_convert_f64_to_f32": [_vp, _vp, _sz, _vp],
@@ -54,6 +55,7 @@ PROTOTYPES = {
     "lit_fir_zscore_rows": [_vp, _i, _l, _l, _l, _vp, _i, _i, _l, _l, _i, _vp, _l, _vp],
     "lit_lanczos_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _d, _d, _i, _vp, _vp, _vp, _l, _vp],
     "lit_lanczos_lambda_max": [_vp, _l, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "lit_lanczos_lambda_max_batched": [_vp, _i, _l, _i, _i, _vp, _vp, _vp, _vp],
     "lit_cheb_update": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _l, _f, _f, _f, _i, _vp],
     "lit_poly_combine": [_vp, _vp, _i, _l, _l, _l, _l, _vp, _vp, _i, _vp, _vp, _l, _vp],
     "lit_series_stack": [_vp, _vp, _l, _l, _l, _vp, _l, _vp, _vp, _l, _vp],

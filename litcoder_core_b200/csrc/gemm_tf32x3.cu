@@ -61,6 +61,10 @@ struct GemmParams {
   const float* Cin;
   long ldc;
   float alpha, beta;
+  // EPI_STORE on fp16 split pairs: power-of-two operand scales to undo, D = alpha * scale_m[row] * scale_n[col] * acc
+  // (either may be NULL = ones; lit_split_f16 writes them as inv_scale)
+  const float* scale_m;
+  const float* scale_n;
   // EPI_CORR
   const float* Yz;  // [parts_per_group*BN/2 rows][>= M cols], row pitch ldy
   long ldy;
@@ -298,20 +302,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
           float* drow = p.D + row * p.ldd + n_base;
           float* lrow = p.D_lo ? p.D_lo + row * p.ldd + n_base : nullptr;
           const float* crow = p.Cin ? p.Cin + row * p.ldc + n_base : nullptr;
+          const float* srow = p.scale_n ? p.scale_n + n_base : nullptr;
+          const float am = p.scale_m ? p.alpha * __ldg(p.scale_m + row) : p.alpha;
 #pragma unroll
           for (int j = 0; j < COLS; j += 4) {
             if (n_base + j >= p.N) break;
             float o[4];
             if (n_base + j + 3 < p.N) {
+              float a4[4] = {am, am, am, am};
+              if (srow) {  // the scale vector is padded to a multiple of 4 entries by its producer
+                const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + j));
+                a4[0] *= sv.x, a4[1] *= sv.y, a4[2] *= sv.z, a4[3] *= sv.w;
+              }
               if (crow) {
                 const float4 cv = *reinterpret_cast<const float4*>(crow + j);
-                o[0] = p.alpha * acc[j] + p.beta * cv.x;
-                o[1] = p.alpha * acc[j + 1] + p.beta * cv.y;
-                o[2] = p.alpha * acc[j + 2] + p.beta * cv.z;
-                o[3] = p.alpha * acc[j + 3] + p.beta * cv.w;
+                o[0] = a4[0] * acc[j] + p.beta * cv.x;
+                o[1] = a4[1] * acc[j + 1] + p.beta * cv.y;
+                o[2] = a4[2] * acc[j + 2] + p.beta * cv.z;
+                o[3] = a4[3] * acc[j + 3] + p.beta * cv.w;
               } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) o[q] = p.alpha * acc[j + q];
+                for (int q = 0; q < 4; ++q) o[q] = a4[q] * acc[j + q];
               }
               if (lrow) {
                 float h[4], l[4];
@@ -329,7 +340,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 if (n_base + j + q < p.N) {
-                  float x = p.alpha * acc[j + q];
+                  float x = (srow ? am * __ldg(srow + j + q) : am) * acc[j + q];
                   if (crow) x += p.beta * crow[j + q];
                   if (lrow) {
                     const float h = ptx::to_tf32(x);
@@ -572,6 +583,46 @@ extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda
       return launch_gemm<256, 2, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
     default:
       set_error("unknown GEMM variant %d", variant);
+      return LIT_ERR_INVALID;
+  }
+}
+
+// D = alpha * A B^T + beta * Cin on fp16 split pairs (lit_split_f16; one scale per row of A and per row of B, whose
+// inverses inv_a / inv_b the epilogue multiplies back in): three kind::f16 MMAs per k-step, twice the rate of the
+// 3xTF32 form at the same product accuracy.
+extern "C" int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+                                 int M, int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D,
+                                 float* D_lo, long ldd, const float* inv_a, const float* inv_b, int variant,
+                                 void* stream) {
+  LIT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative GEMM extent");
+  LIT_REQUIRE(ldd % 4 == 0 && ldd >= N, "output pitch must be a multiple of 4 floats and >= N");
+  LIT_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "output must be 16-byte aligned");
+  LIT_REQUIRE(!Cin || (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0), "Cin alignment");
+  LIT_REQUIRE(!D_lo || (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0, "D_lo alignment");
+  LIT_REQUIRE(!inv_b || (reinterpret_cast<uintptr_t>(inv_b) & 15) == 0, "inv_b must be 16-byte aligned");
+  if (M == 0 || N == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.D = D;
+  p.D_lo = D_lo;
+  p.ldd = ldd;
+  p.Cin = Cin;
+  p.ldc = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.scale_m = inv_a;
+  p.scale_n = inv_b;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
+  switch (variant) {
+    case LIT_GEMM_1CTA_N256:
+      return launch_gemm<256, 1, EPI_STORE, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    case LIT_GEMM_2CTA_N256:
+      return launch_gemm<256, 2, EPI_STORE, 1>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s);
+    default:
+      set_error("unknown f16x3 GEMM variant %d", variant);
       return LIT_ERR_INVALID;
   }
 }

@@ -19,16 +19,28 @@ namespace lit {
 
 __host__ __device__ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Batched Lanczos: blockIdx.y is the matrix index b.  Matrix b is Gs.p[b] (all n x n, pitch ld); its work vectors
+// live at vec + b * 3n (three n-vectors whose roles rotate: offsets o_v / o_prev / o_y in units of n) and its
+// scalars at scal + b * scal_stride: [dot, -, alpha[steps], beta[steps + 1]].
+constexpr int LANCZOS_MAX_BATCH = 32;
+struct MatPtrs {
+  const float* p[LANCZOS_MAX_BATCH];
+};
+
 // y = G v (G symmetric, row-major, n x n), and dot += v . y.  One warp per row.
-__global__ void sym_gemv_dot_kernel(const float* __restrict__ G, long ld, int n, const float* __restrict__ v,
-                                    float* __restrict__ y, double* __restrict__ dot) {
+__global__ void sym_gemv_dot_kernel(MatPtrs Gs, long ld, int n, float* __restrict__ vec, int o_v, int o_y,
+                                    double* __restrict__ scal, long scal_stride) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
+  const float* __restrict__ G = Gs.p[blockIdx.y];
+  const float* __restrict__ v = vec + ((long)blockIdx.y * 3 + o_v) * n;
+  float* __restrict__ y = vec + ((long)blockIdx.y * 3 + o_y) * n;
+  double* dot = scal + (long)blockIdx.y * scal_stride;
   const float* row = G + (long)warp * ld;
   double acc = 0.0;
-  const bool vec = (ld % 4 == 0) && aligned16(G) && aligned16(v);
-  if (vec) {
+  const bool vec4 = (ld % 4 == 0) && aligned16(G) && aligned16(v);
+  if (vec4) {
     const int n4 = n >> 2;
     for (int j = lane; j < n4; j += 32) {
       const float4 g = *reinterpret_cast<const float4*>(row + 4 * j);
@@ -59,10 +71,15 @@ __device__ __forceinline__ double block_sum(double x, double* sh) {
   return t;
 }
 
-// Deterministic start vector (unit norm).  Single block.
-__global__ void lanczos_init_kernel(float* __restrict__ v, float* __restrict__ v_prev, int n, double* __restrict__ dot,
-                                    double* __restrict__ alpha, double* __restrict__ beta, int steps) {
+// Deterministic start vector (unit norm).  One block per matrix.
+__global__ void lanczos_init_kernel(float* __restrict__ vec, int n, double* __restrict__ scal, long scal_stride,
+                                    int steps) {
   __shared__ double sh[32];
+  float* __restrict__ v = vec + (long)blockIdx.x * 3 * n;
+  float* __restrict__ v_prev = v + n;
+  double* dot = scal + (long)blockIdx.x * scal_stride;
+  double* alpha = dot + 2;
+  double* beta = alpha + steps;
   double part = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     uint32_t h = (uint32_t)i * 2654435761u + 12345u;
@@ -85,11 +102,16 @@ __global__ void lanczos_init_kernel(float* __restrict__ v, float* __restrict__ v
 
 // One three-term Lanczos step after y = G v_j and dot = v_j . y have been formed:
 //   alpha_j = dot;  w = y - alpha_j v_j - beta_j v_{j-1};  beta_{j+1} = ||w||;  v_{j+1} = w / beta_{j+1}
-// v_next may alias v_prev (it is read before it is written by the same thread).  Single block.
-__global__ void lanczos_step_kernel(const float* __restrict__ y, const float* __restrict__ v, float* v_prev_next, int n,
-                                    int j, double* __restrict__ dot, double* __restrict__ alpha,
-                                    double* __restrict__ beta) {
+// v_next overwrites v_prev (it is read before it is written by the same thread).  One block per matrix.
+__global__ void lanczos_step_kernel(float* __restrict__ vec, int o_y, int o_v, int o_prev, int n, int j, int steps,
+                                    double* __restrict__ scal, long scal_stride) {
   __shared__ double sh[32];
+  const float* __restrict__ y = vec + ((long)blockIdx.x * 3 + o_y) * n;
+  const float* __restrict__ v = vec + ((long)blockIdx.x * 3 + o_v) * n;
+  float* v_prev_next = vec + ((long)blockIdx.x * 3 + o_prev) * n;
+  double* dot = scal + (long)blockIdx.x * scal_stride;
+  double* alpha = dot + 2;
+  double* beta = alpha + steps;
   const double a = *dot;
   const double b = beta[j];
   double part = 0.0;
@@ -113,10 +135,14 @@ __global__ void lanczos_step_kernel(const float* __restrict__ y, const float* __
 
 // Largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[1..m)) by Sturm multisection (fp64):
 // one warp evaluates 32 trial points per round (5 bits per round instead of 1).
-__global__ void tridiag_lmax_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int m,
+__global__ void tridiag_lmax_kernel(const double* __restrict__ scal, long scal_stride, int m,
                                     float* __restrict__ out_f32, double* __restrict__ out_f64) {
-  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
+  const double* __restrict__ alpha = scal + (long)blockIdx.x * scal_stride + 2;
+  const double* __restrict__ beta = alpha + m;
+  if (out_f32) out_f32 += blockIdx.x;
+  if (out_f64) out_f64 += blockIdx.x;
   // an (almost) invariant subspace ends the recurrence early: keep the leading block
   double scale = 0.0;
   for (int i = 0; i < m; ++i) scale = fmax(scale, fabs(alpha[i]));
@@ -302,34 +328,57 @@ __global__ void series_stack_kernel(PolySources src, long ld_src, long rows, lon
 
 using namespace lit;
 
+static int lanczos_batch(const float* const* G, int batch, long ld, int n, int steps, float* vec_scratch,
+                         double* scal_scratch, float* lam_out_f32, double* lam_out_f64, cudaStream_t s) {
+  const long scal_stride = 2L * steps + 4;
+  for (int b0 = 0; b0 < batch; b0 += LANCZOS_MAX_BATCH) {
+    const int nb = batch - b0 < LANCZOS_MAX_BATCH ? batch - b0 : LANCZOS_MAX_BATCH;
+    MatPtrs ptrs = {};
+    for (int b = 0; b < nb; ++b) {
+      LIT_REQUIRE(G[b0 + b], "lanczos_lambda_max: null matrix");
+      ptrs.p[b] = G[b0 + b];
+    }
+    float* vec = vec_scratch + (long)b0 * 3 * n;
+    double* scal = scal_scratch + (long)b0 * scal_stride;
+    lanczos_init_kernel<<<nb, 1024, 0, s>>>(vec, n, scal, scal_stride, steps);
+    LIT_LAUNCH_CHECK();
+    const int rows_per_block = 8;
+    const int gblocks = (n + rows_per_block - 1) / rows_per_block;
+    int o_v = 0, o_prev = 1;  // roles of the three work vectors (offset 2 holds y)
+    for (int j = 0; j < steps; ++j) {
+      sym_gemv_dot_kernel<<<dim3(gblocks, nb), rows_per_block * 32, 0, s>>>(ptrs, ld, n, vec, o_v, 2, scal, scal_stride);
+      lanczos_step_kernel<<<nb, 1024, 0, s>>>(vec, 2, o_v, o_prev, n, j, steps, scal, scal_stride);
+      const int tmp = o_v;  // v_{j+1} was written over v_{j-1}
+      o_v = o_prev;
+      o_prev = tmp;
+    }
+    LIT_LAUNCH_CHECK();
+    tridiag_lmax_kernel<<<nb, 32, 0, s>>>(scal, scal_stride, steps, lam_out_f32 ? lam_out_f32 + b0 : nullptr,
+                                          lam_out_f64 ? lam_out_f64 + b0 : nullptr);
+    LIT_LAUNCH_CHECK();
+  }
+  return LIT_OK;
+}
+
 extern "C" int lit_lanczos_lambda_max(const float* G, long ld, int n, int steps, float* vec_scratch /* 3*n floats */,
                                       double* scal_scratch /* 2*steps + 4 doubles */, float* lam_out_f32,
                                       double* lam_out_f64, void* stream) {
   LIT_REQUIRE(n > 0 && ld >= n && steps > 0, "lanczos_lambda_max: bad extents");
   LIT_REQUIRE(vec_scratch && scal_scratch, "lanczos_lambda_max: scratch required");
   if (steps > n) steps = n;
-  cudaStream_t s = (cudaStream_t)stream;
-  float* va = vec_scratch;
-  float* vb = vec_scratch + n;
-  float* y = vec_scratch + 2L * n;
-  double* dot = scal_scratch;
-  double* alpha = scal_scratch + 2;
-  double* beta = alpha + steps;  // steps + 1 entries
-  lanczos_init_kernel<<<1, 1024, 0, s>>>(va, vb, n, dot, alpha, beta, steps);
-  LIT_LAUNCH_CHECK();
-  const int rows_per_block = 8;
-  const int gblocks = (n + rows_per_block - 1) / rows_per_block;
-  for (int j = 0; j < steps; ++j) {
-    sym_gemv_dot_kernel<<<gblocks, rows_per_block * 32, 0, s>>>(G, ld, n, va, y, dot);
-    lanczos_step_kernel<<<1, 1024, 0, s>>>(y, va, vb, n, j, dot, alpha, beta);
-    float* tmp = va;  // v_{j+1} was written over v_{j-1}
-    va = vb;
-    vb = tmp;
-  }
-  LIT_LAUNCH_CHECK();
-  tridiag_lmax_kernel<<<1, 32, 0, s>>>(alpha, beta, steps, lam_out_f32, lam_out_f64);
-  LIT_LAUNCH_CHECK();
-  return LIT_OK;
+  return lanczos_batch(&G, 1, ld, n, steps, vec_scratch, scal_scratch, lam_out_f32, lam_out_f64, (cudaStream_t)stream);
+}
+
+extern "C" int lit_lanczos_lambda_max_batched(const float* const* G /* host array of `batch` device pointers */,
+                                              int batch, long ld, int n, int steps,
+                                              float* vec_scratch /* batch * 3*n floats */,
+                                              double* scal_scratch /* batch * (2*steps + 4) doubles */,
+                                              double* lam_out_f64 /* batch */, void* stream) {
+  LIT_REQUIRE(batch >= 0 && n > 0 && ld >= n && steps > 0, "lanczos_lambda_max_batched: bad extents");
+  LIT_REQUIRE(steps <= n, "lanczos_lambda_max_batched: steps must not exceed n (the scratch layout depends on it)");
+  LIT_REQUIRE(batch == 0 || (G && vec_scratch && scal_scratch && lam_out_f64), "lanczos_lambda_max_batched: null argument");
+  if (batch == 0) return LIT_OK;
+  return lanczos_batch(G, batch, ld, n, steps, vec_scratch, scal_scratch, nullptr, lam_out_f64, (cudaStream_t)stream);
 }
 
 extern "C" int lit_cheb_update(float* d, const float* r, float* x, float* t, float* d_hi, float* d_lo, long ld, long rows,

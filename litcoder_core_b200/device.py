@@ -460,8 +460,14 @@ class DeviceOps:
             self.set_gemm_sm_limit(want)
 
     def gemm(self, A: Mat, B: Mat, alpha: float = 1.0, Cin: Optional[Mat] = None, beta: float = 0.0,
-             split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None) -> Mat:
-        """out[M,N] = alpha * A[M,K] @ B[N,K]^T + beta * Cin (A, B split pairs)."""
+             split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None,
+             precision: str = "tf32x3") -> Mat:
+        """out[M,N] = alpha * A[M,K] @ B[N,K]^T + beta * Cin (A, B split pairs).
+        precision "f16x3": the operands are re-split into scaled fp16 pairs (one power-of-two scale per row of A
+        and of B, lit_split_f16) and multiplied by lit_gemm_f16x3_nt, whose epilogue undoes the scales: the same
+        product accuracy at twice the tensor-core rate; pays for the large voxel-side products."""
+        if precision not in ("tf32x3", "f16x3"):
+            raise ValueError(f"gemm: unknown precision {precision!r}")
         if not (A.is_split and B.is_split):
             raise ValueError("GEMM operands must be 3xTF32 split pairs")
         if A.cols != B.cols:
@@ -469,9 +475,21 @@ class DeviceOps:
         M, N, K = A.rows, B.rows, A.cols
         if out is None:
             out = self.empty(M, N, split=split_out, ld=ld_out)
+        if precision == "f16x3" and M and N:
+            A, B = self.split_f16(A, 1), self.split_f16(B, 1)
         self._apply_sm_limit()
         with self.timed("gemm"):
-            self._gemm_call(A, B, M, N, K, alpha, Cin, beta, out)
+            if isinstance(A, MatF16):
+                variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256,
+                                                                     _lib.GEMM_2CTA_N256) else _lib.GEMM_AUTO
+                check(self.lib.lit_gemm_f16x3_nt(
+                    _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld,
+                    M, N, K, alpha, _vp(Cin.hi.data_ptr() if Cin is not None else 0), Cin.ld if Cin is not None else 0,
+                    beta, _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr() if out.is_split else 0), out.ld,
+                    _vp(A.inv_scale.data_ptr()), _vp(B.inv_scale.data_ptr()), variant, _vp(self.stream)),
+                    "gemm_f16x3_nt")
+            else:
+                self._gemm_call(A, B, M, N, K, alpha, Cin, beta, out)
         self.launches += 1
         self.store_gemms += 1
         self.gemm_flops += 2.0 * M * N * K
@@ -638,6 +656,26 @@ class DeviceOps:
         self.launches += 2 * steps + 2
         return out
 
+    def lambda_max_batched(self, mats, steps: int = 96):
+        """lambda_max of several symmetric matrices of ONE size and pitch in lock step (one launch per Lanczos step
+        for all of them; lit_lanczos_lambda_max_batched).  Returns a device f64 vector with one value per matrix."""
+        if not mats:
+            return self.vec(0, "f64")
+        n, ld = mats[0].rows, mats[0].ld
+        if any(m.rows != n or m.cols != n or m.ld != ld for m in mats):
+            raise ValueError("lambda_max_batched: the matrices must share one size and pitch")
+        steps = min(steps, n)
+        nb = len(mats)
+        vec_scratch = self.vec(nb * 3 * n)
+        scal_scratch = self.vec(nb * (2 * steps + 4), "f64")
+        out = self.vec(nb, "f64")
+        ptrs = (C.c_void_p * nb)(*[m.hi.data_ptr() for m in mats])
+        check(self.lib.lit_lanczos_lambda_max_batched(C.cast(ptrs, _vp), nb, ld, n, steps, _vp(vec_scratch.data_ptr()),
+                                                      _vp(scal_scratch.data_ptr()), _vp(out.data_ptr()),
+                                                      _vp(self.stream)), "lanczos_lambda_max_batched")
+        self.launches += (2 * steps + 2) * -(-nb // 32)
+        return out
+
     @staticmethod
     def chebyshev_plan_interval(lo: float, hi: float, tol: float = 1e-6):
         """Scalar schedule of the Chebyshev iteration for a symmetric operator with spectrum in [lo, hi], lo > 0:
@@ -677,19 +715,20 @@ class DeviceOps:
     def _view_rows(self, m: Mat, r0: int, rows: int) -> Mat:
         return Mat(m.hi[r0:r0 + rows], m.lo[r0:r0 + rows] if m.lo is not None else None, rows, m.cols, ld=m.ld)
 
-    def lbo_prepare(self, Pv: Mat, Vt: Mat, lam_o, a2_min: float, steps: int = 48) -> dict:
+    def lbo_prepare(self, Pv: Mat, Vt: Mat, lam_o, a2_min: float, steps: int = 48, lanczos: bool = True) -> dict:
         """Leave-block-out form of an inner fold whose validation rows R are exactly the rows removed from the
         outer training set (G_in = G_o - X_R^T X_R) once the outer Gram's eigendecomposition G_o = V diag(lam_o) V^T
         is known:
             X_R (G_in + a^2 I)^-1 = (I - H_a)^-1 X_R M_a,   M_a = V diag(1/(lam_o + a^2)) V^T,  H_a = X_R M_a X_R^T
         (Woodbury on the downdate), i.e. an |R| x |R| system with spectrum in (0, 1] instead of a p x p one with
         condition number (lam_max + a^2)/a^2.  Queues B = X_R V (|R| x k), E = B diag(1/(lam_o + a2_min)),
-        H = E B^T for the smallest alpha and the Lanczos estimate of lambda_max(H); nothing is read back here.
+        H = E B^T for the smallest alpha and (unless the caller batches it: lanczos=False) the Lanczos estimate of
+        lambda_max(H); nothing is read back here.
         Pv: split pair of X_R (|R| x p); Vt: split pair of the eigenvectors as rows (k x p)."""
         B = self.gemm(Pv, Vt, split_out=True)
         E = self._lbo_scaled(B, lam_o, a2_min)
         H = self.gemm(E, B, split_out=True)
-        return {"B": B, "E": E, "H": H, "a2": float(a2_min), "hmax_dev": self.lambda_max(H, steps)}
+        return {"B": B, "E": E, "H": H, "a2": float(a2_min), "hmax_dev": self.lambda_max(H, steps) if lanczos else None}
 
     def _lbo_scaled(self, B: Mat, lam_o, a2: float) -> Mat:
         """B diag(1 / (lam_o + a2)) as a split pair (columns of non-positive eigenvalues -- numerically null
@@ -703,9 +742,11 @@ class DeviceOps:
     @staticmethod
     def lbo_bounds(h0: float, a2_0: float, a2: float, lam_top: float):
         """Spectral interval [lo, 1] of I - H_a from the Lanczos estimate h0 of lambda_max(H_a0) at the smallest
-        alpha: H_a <= H_a0 (lam_top + a2_0)/(lam_top + a2) for a2 >= a2_0 (the ratio of the two diagonal scalings is
-        largest at the top eigenvalue), and I - H_a >= a2/(a2 + lam_top) always (G_R <= G_o)."""
-        hi_h = (1.06 * h0 + 0.01) * (1.001 * lam_top + a2_0) / (1.001 * lam_top + a2)
+        alpha.  A Ritz value never exceeds the eigenvalue it approaches, so 15 % of the gap 1 - h0 is given back as
+        a margin; H_a <= H_a0 (lam_top + a2_0)/(lam_top + a2) for a2 >= a2_0 (the ratio of the two diagonal scalings
+        is largest at the top eigenvalue), and I - H_a >= a2/(a2 + lam_top) always (G_R <= G_o)."""
+        hi_h0 = 1.0 - 0.85 * min(max(1.0 - h0, 0.0), 1.0)
+        hi_h = hi_h0 * (1.001 * lam_top + a2_0) / (1.001 * lam_top + a2)
         lo_rigorous = a2 / (a2 + 1.001 * lam_top)
         return max(1.0 - hi_h, lo_rigorous), 1.0
 

@@ -63,6 +63,9 @@ class RidgeConfig:
     # operand format of the fused inner-CV prediction + correlation GEMM: "tf32x3" or "f16x3" (scaled fp16 split
     # pairs, lit_split_f16: same product accuracy, twice the tensor-core rate)
     corr_precision: str = "f16x3"
+    # operand format of the other voxel-side GEMMs (cross products Y^T X and their downdates, rotations of the
+    # coefficients, weights): same choice, through lit_gemm_f16x3_nt
+    voxel_gemm_precision: str = "f16x3"
     # GEMM-only folds: the alphas served by the Neumann series (a^2 >= 60 lambda_max; 16 of the 20 BASELINE alphas)
     # share FOUR stacked row blocks P_c G^q instead of one block each; their scores are 4-term combinations of 14
     # per-voxel sums taken in the GEMM epilogue (DeviceOps.assemble_series_stack).  2.5x fewer prediction flops.
@@ -220,7 +223,7 @@ class RidgeCVEngine:
             if d.get("cheb"):
                 # GEMM-only fold: lambda_max by Lanczos now (read back once for all folds by fit_shard)
                 d["lam"], d["ticket"] = None, None
-                d["lmax_dev"] = ops.lambda_max(d["G"]) if d["owner"] == comm.rank else None
+                d["lmax_dev"] = None  # all folds' Lanczos runs advance together: see _finish_design
             elif d["owner"] != comm.rank:
                 d["lam"], d["ticket"] = ops.vec(d["G"].rows), None
             elif cfg.overlap_eig:
@@ -281,14 +284,20 @@ class RidgeCVEngine:
             if "V_split" not in outer:
                 outer["V_split"] = ops.transpose(Vt, split=True)  # V (p x k): rows = features
             Pv = ops.gather_rows(X, d["val"], len(d["val_rows"]), split=True)  # X_R (|R| x p)
-            d["lbo_args"] = {"prep": ops.lbo_prepare(Pv, Vt_s, lam, a2[cheb[0]]), "V": outer["V_split"], "lam": lam}
+            d["lbo_args"] = {"prep": ops.lbo_prepare(Pv, Vt_s, lam, a2[cheb[0]], lanczos=False), "V": outer["V_split"],
+                             "lam": lam}
             todo.append(d)
         if not todo:
             return
+        runs = [(idx, ops.lambda_max_batched([todo[i]["lbo_args"]["prep"]["H"] for i in idx], 48))
+                for idx in self._same_shape_groups([(i, d["lbo_args"]["prep"]["H"]) for i, d in enumerate(todo)])]
         lam_top = float(np.asarray(ops.download(lam)).reshape(-1)[Vt.rows - 1])
+        for idx, h_dev in runs:
+            h = np.asarray(ops.download(h_dev)).reshape(-1)
+            for k, i in enumerate(idx):
+                todo[i]["lbo_args"]["h0"] = float(h[k])
         for d in todo:
             d["lbo_args"]["lam_top"] = lam_top
-            d["lbo_args"]["h0"] = float(np.asarray(ops.download(d["lbo_args"]["prep"]["hmax_dev"])).reshape(-1)[0])
             if not (0.0 <= d["lbo_args"]["h0"] < 1.0 + 1e-3) or not (lam_top > 0.0):
                 raise FloatingPointError("leave-block-out: lambda_max(H) outside [0, 1] (degenerate design)")
         if comm.world > 1:
@@ -321,10 +330,9 @@ class RidgeCVEngine:
         if not jobs:
             return
         vals = np.zeros(len(jobs), dtype=np.float64)
-        for i, (_, d) in enumerate(jobs):
-            if d["owner"] == comm.rank:
-                vals[i] = float(ops.download(d["lmax_dev"])[0])
-                d["lmax_dev"] = None
+        for idx in self._same_shape_groups([(i, d["G"]) for i, (_, d) in enumerate(jobs) if d["owner"] == comm.rank]):
+            got = np.asarray(ops.download(ops.lambda_max_batched([jobs[i][1]["G"] for i in idx]))).reshape(-1)
+            vals[idx] = got[: len(idx)]
         if comm.world > 1:
             vals = comm.all_reduce_sum(vals)
         for (X, d), v in zip(jobs, vals):
@@ -333,6 +341,14 @@ class RidgeCVEngine:
             for X, d in jobs:
                 if d["owner"] == comm.rank and not d.get("lbo"):  # leave-block-out folds: see _prepare_lbo
                     d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
+
+    @staticmethod
+    def _same_shape_groups(items):
+        """Index lists of the (index, Mat) pairs that share one size and pitch (batched Lanczos runs)."""
+        groups = {}
+        for i, m in items:
+            groups.setdefault((m.rows, m.ld), []).append(i)
+        return list(groups.values())
 
     def _next_eig_owner(self) -> int:
         owner = self._eig_jobs % self.comm.world
@@ -359,10 +375,11 @@ class RidgeCVEngine:
         """Sum over inner folds of the (n_alphas x V_r) validation scores (ridge_corr_torch per fold).
         Also returns C_o^T (V_r x p fp32) for a primal outer fit (None when the outer fold is dual)."""
         ops = self.ops
+        vp = cfg.voxel_gemm_precision
         Ct_o = None
         if not outer["dual"]:
             YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
-            Ct_o = ops.gemm(YoT, outer["XtT"])  # (V_r x p), K = n_o
+            Ct_o = ops.gemm(YoT, outer["XtT"], precision=vp)  # (V_r x p), K = n_o
             del YoT
         self._prepare_lbo(X, outer, inners, cfg)
         corr_sum = ops.empty(n_alphas, Y.cols)
@@ -377,7 +394,7 @@ class RidgeCVEngine:
                 # dual form: Z^T = Y_tr^T U (V_r x n), L = (P X_tr^T) U (n_v x n); lam = eig(X_tr X_tr^T) = S^2
                 YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)  # (V_r x n)
                 Ut, _, lam = self._eig_ready(d)
-                Zt = ops.gemm(YtT, Ut, split_out=True)
+                Zt = ops.gemm(YtT, Ut, split_out=True, precision=vp)
                 del YtT
                 XiR = ops.gather_rows(X, d["train"], n_tr, split=True)  # (n x p)
                 Kpt = ops.gemm(Pv, XiR, split_out=True)  # (n_v x n), K = p
@@ -388,11 +405,11 @@ class RidgeCVEngine:
                 # cross product of the inner training rows (downdated from the outer fold's when possible)
                 if d["R"] is not None:
                     YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]))  # (V_r x |R|)
-                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True)
+                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True, precision=vp)
                     del YRt
                 else:
                     YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
-                    Ct = ops.gemm(YtT, d["XtT"], split_out=True)
+                    Ct = ops.gemm(YtT, d["XtT"], split_out=True, precision=vp)
                     del YtT
                 if d["cheb"]:
                     # GEMM-only fold: pred_a^T = C^T [P_c (G + a^2 I)^-1]^T, no rotation into an eigenbasis
@@ -401,7 +418,7 @@ class RidgeCVEngine:
                     L = None
                 else:
                     Vt, _, lam = self._eig_ready(d)
-                    Zt = ops.gemm(Ct, Vt, split_out=True)  # (V_r x k), K = p
+                    Zt = ops.gemm(Ct, Vt, split_out=True, precision=vp)  # (V_r x k), K = p
                     L = ops.gemm(Pv, Vt)  # P V  (n_v x k)
                     del Vt
                 del Ct
@@ -437,10 +454,10 @@ class RidgeCVEngine:
         Vt, G, lam = self._eig_ready(outer)
         if outer["dual"]:
             YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
-            Zt = ops.gemm(YoT, Vt, split_out=True)  # Y_tr^T U
+            Zt = ops.gemm(YoT, Vt, split_out=True, precision=cfg.voxel_gemm_precision)  # Y_tr^T U
             del YoT
         else:
-            Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True)  # (V_r x k)
+            Zt = ops.gemm(ops.split(Ct_o), Vt, split_out=True, precision=cfg.voxel_gemm_precision)  # (V_r x k)
         del Vt
         return ops.scale_rows_by_alpha(Zt, lam, alpha_v, cfg.normalpha, cfg.singcutoff), G
 
@@ -456,7 +473,7 @@ class RidgeCVEngine:
             basis = outer.get("V_split")
             if basis is None:
                 basis = ops.transpose(G, split=True)  # V (p x k): rows = features
-        return ops.gemm(ZS, basis, split_out=True)
+        return ops.gemm(ZS, basis, split_out=True, precision=cfg.voxel_gemm_precision)
 
     def _outer_fit_and_score(self, X, Y, Xte_src, Yte_src, sp, outer, Ct_o, alpha_v, cfg: RidgeConfig):
         """ridge_torch on the outer training set with the selected alphas, then test r / p."""

@@ -275,6 +275,7 @@ class NestedCVModel:
         if corr_precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"Unknown corr_precision: {corr_precision}")
         cfg.corr_precision = corr_precision
+        cfg.voxel_gemm_precision = os.environ.get("LIT_VOXEL_GEMM", corr_precision)  # development override
         cfg.series_moments = os.environ.get("LIT_SERIES_MOMENTS", "1") != "0"  # development override
         cfg.leave_block_out = os.environ.get("LIT_LEAVE_BLOCK_OUT", "1") != "0"  # development override
 

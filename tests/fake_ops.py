@@ -213,10 +213,14 @@ class FakeOps:
         return FMat(out, split)
 
     # ------------------------------------------------------------------ GEMMs
-    def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None):
+    def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None, precision="tf32x3"):
         assert A.is_split and B.is_split, "GEMM operands must be split pairs"
-        assert A.cols == B.cols
-        d = alpha * (A.a.astype(np.float64) @ B.a.astype(np.float64).T)
+        assert A.cols == B.cols and precision in ("tf32x3", "f16x3")
+        if precision == "f16x3":  # lit_gemm_f16x3_nt: what the scaled fp16 pairs keep of the operands
+            d = alpha * (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, 1).T)
+            self.f16_gemms = getattr(self, "f16_gemms", 0) + 1
+        else:
+            d = alpha * (A.a.astype(np.float64) @ B.a.astype(np.float64).T)
         if Cin is not None:
             d = d + beta * Cin.a.astype(np.float64)
         self.launches += 1
@@ -326,7 +330,7 @@ class FakeOps:
         cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
         return (len(cheb) + (3 if series else 0)) * n_rows
 
-    def lbo_prepare(self, Pv, Vt, lam_o, a2_min, steps=48):
+    def lbo_prepare(self, Pv, Vt, lam_o, a2_min, steps=48, lanczos=True):
         """DeviceOps.lbo_prepare: B = X_R V, E = B diag(1/(lam_o + a2)), H = E B^T, lambda_max(H)."""
         assert Pv.is_split and Vt.is_split
         B = (Pv.a.astype(np.float64) @ Vt.a.astype(np.float64).T).astype(F32)
@@ -334,7 +338,7 @@ class FakeOps:
         H = (E.astype(np.float64) @ B.astype(np.float64).T).astype(F32)
         self.lbo_prepared = getattr(self, "lbo_prepared", 0) + 1
         return {"B": FMat(B, split=True), "E": FMat(E, split=True), "H": FMat(H, split=True), "a2": float(a2_min),
-                "hmax_dev": self.lambda_max(FMat(H))}
+                "hmax_dev": self.lambda_max(FMat(H)) if lanczos else None}
 
     @staticmethod
     def _lbo_scaled(B, lam_o, a2):
@@ -342,6 +346,11 @@ class FakeOps:
         a = F32(np.sqrt(np.float64(a2)))
         with np.errstate(divide="ignore", invalid="ignore"):
             return np.where(lam[None, :] > 0, B / (lam[None, :] + a * a), F32(0)).astype(F32)
+
+    def lambda_max_batched(self, mats, steps=96):
+        assert len({(m.rows, m.cols) for m in mats}) <= 1, "one size per batch"
+        self.lanczos_batches = getattr(self, "lanczos_batches", 0) + 1
+        return np.array([self.lambda_max(m)[0] for m in mats])
 
     def solve_blocks(self, Gs, Pc, n_rows, lam_max, a2_list, series_ratio=60.0, lbo=None):
         """Compact per-fold solution block in the layout of DeviceOps.solve_blocks: the solutions of the small

@@ -126,6 +126,35 @@ def test_gemm_3xtf32_matches_fp64(ops, M, N, K, variant):
     assert abs(np.mean((D - ref) * np.sign(ref))) / scale < 1.5e-6  # bounded (K-independent) truncation bias
 
 
+@pytest.mark.parametrize("M,N,K", [(200, 300, 100), (1000, 777, 515), (130, 36, 8), (2048, 1024, 1504), (300, 260, 7520)])
+@pytest.mark.parametrize("variant", [1, 3])
+def test_gemm_f16x3_store_matches_fp64(ops, M, N, K, variant):
+    """lit_gemm_f16x3_nt (fp16 split pairs, scales undone in the epilogue) against fp64: rows of both operands
+    scaled over 16 orders of magnitude, beta / Cin and split-pair outputs, at the accuracy of the 3xTF32 form."""
+    rng = np.random.default_rng(M + N + K + 1)
+    sa, sb = np.exp(rng.uniform(-9, 9, (M, 1))), np.exp(rng.uniform(-9, 9, (N, 1)))
+    sa[3 % M], sb[5 % N] = 0.0, 0.0  # all-zero rows (scale 1)
+    A = (rng.standard_normal((M, K)) * sa).astype(np.float32)
+    B = (rng.standard_normal((N, K)) * sb).astype(np.float32)
+    C = (rng.standard_normal((M, N)) * sa * sb.T).astype(np.float32)
+    old = ops.gemm_variant
+    ops.gemm_variant = variant
+    try:
+        D = _mat(ops, ops.gemm(_split(ops, A), _split(ops, B), precision="f16x3"))
+        D2 = _mat(ops, ops.gemm(_split(ops, A), _split(ops, B), alpha=-1.0, Cin=ops.upload_matrix(C), beta=1.0,
+                                split_out=True, precision="f16x3"))
+        T = _mat(ops, ops.gemm(_split(ops, A), _split(ops, B)))
+    finally:
+        ops.gemm_variant = old
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.sqrt(K) * np.maximum(sa * sb.T, 1e-300)  # typical magnitude of an entry
+    e16 = np.abs(D - ref) / scale
+    assert e16.max() < 8e-6
+    assert (np.abs(D2 - (C.astype(np.float64) - ref)) / scale).max() < 8e-6
+    assert e16.max() <= 2 * (np.abs(T - ref) / scale).max() + 1e-6  # no worse than the 3xTF32 form
+    assert not D[3 % M].any() and not D[:, 5 % N].any()
+
+
 def test_gemm_corr_epilogue(ops):
     rng = np.random.default_rng(5)
     for M, G, R, K, variant in [(300, 3, 256, 64, 1), (1000, 4, 512, 128, 3), (130, 1, 2048, 96, 3)]:
@@ -506,6 +535,14 @@ def test_gemm_only_inner_solver_kernels(ops):
     Gw = Wn.T.astype(np.float64) @ Wn.astype(np.float64)
     lw = float(ops.lambda_max(ops.upload_matrix(Gw.astype(np.float32))).cpu()[0])
     assert abs(lw - np.linalg.eigvalsh(Gw)[-1]) <= 1e-4 * lw
+    # batched runs (one launch per step for all matrices) reproduce the single-matrix ones; 40 matrices = 2 launches
+    mats = [ops.upload_matrix((G * (1.0 + 0.01 * i)).astype(np.float32)) for i in range(40)]
+    single = np.array([float(ops.lambda_max(m).cpu()[0]) for m in mats[:3] + mats[-2:]])
+    batched = ops.lambda_max_batched(mats).cpu().numpy()
+    np.testing.assert_allclose(batched[[0, 1, 2, 38, 39]], single, rtol=1e-9)
+    np.testing.assert_allclose(batched, lam[-1] * (1.0 + 0.01 * np.arange(40)), rtol=3e-6)
+    short = ops.lambda_max_batched(mats[:5], steps=48).cpu().numpy()
+    np.testing.assert_allclose(short, batched[:5], rtol=1e-4)
     P = rng.standard_normal((m, p)).astype(np.float32)
     Pc = P - P.mean(0)
     alphas = np.logspace(-1, 8, 20)
@@ -670,7 +707,8 @@ def test_gemm_corr_f16x3_matches_fp64(ops):
 
 
 def test_corr_precisions_agree_on_fit(ops):
-    """Whole fit with the fused GEMM in both operand formats: same alphas (up to near-ties), same r."""
+    """Whole fit with the voxel-side GEMMs (fused prediction GEMM, cross products, rotations, weights) in both
+    operand formats: same alphas (up to near-ties), same r, same weights."""
     from litcoder_core_b200 import NestedCVModel
 
     rng = np.random.default_rng(21)
@@ -684,6 +722,8 @@ def test_corr_precisions_agree_on_fit(ops):
     same = out["tf32x3"][2] == out["f16x3"][2]
     assert same.mean() > 0.97, same.mean()
     assert np.abs(out["tf32x3"][0][same] - out["f16x3"][0][same]).max() < 2e-5
+    wt, wf = out["tf32x3"][1][:, same], out["f16x3"][1][:, same]
+    assert np.abs(wt - wf).max() < 2e-5 * np.abs(wt).max()
     with pytest.raises(ValueError, match="Unknown corr_precision"):
         NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision="bf16", **kw)
 
