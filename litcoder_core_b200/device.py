@@ -750,7 +750,7 @@ class DeviceOps:
         lo_rigorous = a2 / (a2 + 1.001 * lam_top)
         return max(1.0 - hi_h, lo_rigorous), 1.0
 
-    def _lbo_solve(self, block: Mat, lbo: dict, cheb, a2_list, n_rows: int, tol: float = 1e-6) -> None:
+    def _lbo_solve(self, block: Mat, lbo: dict, cheb, a2_list, n_rows: int, tol: float = 2e-7) -> None:
         """Rows [i * n_rows, (i+1) * n_rows) of `block` <- J (I - H_a)^-1 B D_a V^T for the i-th Chebyshev alpha
         (J = column centring over the validation rows).  The |R| x |R| systems are solved by Chebyshev iteration on
         the transposed unknown x = Z^T (k x |R|), so that every step is one NT GEMM r = t + d H; a handful of steps

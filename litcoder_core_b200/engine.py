@@ -125,7 +125,8 @@ class RidgeCVEngine:
     def __init__(self, ops, comm=None):
         self.ops = ops
         self.comm = comm if comm is not None else SingleProcess()
-        self._eig_jobs = 0  # running count of eigenproblems; job j is solved by rank j % world
+        self._eig_jobs = 0  # running count of inner-fold solves / eigenproblems; job j belongs to rank j % world
+        self._outer_jobs = 0  # outer eigendecompositions are dealt out separately, from the last rank downwards
 
     # ------------------------------------------------------------------------------------------
     # row-index vectors of every fold, staged to the device in ONE asynchronous copy
@@ -212,7 +213,7 @@ class RidgeCVEngine:
                     XtT = ops.gather_rows_T_split(X, d["train"], n_i)
                     d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if need_G else ops.empty(p, p))
             inners.append(d)
-        outer["owner"] = self._next_eig_owner()
+        outer["owner"] = self._next_outer_owner()
         if not outer["dual"]:
             outer["G"] = ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o
             outer["G_keep"] = G_o
@@ -349,6 +350,15 @@ class RidgeCVEngine:
         for i, m in items:
             groups.setdefault((m.rows, m.ld), []).append(i)
         return list(groups.values())
+
+    def _next_outer_owner(self) -> int:
+        """Owner of an outer fold's eigendecomposition: outer k -> rank (world - 1 - k) mod world, so that the long
+        cuSOLVER calls land on distinct ranks (and on the ranks with the fewest inner-fold solves) instead of
+        wherever a single running job count happens to put them (with 2 ranks and 5 + 1 jobs per outer fold: all
+        on rank 1)."""
+        owner = (self.comm.world - 1 - self._outer_jobs) % self.comm.world
+        self._outer_jobs += 1
+        return owner
 
     def _next_eig_owner(self) -> int:
         owner = self._eig_jobs % self.comm.world
@@ -499,7 +509,7 @@ class RidgeCVEngine:
         `inner`, the validation rows of a single inner fold on the same training rows -- follow them."""
         tr = np.arange(n_train, dtype=np.int64)
         va = np.arange(n_train, n_train + n_val, dtype=np.int64)
-        self._eig_jobs = 0
+        self._eig_jobs = self._outer_jobs = 0
         return self.stage_plans([FoldPlan(tr, va, [(tr, va)] if (inner and n_val) else [])], cfg)[0]
 
     def ridge_corr(self, XX, YY, n_train: int, cfg: RidgeConfig):
@@ -590,7 +600,7 @@ class RidgeCVEngine:
         # eigendecompositions now lets the side stream run ahead of the response-side GEMMs.
         Xte_src, Yte_src = (X, Y) if same_source else (X_test, Y_test)
         staged = self.stage_plans(plans, cfg)
-        self._eig_jobs = 0
+        self._eig_jobs = self._outer_jobs = 0
         prepared = []
         for sp in staged:
             Xs, Xts = self._normalised(X, Xte_src, sp["train_rows"], sp["train"], cfg.normalize_features, same_source)
