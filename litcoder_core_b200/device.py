@@ -167,7 +167,9 @@ class DeviceOps:
         self.gemm_flops = 0.0  # algorithmic 2*M*N*K of the executed GEMMs (x3 tensor-core MMAs each)
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.store_gemms = 0  # launches of the store-epilogue GEMM
+        self.store_gemms = 0  # launches of the store-epilogue GEMM (both operand formats)
+        self.store_gemms_f16 = 0  # ... of which on fp16 split pairs (lit_gemm_f16x3_nt)
+        self.gemm_flops_f16 = 0.0  # algorithmic flops of those
         self.compact_stacks = 0  # fused-GEMM launches on a compact (series) alpha stack
         self._corr_log: List[tuple] = []  # (start, stop, flops) of every fused prediction+correlation GEMM
         self._staging: List[object] = []
@@ -478,7 +480,7 @@ class DeviceOps:
         if precision == "f16x3" and M and N:
             A, B = self.split_f16(A, 1), self.split_f16(B, 1)
         self._apply_sm_limit()
-        with self.timed("gemm"):
+        with self.timed("gemm_f16" if isinstance(A, MatF16) else "gemm"):
             if isinstance(A, MatF16):
                 variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256,
                                                                      _lib.GEMM_2CTA_N256) else _lib.GEMM_AUTO
@@ -493,6 +495,9 @@ class DeviceOps:
         self.launches += 1
         self.store_gemms += 1
         self.gemm_flops += 2.0 * M * N * K
+        if isinstance(A, MatF16):
+            self.store_gemms_f16 += 1
+            self.gemm_flops_f16 += 2.0 * M * N * K
         return out
 
     def _gemm_call(self, A, B, M, N, K, alpha, Cin, beta, out):

@@ -348,6 +348,9 @@ class NestedCVModel:
                            "world": comm.world, "voxels_this_rank": c1 - c0,
                            "h2d_bytes": getattr(ops, "h2d_bytes", 0), "d2h_bytes": getattr(ops, "d2h_bytes", 0),
                            "store_gemm_launches": getattr(ops, "store_gemms", 0),
+                           "store_gemm_f16_launches": getattr(ops, "store_gemms_f16", 0),
+                           "store_gemm_f16_flops": getattr(ops, "gemm_flops_f16", 0.0),
+                           "voxel_gemm_precision": cfg.voxel_gemm_precision,
                            "compact_stacks": getattr(ops, "compact_stacks", 0)}
         if hasattr(ops, "corr_launches"):
             log = ops.corr_launches()
