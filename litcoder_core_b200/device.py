@@ -350,6 +350,12 @@ class DeviceOps:
         full = self.wrap(tensor)
         return Mat(tensor[:, c0:c1], None, full.rows, c1 - c0, ld=full.ld)
 
+    def col_view(self, m: Mat, c0: int, c1: int) -> Mat:
+        """Columns [c0, c1) of a matrix or split pair as a view (c0 on a multiple of 4 floats: TMA base alignment)."""
+        if c0 % 4:
+            raise ValueError("col_view: the first column must be a multiple of 4")
+        return Mat(m.hi[:, c0:c1], m.lo[:, c0:c1] if m.lo is not None else None, m.rows, c1 - c0, ld=m.ld)
+
     def raw(self, x):
         """Underlying torch tensor of a Mat (first plane) or device vector, for in-place collectives."""
         return x.hi if isinstance(x, Mat) else x

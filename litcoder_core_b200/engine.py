@@ -74,6 +74,8 @@ class RidgeConfig:
     # chunked / k-fold layouts of the reference): solve the small alphas through the leave-block-out identity on
     # the outer fold's eigendecomposition (DeviceOps.lbo_prepare) instead of Chebyshev iteration on the p x p Gram
     leave_block_out: bool = True
+    # several ranks: each forms the outer Gram / kernel matrix over its slice of the contraction axis, one all-reduce
+    row_shard_gram: bool = False
 
 
 @dataclass
@@ -105,6 +107,9 @@ class SingleProcess:
         return arr
 
     def broadcast_inplace(self, buffers, src: int) -> None:
+        pass
+
+    def all_reduce_sum_inplace(self, buffers) -> None:
         pass
 
 
@@ -159,6 +164,23 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     # design side: Grams and their eigendecompositions (depend on X only)
     # ------------------------------------------------------------------------------------------
+    def _gram(self, A, cfg: RidgeConfig):
+        """A A^T for a split pair A (rows x K).  With `row_shard_gram` and several ranks: this rank's slice of the
+        contraction axis only (slice boundaries on multiples of 32 values), then ONE all-reduce of the partial sums
+        (the row-sharded Gram of the wide designs)."""
+        ops, comm = self.ops, self.comm
+        if not (cfg.row_shard_gram and comm.world > 1):
+            return ops.gemm(A, A)
+        per = -(-(-(-A.cols // comm.world)) // 32) * 32
+        k0, k1 = min(comm.rank * per, A.cols), min((comm.rank + 1) * per, A.cols)
+        if k1 > k0:
+            part = ops.col_view(A, k0, k1)
+            G = ops.gemm(part, part)
+        else:
+            G = ops.zeros(A.rows, A.rows)
+        comm.all_reduce_sum_inplace([ops.raw(G)])
+        return G
+
     def _design_side(self, X, sp, cfg: RidgeConfig):
         """Gram + syevd for the outer training set and for every inner fold of one staged plan `sp`.
 
@@ -176,11 +198,11 @@ class RidgeCVEngine:
         if outer["dual"]:
             XoR = ops.gather_rows(X, sp["train"], n_o, split=True)  # (n_o x p)
             G_o = None
-            outer["G"] = ops.gemm(XoR, XoR)  # kernel matrix, n_o x n_o (needed on every rank only after the eig)
+            outer["G"] = self._gram(XoR, cfg)  # kernel matrix, n_o x n_o (needed on every rank only after the eig)
             del XoR
         else:
             XoT = ops.gather_rows_T_split(X, sp["train"], n_o)  # (p x n_o)
-            G_o = ops.gemm(XoT, XoT)  # outer Gram, p x p
+            G_o = self._gram(XoT, cfg)  # outer Gram, p x p
             outer["XtT"] = XoT
         inners = []
         for d in sp["inner"]:

@@ -71,6 +71,12 @@ class TorchDistComm:
         self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
+    def all_reduce_sum_inplace(self, buffers) -> None:
+        """Sum the ranks' buffers in place (torch tensors on the communicator's device, or NumPy arrays with gloo)."""
+        for b in buffers:
+            t = b if self._torch.is_tensor(b) else self._torch.from_numpy(b)
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+
     def broadcast_inplace(self, buffers, src: int) -> None:
         """Broadcast rank `src`'s buffers into everybody's (torch tensors on the communicator's device, or
         NumPy arrays with the gloo backend), in place."""
@@ -214,6 +220,7 @@ class NestedCVModel:
         device_outputs: bool = False,
         inner_solver: str = "auto",
         corr_precision: str = "auto",
+        row_shard_gram: bool = False,
     ) -> Tuple[Dict[str, Union[float, List[float], List[bool]]], np.ndarray, np.ndarray]:
         """Fit with nested CV (or inner CV + a given test set), per-voxel or single alpha, FDR correction.
 
@@ -227,6 +234,10 @@ class NestedCVModel:
         ``corr_precision`` (extension): operand format of the fused inner-CV prediction + correlation GEMM:
         "tf32x3" (3xTF32 split pairs) or "f16x3" (scaled fp16 split pairs: same 2^-22 product accuracy, twice the
         tensor-core rate); "auto" = "f16x3".
+        ``row_shard_gram`` (extension, multi-GPU only): every rank forms the outer-fold Gram (or kernel matrix) over
+        its own 1/G of the contraction axis and the ranks all-reduce the partial sums (NCCL) instead of each forming
+        the whole Gram -- for wide designs (BASELINE config 5); results then agree across rank counts to fp32
+        rounding of that sum instead of bit for bit.
         """
         t_start = time.perf_counter()
         if alphas is None:
@@ -275,6 +286,7 @@ class NestedCVModel:
         if corr_precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"Unknown corr_precision: {corr_precision}")
         cfg.corr_precision = corr_precision
+        cfg.row_shard_gram = bool(row_shard_gram)
         cfg.voxel_gemm_precision = os.environ.get("LIT_VOXEL_GEMM", corr_precision)  # development override
         cfg.series_moments = os.environ.get("LIT_SERIES_MOMENTS", "1") != "0"  # development override
         cfg.leave_block_out = os.environ.get("LIT_LEAVE_BLOCK_OUT", "1") != "0"  # development override

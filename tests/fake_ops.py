@@ -101,6 +101,10 @@ class FakeOps:
         self.h2d_bytes += host[:, col_start:col_stop].nbytes
         return FMat(host[:, col_start:col_stop].astype(F32))
 
+    def col_view(self, m, c0, c1):
+        assert c0 % 4 == 0
+        return FMat(m.a[:, c0:c1], m.is_split)
+
     def raw(self, x):
         return x.a if isinstance(x, FMat) else x
 

@@ -19,15 +19,17 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _problem():
+def _problem(wide=False):
     rng = np.random.default_rng(5)
     N, p, V = 300, 10, 300  # 300 voxels -> blocks of 256 + 44 (shards start on 128-voxel tile boundaries)
+    if wide:
+        p = 330  # more features than training rows: dual form (n x n kernel matrix, contraction over features)
     X = rng.standard_normal((N, p)).astype(np.float32)
     Y = (X @ rng.standard_normal((p, V)) * 0.4 + rng.standard_normal((N, V))).astype(np.float32)
     return X, Y
 
 
-def _worker(rank, world, port, single_alpha, out_dir):
+def _worker(rank, world, port, single_alpha, out_dir, row_shard_gram=False, wide=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     import torch.distributed as dist
@@ -37,12 +39,13 @@ def _worker(rank, world, port, single_alpha, out_dir):
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
-        X, Y = _problem()
+        X, Y = _problem(wide)
         random.seed(11)
         ops = FakeOps()
         model = NestedCVModel("ridge_regression", ops=ops, comm=TorchDistComm())
         m, w, a = model.fit_predict(X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10,
-                                    alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
+                                    alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha,
+                                    row_shard_gram=row_shard_gram)
         assert model.last_stats["world"] == world and model.last_stats["voxels_this_rank"] in (256, 44)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
                  p=np.asarray(m["p_values"]), sig=np.asarray(m["significant_mask"]), n_sig=m["n_significant"],
@@ -76,3 +79,27 @@ def test_two_ranks_match_single_process(tmp_path, single_alpha):
         np.testing.assert_allclose(g["p"], np.asarray(m["p_values"]), rtol=1e-4, atol=1e-12)
         assert int(g["n_sig"]) == m["n_significant"]
         np.testing.assert_array_equal(g["sig"], np.asarray(m["significant_mask"]))
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_row_sharded_gram_matches_single_process(tmp_path, wide):
+    """row_shard_gram=True: each rank forms the outer Gram over its half of the TRs, one all-reduce; the fit then
+    agrees with the single-process one to fp32 rounding of that sum (not bit for bit)."""
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    from fake_ops import FakeOps
+    from litcoder_core_b200.nested_cv import NestedCVModel
+
+    X, Y = _problem(wide)
+    random.seed(11)
+    m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(
+        X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6))
+    mp.spawn(_worker, args=(2, _free_port(), False, str(tmp_path), True, wide), nprocs=2, join=True)
+    for rank in range(2):
+        g = np.load(tmp_path / f"rank{rank}.npz")
+        same = g["a"] == a
+        assert same.mean() > 0.98
+        np.testing.assert_allclose(g["r"][same], np.asarray(m["correlations"])[same], atol=1e-5)
+        np.testing.assert_allclose(g["w"][:, same], w[:, same], atol=1e-5 * np.abs(w).max())
+    np.testing.assert_array_equal(np.load(tmp_path / "rank0.npz")["a"], np.load(tmp_path / "rank1.npz")["a"])

@@ -187,6 +187,27 @@ def test_engine_on_fake_ops_matches_reference_golden(name):
     assert err < 1e-4, (name, err)
 
 
+@pytest.mark.parametrize("name", ["tt_default", "cv_default"])
+def test_results_hand_off_to_the_reference_trainer(name, tmp_path):
+    """What AbstractTrainer.train does with the triple after fit_predict: log_metrics reads scalars
+    and arrays out of the metrics dict (trainer.py:322-336), ModelSaver pickles the dict and np.saves the weights
+    (encoding/utils.py:324-354)."""
+    import pickle
+
+    _, (m, w, a) = _run_product(name)
+    for k in ("median_score", "mean_score", "std_score"):
+        assert isinstance(float(m[k]), float)
+    corr = np.array(m["correlations"])
+    mask = np.array(m["significant_mask"], dtype=bool)
+    assert corr.shape == mask.shape == (w.shape[1],) and float(m["n_significant"]) == mask.sum()
+    back = pickle.loads(pickle.dumps(m))
+    assert back.keys() == m.keys() and back["correlations"] == m["correlations"]
+    np.save(tmp_path / "weights.npy", w)
+    np.testing.assert_array_equal(np.load(tmp_path / "weights.npy"), w)
+    assert isinstance(m["correlations"], list) and isinstance(m["significant_mask"], list)
+    assert a.shape == (w.shape[1],)
+
+
 @pytest.mark.parametrize("name", ["tt_default", "cv_default", "cv_kfold"])
 def test_downdate_and_overlap_do_not_change_results(name):
     """The Gram / cross-product downdates and the asynchronous eigendecompositions are pure
