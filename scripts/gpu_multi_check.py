@@ -32,20 +32,23 @@ def main():
     W = (rng.standard_normal((p, V)) / np.sqrt(p)).astype(np.float32) * (rng.random(V) < 0.3)
     Y = (X @ W + 3.0 * rng.standard_normal((N, V))).astype(np.float32)
     out = {}
-    for single_alpha in (False, True):
+    # --row-shard-gram: only the run with the outer Gram formed over 1/world of the TRs per rank + one all-reduce
+    # (agreement with the unsharded fit then holds to fp32 rounding of that sum, not bit for bit)
+    row_shard = "--row-shard-gram" in sys.argv
+    for single_alpha in ((False,) if row_shard else (False, True)):
         kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 6, 12), single_alpha=single_alpha)
         random.seed(1)
-        m, w, a = L.NestedCVModel("ridge_regression").fit_predict(X, Y, **kw)
+        m, w, a = L.NestedCVModel("ridge_regression").fit_predict(X, Y, row_shard_gram=row_shard, **kw)
         if rank == 0:
             random.seed(1)
             m1, w1, a1 = L.NestedCVModel("ridge_regression", comm=SingleProcess()).fit_predict(X, Y, **kw)
             same = np.isclose(a, a1)
             r, r1 = np.asarray(m["correlations"]), np.asarray(m1["correlations"])
-            out[f"single_alpha={single_alpha}"] = {
+            out[f"single_alpha={single_alpha}" + (",row_shard_gram" if row_shard else "")] = {
                 "world": world, "alpha_agreement": float(same.mean()), "max_dr_same_alpha": float(np.abs(r - r1)[same].max()),
                 "max_dw_rel": float(np.abs(w[:, same] - w1[:, same]).max() / np.abs(w1).max()),
                 "n_significant": [m["n_significant"], m1["n_significant"]], "w_shape": list(w.shape)}
-            assert same.mean() > 0.999 and np.abs(r - r1)[same].max() < 1e-5, out
+            assert same.mean() > (0.97 if row_shard else 0.999) and np.abs(r - r1)[same].max() < 1e-5, out
             assert w.shape == w1.shape and abs(m["n_significant"] - m1["n_significant"]) <= 1
     if rank == 0:
         print(json.dumps(out), flush=True)
