@@ -29,15 +29,22 @@ Two further savings inside one outer fold (both exact up to fp32 rounding of a s
   * all eigendecompositions of an outer fold depend only on X, so they are queued up front on a
     side stream and overlap the response-side GEMMs on the main stream.
 
+Inner folds are by default solved WITHOUT an eigendecomposition of their own: the large
+alphas through a 4-term Neumann series whose terms share four stacked row blocks (compact alpha stack), the small
+ones through the leave-block-out identity on the outer fold's decomposition, or Chebyshev iteration on the p x p Gram.
+
 The engine is written against the small `ops` interface of device.DeviceOps so that its control
 flow can be unit-tested on CPU with a NumPy stand-in (tests/fake_ops.py).
 """
 from __future__ import annotations
 
+import logging
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
+
+logger = logging.getLogger(__name__)
 
 EPS = 1e-8  # ridge_utils.z_score / DataNormalizer eps
 
@@ -322,7 +329,11 @@ class RidgeCVEngine:
         for d in todo:
             d["lbo_args"]["lam_top"] = lam_top
             if not (0.0 <= d["lbo_args"]["h0"] < 1.0 + 1e-3) or not (lam_top > 0.0):
-                raise FloatingPointError("leave-block-out: lambda_max(H) outside [0, 1] (degenerate design)")
+                # lambda_max(H) must lie in [0, 1): a degenerate outer decomposition -- this fold keeps the direct
+                # Chebyshev route on its own Gram (an owner-local decision: the other ranks only receive the block)
+                logger.warning("leave-block-out bounds invalid (lambda_max(H) = %r); solving the p x p system",
+                               d["lbo_args"]["h0"])
+                del d["lbo_args"]
         if comm.world > 1:
             for d in todo:
                 d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)

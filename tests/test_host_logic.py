@@ -442,6 +442,14 @@ def test_leave_block_out_matches_chebyshev_route_on_fake_ops(monkeypatch):
     same = np.isclose(out["1"][2], ref_va, rtol=1e-6)
     assert same.mean() >= 0.9
     assert np.abs(out["1"][0][same] - ref_r[same]).max() < 3e-5
+    # invalid spectral bounds (a Lanczos value outside [0, 1)) send the fold back to the direct route
+    ops = FakeOps()
+    ops.lambda_max_batched = lambda mats, steps=96: (
+        np.full(len(mats), np.nan) if steps == 48 else FakeOps.lambda_max_batched(ops, mats, steps))
+    random.seed(7)
+    m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X[:400], Y[:400], inner_solver="chebyshev", **kw)
+    assert getattr(ops, "lbo_solved", 0) == 0 and ops.solver_calls == 12
+    np.testing.assert_array_equal(np.asarray(a), out["0"][2])
     # a fold whose validation rows are only PART of the rows removed from the outer training set is downdated but
     # keeps the direct solve; validating on all of them makes it a leave-block-out fold
     from fake_ops import FMat
