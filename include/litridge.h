@@ -85,7 +85,9 @@ int lit_gemm_f16x3_nt_corr(const void* A_hi, const void* A_lo, long lda, const v
 /* D = alpha * A B^T + beta * Cin with the operands as fp16 split pairs (lit_split_f16 with rows_per_group = 1 for
  * both): inv_a[M] / inv_b[N, readable up to the next multiple of 4] are the inverse operand scales the epilogue
  * multiplies back in (NULL = ones).  Same output options as lit_gemm_tf32x3_nt; variants 1CTA_N256 / 2CTA_N256.
- * lda / ldb in fp16 elements (multiples of 8). */
+ * lda / ldb in fp16 elements (multiples of 8).  Used for the voxel-side products: U^T Rresp
+ * (ridge_regression.py:32,104) as C^T = Y^T X and its fold downdates, the rotation into the eigenbasis and the
+ * weights (ridge_regression.py:59-61). */
 int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb, int M,
                       int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D, float* D_lo, long ldd,
                       const float* inv_a, const float* inv_b, int variant, void* stream);
@@ -96,14 +98,17 @@ int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* 
  * T_q = Q_q A[v]^T.  Every alpha of the series is then a 4-term combination (lit_corr_finalize_series) instead of
  * its own block of stacked rows: 16 of the 20 BASELINE alphas cost 4 row blocks.  The first n_groups *
  * rows_per_group rows are ordinary alpha groups (dot_part / ssq_part as in lit_gemm_tf32x3_nt_corr).
- * precision: 0 = 3xTF32 split pairs (float planes), 1 = fp16 split pairs (lit_split_f16). */
+ * precision: 0 = 3xTF32 split pairs (float planes), 1 = fp16 split pairs (lit_split_f16).
+ * Replaces the per-alpha loop of ridge_corr_torch (ridge_regression.py:115-133) for all alphas of a fold at once. */
 int lit_gemm_corr_series(int precision, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
                          long ldb, int M, int n_groups, int rows_per_group, int n_series_tiles, int K, const float* Yz,
                          long ldy, float* dot_part, float* ssq_part, float* series_part, long ld_part, int variant,
                          void* stream);
 /* fp16 split pair of x = src_hi (+ src_lo when non-NULL):  out_hi = fp16(s x), out_lo = fp16(s x - out_hi) with one
  * power-of-two scale s per group of rows_per_group consecutive rows (1 for the voxel rows of A, 256 = one N tile
- * for the stacked design B), chosen so that the group's largest magnitude lands in [2^14, 2^15).  inv_scale[g] = 1/s.  scratch: 8 bytes per group.  ld_out in fp16 elements. */
+ * for the stacked design B), chosen so that the group's largest magnitude lands in [2^14, 2^15).
+ * inv_scale[g] = 1/s.  scratch: 8 bytes per group.  ld_out in fp16 elements.  (Operand format only: no reference
+ * counterpart; the reference multiplies fp32 tensors, ridge_regression.py:32,104,120.) */
 int lit_split_f16(const float* src_hi, const float* src_lo, long ld_src, long rows, long cols, long rows_per_group,
                   void* out_hi, void* out_lo, long ld_out, float* inv_scale, void* scratch, void* stream);
 
