@@ -103,3 +103,59 @@ def test_row_sharded_gram_matches_single_process(tmp_path, wide):
         np.testing.assert_allclose(g["r"][same], np.asarray(m["correlations"])[same], atol=1e-5)
         np.testing.assert_allclose(g["w"][:, same], w[:, same], atol=1e-5 * np.abs(w).max())
     np.testing.assert_array_equal(np.load(tmp_path / "rank0.npz")["a"], np.load(tmp_path / "rank1.npz")["a"])
+
+
+def _problem_5x5():
+    rng = np.random.default_rng(5)
+    N, p, V = 500, 12, 1100  # 1,100 voxels over 4 ranks: blocks of 384, 384, 332 and 0 (tile-aligned starts)
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Y = (X @ rng.standard_normal((p, V)) * 0.4 + rng.standard_normal((N, V))).astype(np.float32)
+    return X, Y
+
+
+_KW_5X5 = dict(n_outer_folds=5, n_inner_folds=5, chunk_length=10, alphas=np.logspace(-1, 8, 20))
+
+
+def _worker_5x5(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+
+    from fake_ops import FakeOps
+    from litcoder_core_b200.nested_cv import NestedCVModel, TorchDistComm
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        X, Y = _problem_5x5()
+        random.seed(11)
+        ops = FakeOps()
+        m, w, a = NestedCVModel("ridge_regression", ops=ops, comm=TorchDistComm()).fit_predict(X, Y, **_KW_5X5)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
+                 n_sig=m["n_significant"], lbo=getattr(ops, "lbo_solved", 0), eig=ops.eig_calls,
+                 solves=getattr(ops, "solver_calls", 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_four_ranks_bench_layout(tmp_path):
+    """The BASELINE layout (5 x 5 chunked folds, 20 alphas: 4 solved + 16 series alphas per inner fold) on 4 ranks:
+    25 leave-block-out solves and 5 outer decompositions dealt out evenly, compact stacks broadcast, same result."""
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, HERE)
+    from fake_ops import FakeOps
+    from litcoder_core_b200.nested_cv import NestedCVModel
+
+    X, Y = _problem_5x5()
+    random.seed(11)
+    m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(X, Y, **_KW_5X5)
+    mp.spawn(_worker_5x5, args=(4, _free_port(), str(tmp_path)), nprocs=4, join=True)
+    per = [np.load(tmp_path / f"rank{r}.npz") for r in range(4)]
+    assert sorted(int(g["eig"]) for g in per) == [1, 1, 1, 2]
+    assert sorted(int(g["solves"]) for g in per) == [6, 6, 6, 7]
+    assert sum(int(g["lbo"]) for g in per) == 25 * 4
+    for g in per:
+        np.testing.assert_array_equal(g["a"], a)
+        np.testing.assert_allclose(g["r"], np.asarray(m["correlations"]), atol=1e-6)
+        np.testing.assert_allclose(g["w"], w, atol=1e-6 * np.abs(w).max())
+        assert int(g["n_sig"]) == m["n_significant"]
