@@ -47,27 +47,31 @@ class FIR:
             out = out.astype(stim.dtype)
         return out
 
-    def n_delays(self) -> int:
-        """Number of delays used."""
-        return len(self.delays) if self.delays is not None else 0
-
-    def output_dim(self, input_dim: int) -> int:
-        """Output dimensionality after expansion."""
-        return input_dim * self.n_delays()
-
-    def valid_length(self, nt: int) -> int:
-        """Number of time points that contain no padding (nt with circular padding)."""
+    # ---- bookkeeping helpers of the reference class (FIR_expander.py:45-73): same names, same answers ----
+    def _shifts(self):
         if self.delays is None:
             raise ValueError("delays must be provided")
-        if self.circpad:
-            return nt
-        return max(0, nt - max(abs(d) for d in self.delays))
+        return [int(d) for d in self.delays]
+
+    def n_delays(self) -> int:
+        """How many shifted copies `expand` stacks (0 for an instance built without delays)."""
+        return 0 if self.delays is None else len(self.delays)
+
+    def output_dim(self, input_dim: int) -> int:
+        """Width of the expanded matrix for an `input_dim`-wide stimulus."""
+        return self.n_delays() * input_dim
+
+    def valid_length(self, nt: int) -> int:
+        """Rows of an nt-row expansion that hold no zero padding: all of them with circular padding, otherwise nt
+        minus the largest shift in either direction (never negative)."""
+        shifts = self._shifts()
+        return nt if self.circpad else max(nt - max(abs(d) for d in shifts), 0)
 
     def summary(self, input_dim: Optional[int] = None, nt: Optional[int] = None) -> str:
-        """Readable summary of the configuration."""
-        msg = f"FIR(delays={list(self.delays)}, circpad={self.circpad})"
+        """One line naming the configuration, plus the output width / unpadded length when asked for."""
+        lines = [f"FIR(delays={list(self.delays)}, circpad={self.circpad})"]
         if input_dim is not None:
-            msg += f"\n- Output dim: {self.output_dim(input_dim)}"
+            lines.append(f"- Output dim: {self.output_dim(input_dim)}")
         if nt is not None:
-            msg += f"\n- Valid length: {self.valid_length(nt)}"
-        return msg
+            lines.append(f"- Valid length: {self.valid_length(nt)}")
+        return "\n".join(lines)
