@@ -173,6 +173,14 @@ class NestedCVModel:
         self.last_stats: Dict[str, Any] = {}
 
     # -- plumbing --------------------------------------------------------------------------------
+    @staticmethod
+    def _single_alpha_values(a_f: np.ndarray, alphas, dtype) -> np.ndarray:
+        """single_alpha=True: the per-fold alpha vectors (n_folds x V; the device holds them as float32) with the grid
+        value itself, in the dtype the reference returns (see fit_predict)."""
+        grid = np.asarray(alphas, dtype=np.float64)
+        idx = np.argmin(np.abs(grid[None, :] - a_f[:, :1].astype(np.float64)), axis=1)
+        return np.repeat(grid[idx].astype(dtype)[:, None], a_f.shape[1], axis=1)
+
     def _get_ops(self):
         if self._ops is None:
             from .device import default_ops
@@ -242,6 +250,9 @@ class NestedCVModel:
         t_start = time.perf_counter()
         if alphas is None:
             alphas = np.logspace(-1, 8, 10)  # nested_cv.py:80-81
+        # single_alpha: the reference builds torch.tensor([alphas[j]] * V) (nested_cv.py:399-401), whose dtype follows
+        # the element -- float64 for an element of a float64 ndarray, torch's default float32 for a Python float
+        single_dtype = np.float64 if (len(alphas) and isinstance(alphas[0], np.float64)) else np.float32
         alphas = [float(a) for a in alphas]
         if not use_gpu:
             logger.info("use_gpu=False ignored: litcoder_core_b200 always runs on the B200 (no CPU path)")
@@ -341,14 +352,15 @@ class NestedCVModel:
             masks, comb_p, sig, padj = engine.significance(p_f, cfg)
 
         if train_test_mode:
-            best = a_f[0].astype(np.float64) if single_alpha else a_f[0]  # reference dtype quirk (:396-405)
+            best = self._single_alpha_values(a_f, alphas, single_dtype)[0] if single_alpha else a_f[0]
             metrics = _metrics(r_f[0].astype(np.float64), p_f[0], padj, sig, best)
         else:
             if comb_p is None:  # a single outer fold: Fisher's method on one p-value is the identity
                 comb_p = p_f[0]
             corr = np.mean(r_f, axis=0)  # nested_cv.py:276
             majority = np.sum(np.stack(masks), axis=0) >= (n_outer_folds // 2 + 1)  # nested_cv.py:288-290
-            best = np.mean(a_f.astype(np.float64) if single_alpha else a_f, axis=0)  # nested_cv.py:293
+            best = np.mean(self._single_alpha_values(a_f, alphas, single_dtype) if single_alpha else a_f,
+                           axis=0)  # nested_cv.py:293
             metrics = _metrics(corr.astype(np.float64), comb_p, padj, sig, best, majority)
 
         t_stats_end = time.perf_counter()

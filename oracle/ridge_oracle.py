@@ -397,7 +397,10 @@ def find_best_alphas(X, Y, splits, alphas, single_alpha=False, normalpha=False, 
     mean_corr = (acc / F32(len(corrs))).astype(F32)  # torch.stack(...).mean(0)
     if single_alpha:
         j = int(np.argmax(mean_corr.mean(axis=1, dtype=F32)))
-        best = np.full(Y.shape[1], alphas[j], dtype=F32)
+        # torch.tensor([alphas[j]] * V) (:399-401) takes its dtype from the element: float64 for an element of a
+        # float64 ndarray, torch's default float32 for a Python float
+        a = alphas[j]
+        best = np.full(Y.shape[1], a, dtype=np.float64 if isinstance(a, np.float64) else F32)
     else:
         best = np.asarray(alphas, dtype=np.float64)[np.argmax(mean_corr, axis=0)].astype(F32)
     return (best, mean_corr) if return_corrs else best

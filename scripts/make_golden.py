@@ -399,9 +399,44 @@ def structure_golden():
     print("structure.npz written", {k: (v.shape, v.dtype) for k, v in list(tt.items()) + list(cc.items())})
 
 
+def grid20_golden():
+    """fit_predict on the BASELINE alpha grid (np.logspace(-1, 8, 20): 4 alphas below sqrt(60), 16 above -- the split
+    between solved and series alphas of the GEMM-only inner folds), same data as fit_predict.npz, nested and
+    train/test mode, per-voxel and single alpha."""
+    NestedCVModel = import_reference()[0]
+    g = np.load(os.path.join(OUT, "fit_predict.npz"))
+    X, Y = g["X"], g["Y"]
+    alphas = np.logspace(-1, 8, 20).tolist()
+    model = NestedCVModel("ridge_regression")
+    out = {"alphas": np.asarray(alphas)}
+    runs = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False),
+            "cv_grid20_single": dict(train_test=False, single_alpha=True)}
+    with quiet():
+        for name, kw in runs.items():
+            kw = dict(kw)
+            tt = kw.pop("train_test")
+            random.seed(7)
+            np.random.seed(7)
+            common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas,
+                          use_gpu=False)
+            common.update(kw)
+            if tt:
+                metrics, wt, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
+            else:
+                metrics, wt, va = model.fit_predict(X[:400], Y[:400], **common)
+            out[f"{name}__weights"] = np.asarray(wt)
+            out[f"{name}__best_alphas"] = np.asarray(va)
+            for key, val in metrics.items():
+                out[f"{name}__m__{key}"] = np.asarray(val)
+    np.savez_compressed(os.path.join(OUT, "fit_predict_grid20.npz"), **out)
+    print("fit_predict_grid20.npz written", sorted(runs))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if "--structure-only" in sys.argv:
+    if "--grid20-only" in sys.argv:
+        grid20_golden()
+    elif "--structure-only" in sys.argv:
         structure_golden()
     elif "--extra-only" in sys.argv:
         extra_golden()
@@ -410,3 +445,4 @@ if __name__ == "__main__":
         main()
         extra_golden()
         structure_golden()
+        grid20_golden()

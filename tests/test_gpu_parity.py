@@ -326,7 +326,7 @@ def test_fit_predict_matches_reference_golden(ops, name):
     import litcoder_core_b200 as L
 
     g = load_golden("fit_predict.npz")
-    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    X, Y, alphas = g["X"], g["Y"], list(g["alphas"])  # np.float64 elements, as the generator passed them
     kw = dict(RUNS[name])
     tt = kw.pop("train_test")
     common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
@@ -949,3 +949,40 @@ def test_structure_kernels_match_reference_trainer(ops):
     m2, w2, a2 = L.fit_nested_cv(features=tt["Rstim"], targets=tt["Rresp"], X_test=tt["Pstim"], y_test=tt["Presp"], **kw)
     np.testing.assert_array_equal(w1, w2)
     np.testing.assert_array_equal(a1, a2)
+
+
+GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False),
+          "cv_grid20_single": dict(train_test=False, single_alpha=True)}
+
+
+@pytest.mark.parametrize("name", sorted(GRID20))
+def test_fit_predict_on_the_baseline_alpha_grid_matches_reference_golden(ops, name):
+    """The unmodified reference's output on np.logspace(-1, 8, 20) (tests/golden/fit_predict_grid20.npz): the
+    compact alpha stack (16 series alphas), the leave-block-out solves (4 small alphas) and the fp16-pair GEMMs
+    against the reference itself, at the tolerances of test_fit_predict_matches_reference_golden."""
+    import litcoder_core_b200 as L
+
+    g0, g = load_golden("fit_predict.npz"), load_golden("fit_predict_grid20.npz")
+    X, Y, alphas = g0["X"], g0["Y"], g["alphas"].tolist()
+    kw = dict(GRID20[name])
+    tt = kw.pop("train_test")
+    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas, **kw)
+    random.seed(7)
+    np.random.seed(7)
+    model = L.NestedCVModel(model_name="ridge_regression")
+    if tt:
+        m, w, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
+    else:
+        m, w, va = model.fit_predict(X[:400], Y[:400], **common)
+    assert model.last_stats["compact_stacks"] == (3 if tt else 12)
+    ref_va, ref_r = g[f"{name}__best_alphas"], g[f"{name}__m__correlations"]
+    assert va.dtype == ref_va.dtype
+    same = np.isclose(va, ref_va, rtol=1e-6)
+    assert same.mean() >= 0.9, (name, same.mean())
+    r = np.asarray(m["correlations"], dtype=np.float64)
+    np.testing.assert_allclose(r[same], ref_r[same], atol=1e-4)  # north-star tolerance
+    assert np.abs(r[same] - ref_r[same]).max() < 3e-5  # and what fp32 actually delivers
+    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
+    wref = g[f"{name}__weights"]
+    assert w.shape == wref.shape and w.dtype == wref.dtype
+    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()

@@ -150,7 +150,7 @@ RUNS = {
 
 def _run_product(name, **extra):
     g = load_golden("fit_predict.npz")
-    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    X, Y, alphas = g["X"], g["Y"], list(g["alphas"])  # np.float64 elements, as the generator passed them
     kw = dict(RUNS[name])
     tt = kw.pop("train_test")
     common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
@@ -462,6 +462,45 @@ def test_leave_block_out_matches_chebyshev_route_on_fake_ops(monkeypatch):
         cfg = E.RidgeConfig(alphas=alphas, inner_solver="chebyshev", n_outer_folds=1)
         RidgeCVEngine(ops).fit_shard(FMat(X[:400]), FMat(Y[:400]), [FoldPlan(tr_o, te, [(np.arange(200), val)])], cfg)
         assert getattr(ops, "lbo_solved", 0) == n_lbo and ops.solver_calls == 1
+
+
+GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False),
+          "cv_grid20_single": dict(train_test=False, single_alpha=True)}
+
+
+@pytest.mark.parametrize("name", sorted(GRID20))
+@pytest.mark.parametrize("solver", ["auto", "eig"])
+def test_engine_on_the_baseline_alpha_grid_matches_reference_golden(name, solver):
+    """The reference's own output on np.logspace(-1, 8, 20) (fit_predict_grid20.npz): with the default solver the
+    inner folds run the compact stack (16 series alphas) and the leave-block-out solves (4 small alphas)."""
+    g0, g = load_golden("fit_predict.npz"), load_golden("fit_predict_grid20.npz")
+    X, Y, alphas = g0["X"], g0["Y"], g["alphas"].tolist()
+    kw = dict(GRID20[name])
+    tt = kw.pop("train_test")
+    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas,
+                  inner_solver=solver, **kw)
+    ops = FakeOps()
+    random.seed(7)
+    np.random.seed(7)
+    model = NestedCVModel("ridge_regression", ops=ops)
+    if tt:
+        m, w, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
+    else:
+        m, w, va = model.fit_predict(X[:400], Y[:400], **common)
+    # 4 small alphas per leave-block-out fold; in train/test mode one of the 3 inner folds validates on 140 of 400
+    # rows (more than half of its 260 training rows), is not downdated and keeps the direct solve
+    n_lbo_folds = 2 if tt else 12
+    assert getattr(ops, "lbo_solved", 0) == (4 * n_lbo_folds if solver == "auto" else 0)
+    ref_va = g[f"{name}__best_alphas"]
+    assert va.dtype == ref_va.dtype and va.shape == ref_va.shape
+    same = np.isclose(va, ref_va, rtol=1e-6)
+    assert same.mean() >= 0.95, (name, same.mean())
+    r = np.asarray(m["correlations"], dtype=np.float64)
+    np.testing.assert_allclose(r[same], g[f"{name}__m__correlations"][same], atol=2e-5)
+    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
+    assert m["n_significant"] == int(g[f"{name}__m__n_significant"])
+    wref = g[f"{name}__weights"]
+    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()
 
 
 def _structure_golden():

@@ -224,7 +224,7 @@ RUNS = {
 @pytest.mark.parametrize("name", sorted(RUNS))
 def test_fit_predict_matches_reference(name):
     g = load_golden("fit_predict.npz")
-    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    X, Y, alphas = g["X"], g["Y"], list(g["alphas"])  # np.float64 elements, as the generator passed them
     kw = dict(RUNS[name])
     tt = kw.pop("train_test")
     common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
@@ -282,3 +282,31 @@ def test_structure_data_matches_reference():
     cc = O.create_concatenated_data(delayed, brain_cc, stories, cfg_cc)
     for k in ("X", "Y"):
         np.testing.assert_array_equal(cc[k], g[f"cc__{k}"])
+
+
+GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False),
+          "cv_grid20_single": dict(train_test=False, single_alpha=True)}
+
+
+@pytest.mark.parametrize("name", sorted(GRID20))
+def test_fit_predict_on_the_baseline_alpha_grid_matches_reference(name):
+    """The reference's output on np.logspace(-1, 8, 20) (tests/golden/fit_predict_grid20.npz, scripts/make_golden.py
+    --grid20-only): the grid the bench runs, 16 of whose alphas lie in the Neumann-series range of the product."""
+    g0, g = load_golden("fit_predict.npz"), load_golden("fit_predict_grid20.npz")
+    X, Y, alphas = g0["X"], g0["Y"], g["alphas"].tolist()
+    kw = dict(GRID20[name])
+    tt = kw.pop("train_test")
+    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas, **kw)
+    random.seed(7)
+    np.random.seed(7)
+    if tt:
+        m, w, va = O.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
+    else:
+        m, w, va = O.fit_predict(X[:400], Y[:400], **common)
+    same = np.isclose(va, g[f"{name}__best_alphas"], rtol=1e-6)
+    assert same.mean() >= 0.95, (name, same.mean())
+    r = np.asarray(m["correlations"], dtype=np.float64)
+    np.testing.assert_allclose(r[same], g[f"{name}__m__correlations"][same], atol=2e-5)
+    assert m["n_significant"] == int(g[f"{name}__m__n_significant"])
+    wref = g[f"{name}__weights"]
+    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()
