@@ -607,9 +607,10 @@ extern "C" int lit_corr_finalize_series(const float* series_part, long ld_part, 
 extern "C" int lit_argmax_alpha(const float* corr_sum, long ld_corr, int n_alphas, long n_vox, int n_folds,
                                 const float* alphas, int32_t* best, float* alpha_out, double* col_sums, void* stream) {
   LIT_REQUIRE(n_alphas > 0 && n_folds > 0 && ld_corr >= n_vox, "argmax_alpha: bad extents");
-  if (n_vox == 0) return LIT_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  // an empty voxel shard (n_vox <= 128 * (world - 1)) still owes the all-reduce true zeros
   if (col_sums) LIT_CUDA_CHECK(cudaMemsetAsync(col_sums, 0, sizeof(double) * n_alphas, s));
+  if (n_vox == 0) return LIT_OK;
   argmax_alpha_kernel<<<blocks_for(n_vox, 256), 256, sizeof(double) * n_alphas, s>>>(
       corr_sum, ld_corr, n_alphas, n_vox, n_folds, alphas, best, alpha_out, col_sums);
   LIT_LAUNCH_CHECK();

@@ -83,6 +83,8 @@ class RidgeConfig:
     leave_block_out: bool = True
     # several ranks: each forms the outer Gram / kernel matrix over its slice of the contraction axis, one all-reduce
     row_shard_gram: bool = False
+    # keep the fold-mean inner score curves (n_alphas x V_r per outer fold) for the caller (tests: near-tie proofs)
+    record_scores: bool = False
 
 
 @dataclass
@@ -100,6 +102,7 @@ class ShardResult:
     p: list = field(default_factory=list)  # per outer fold: (V_r,) f64
     alpha: list = field(default_factory=list)  # per outer fold: (V_r,) f32
     Wt_mean: object = None  # Mat (V_r x p): fold-mean of the weights, voxel-major
+    scores: list = field(default_factory=list)  # per outer fold: (n_alphas x V_r) host array (cfg.record_scores)
     n_test: list = field(default_factory=list)
 
 
@@ -262,12 +265,27 @@ class RidgeCVEngine:
                 d["lam"], d["ticket"] = ops.syevd(d["G"]), None
         return outer, inners
 
-    @staticmethod
-    def _use_chebyshev(cfg: RidgeConfig) -> bool:
+    # The GEMM-only inner solvers invert (G + a^2 I) over the FULL spectrum: they cannot drop the directions with
+    # S <= singcutoff the way svd_wrapper does (ridge_utils.py:62-65).  That is invisible while the cutoff is far
+    # below the smallest shift (a >= 0.05 S[0] in the 'auto' case), so 'auto' keeps them only for cutoffs that small.
+    SINGCUTOFF_NEGLIGIBLE = 1e-6
+
+    @classmethod
+    def _use_chebyshev(cls, cfg: RidgeConfig) -> bool:
         if cfg.inner_solver == "chebyshev":
+            if cfg.singcutoff > cls.SINGCUTOFF_NEGLIGIBLE:
+                raise ValueError("inner_solver='chebyshev' solves over the full spectrum and cannot honour "
+                                 f"singcutoff={cfg.singcutoff!r}; use inner_solver='eig'")
             return True
         if cfg.inner_solver == "auto":
-            return bool(cfg.normalpha and len(cfg.alphas) and min(cfg.alphas) >= 0.05)
+            ok = bool(cfg.normalpha and len(cfg.alphas) and min(cfg.alphas) >= 0.05
+                      and cfg.singcutoff <= cls.SINGCUTOFF_NEGLIGIBLE)
+            if not ok and not getattr(cfg, "_warned_eig", False):
+                cfg._warned_eig = True
+                logger.warning("inner_solver='auto': alphas are not normalised / below 0.05 or singcutoff is not "
+                               "negligible -> every inner fold is decomposed with cuSOLVER syevd (about 2.7x slower "
+                               "than the GEMM-only inner solver on the BASELINE config)")
+            return ok
         return False
 
     def _scaled_alphas_sq(self, lam_max: float, alphas, cfg: RidgeConfig):
@@ -280,15 +298,17 @@ class RidgeCVEngine:
         pm, _ = ops.col_stats(X, d["val"], n_va, ddof=0)
         return ops.gather_normalize(X, d["val"], n_va, pm, None, 2, EPS)  # (n_v x p) fp32
 
+    def _check_lmax(self, lam_max: float, cfg: RidgeConfig) -> None:
+        if not (lam_max > 0.0) or not np.isfinite(lam_max):
+            raise FloatingPointError("inner-fold Gram has no positive eigenvalue (degenerate design)")
+        if min(self._scaled_alphas_sq(lam_max, cfg.alphas, cfg)) * 1e4 < lam_max:
+            raise ValueError("inner_solver='chebyshev' needs alpha^2 >= 1e-4 * lambda_max; use inner_solver='eig'")
+
     def _solve_blocks(self, X, d, alphas, cfg: RidgeConfig):
         """Owner rank: the compact solution block of a GEMM-only fold (see DeviceOps.solve_blocks)."""
         ops = self.ops
         lam_max = float(d["lmax"])
-        if not (lam_max > 0.0) or not np.isfinite(lam_max):
-            raise FloatingPointError("inner-fold Gram has no positive eigenvalue (degenerate design)")
         a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
-        if min(a2) * 1e4 < lam_max:
-            raise ValueError("inner_solver='chebyshev' needs alpha^2 >= 1e-4 * lambda_max; use inner_solver='eig'")
         block = ops.solve_blocks(ops.split(d["G"]), self._centred_val_design(X, d), len(d["val_rows"]), lam_max, a2,
                                  lbo=d.pop("lbo_args", None))
         d["G"] = None
@@ -372,6 +392,9 @@ class RidgeCVEngine:
             vals = comm.all_reduce_sum(vals)
         for (X, d), v in zip(jobs, vals):
             d["lmax"] = float(v)
+            # every rank holds every lambda_max after the all-reduce: all of them raise together (an owner-only
+            # check would leave the other ranks waiting in the broadcast of the fold's solution block)
+            self._check_lmax(float(v), cfg)
         if comm.world > 1:
             for X, d in jobs:
                 if d["owner"] == comm.rank and not d.get("lbo"):  # leave-block-out folds: see _prepare_lbo
@@ -650,6 +673,8 @@ class RidgeCVEngine:
             with ops.timed("phase_inner_cv"):
                 corr_sum, Ct_o = self._inner_scores(Xs, Ys, sp, outer, inners, alphas_f64, len(alphas), cfg)
                 alpha_v = self._select_alphas(corr_sum, len(plan.inner), alphas_f32, cfg, n_vox_total)
+                if cfg.record_scores:  # torch.stack(all_corrs).mean(dim=0), nested_cv.py:391-393
+                    res.scores.append(ops.download_matrix(corr_sum) / np.float32(len(plan.inner)))
             del corr_sum, inners
             with ops.timed("phase_outer_fit"):
                 Wt, r, p = self._outer_fit_and_score(Xs, Ys, Xts, Yts, sp, outer, Ct_o, alpha_v, cfg)

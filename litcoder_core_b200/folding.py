@@ -76,6 +76,9 @@ def group_kfold_indices(groups: Sequence, k: int) -> List[Fold]:
         raise ValueError(f"Cannot have number of splits n_splits={k} greater than the number of groups: {len(uniq)}.")
     _check_kfold(len(groups), k)
     counts = np.bincount(inv.ravel())
+    # kind="stable" as scikit-learn >= 1.7 (model_selection/_split.py:640 in this image's 1.9, which is what the
+    # golden fold sets were generated with).  The reference pins 1.6.0, whose default-kind argsort may break ties
+    # between MANY equal-sized groups differently (introsort is unstable beyond 16 elements).
     by_size = np.argsort(counts, kind="stable")[::-1]
     load = np.zeros(k)
     fold_of_group = np.empty(len(uniq), dtype=np.int64)

@@ -171,6 +171,8 @@ class NestedCVModel:
         self._comm = comm
         self.last_timings: Dict[str, float] = {}  # per-phase milliseconds of the most recent fit
         self.last_stats: Dict[str, Any] = {}
+        self.last_fold_results: Dict[str, np.ndarray] = {}
+        self.record_inner_scores = False  # True: last_fold_results["inner_scores"] = (folds x alphas x V) score curves
 
     # -- plumbing --------------------------------------------------------------------------------
     @staticmethod
@@ -298,6 +300,7 @@ class NestedCVModel:
             raise ValueError(f"Unknown corr_precision: {corr_precision}")
         cfg.corr_precision = corr_precision
         cfg.row_shard_gram = bool(row_shard_gram)
+        cfg.record_scores = bool(self.record_inner_scores)
         cfg.voxel_gemm_precision = os.environ.get("LIT_VOXEL_GEMM", corr_precision)  # development override
         cfg.series_moments = os.environ.get("LIT_SERIES_MOMENTS", "1") != "0"  # development override
         cfg.leave_block_out = os.environ.get("LIT_LEAVE_BLOCK_OUT", "1") != "0"  # development override
@@ -328,10 +331,13 @@ class NestedCVModel:
             r_f = np.stack([ops.download(v)[: c1 - c0] for v in res.r]).astype(np.float32)
             p_f = np.stack([ops.download(v)[: c1 - c0] for v in res.p]).astype(np.float64)
             a_f = np.stack([ops.download(v)[: c1 - c0] for v in res.alpha]).astype(np.float32)
+            scores = np.stack(res.scores) if res.scores else None
             if comm.world > 1:
                 r_f = comm.all_gather_concat(r_f, counts)
                 p_f = comm.all_gather_concat(p_f, counts)
                 a_f = comm.all_gather_concat(a_f, counts)
+                if scores is not None:
+                    scores = comm.all_gather_concat(scores, counts)
             t_w0 = time.perf_counter()
             Wd = engine.weights_matrix(res)  # (p x V_rank) float32 on the device
             if device_outputs:
@@ -363,6 +369,11 @@ class NestedCVModel:
                            axis=0)  # nested_cv.py:293
             metrics = _metrics(corr.astype(np.float64), comb_p, padj, sig, best, majority)
 
+        # per-outer-fold vectors of the most recent fit (extension: what the parity proofs in tests/ compare fold by
+        # fold; the reference only returns their means)
+        self.last_fold_results = {"alphas": a_f, "correlations": r_f, "p_values": p_f, "masks": np.stack(masks)}
+        if scores is not None:
+            self.last_fold_results["inner_scores"] = scores
         t_stats_end = time.perf_counter()
         self.last_timings = ops.timings()
         self.last_timings["wall_ms"] = (time.perf_counter() - t_start) * 1e3

@@ -555,11 +555,14 @@ def _normalise(Xtr, Ytr, Xte, Yte, nf, nt, eps=1e-8):
 def fit_predict(features, targets, X_test=None, y_test=None, groups=None, folding_type="chunked", n_outer_folds=5,
                 n_inner_folds=5, chunk_length=20, alphas=None, alpha_fdr=0.05, single_alpha=False, normalpha=True,
                 use_corr=True, normalize_features=False, normalize_targets=False, singcutoff=1e-10,
-                vectorised_stats=False):
+                vectorised_stats=False, details=None):
     """Restatement of NestedCVModel.fit_predict; returns (metrics, weights, best_alphas).
 
     vectorised_stats=True swaps the per-voxel SciPy loops for their closed forms (identical
-    statistics, needed to keep large-V test cases within seconds)."""
+    statistics, needed to keep large-V test cases within seconds).
+    details: optional list; receives one dict per outer fold (one in train/test mode) with what the parity proofs
+    of tests/parity.py need: the fold's (normalised) arrays, the fold-mean inner score curves `mean_corr`
+    (n_alphas x V), the selected alphas, the test r / p and the weights."""
     if alphas is None:
         alphas = np.logspace(-1, 8, 10)
     X = np.asarray(features).astype(F32)
@@ -576,9 +579,13 @@ def fit_predict(features, targets, X_test=None, y_test=None, groups=None, foldin
         if normalize_features or normalize_targets:
             X, Y, Xt, Yt = _normalise(X, Y, Xt, Yt, normalize_features, normalize_targets)
         splits = create_folds(len(X), folding_type, n_inner_folds, chunk_length, groups)
-        best = find_best_alphas(X, Y, splits, alphas, single_alpha, normalpha, use_corr, singcutoff)
+        best, mean_corr = find_best_alphas(X, Y, splits, alphas, single_alpha, normalpha, use_corr, singcutoff,
+                                           return_corrs=True)
         wt = ridge_weights(X, Y, best, singcutoff=singcutoff, normalpha=normalpha)
         r, p = stats(Yt, Xt @ wt)
+        if details is not None:
+            details.append(dict(Xtr=X, Ytr=Y, Xte=Xt, Yte=Yt, mean_corr=mean_corr, best=best, r=np.asarray(r),
+                                p=np.asarray(p), wt=wt))
         sig, padj = fdr_bh(p, alpha_fdr)
         return metrics_train_test(r, p, padj, sig, best, int(np.sum(sig))), wt, best
 
@@ -596,11 +603,15 @@ def fit_predict(features, targets, X_test=None, y_test=None, groups=None, foldin
             inner = create_folds(len(tr), "group", n_inner_folds, groups=[groups[i] for i in tr])
         else:
             inner = create_folds(len(tr), folding_type, n_inner_folds, chunk_length)
-        best = find_best_alphas(Xtr, Ytr, inner, alphas, single_alpha, normalpha, use_corr, singcutoff)
+        best, mean_corr = find_best_alphas(Xtr, Ytr, inner, alphas, single_alpha, normalpha, use_corr, singcutoff,
+                                           return_corrs=True)
         valphas.append(best)
         wt = ridge_weights(Xtr, Ytr, best, singcutoff=singcutoff, normalpha=normalpha)
         weights.append(wt)
         r, p = stats(Yte, Xte @ wt)
+        if details is not None:
+            details.append(dict(Xtr=Xtr, Ytr=Ytr, Xte=Xte, Yte=Yte, mean_corr=mean_corr, best=best, r=np.asarray(r),
+                                p=np.asarray(p), wt=wt))
         scores.append(r)
         pvals.append(p)
         masks.append(fdr_bh(p, alpha_fdr)[0])

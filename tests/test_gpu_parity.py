@@ -11,6 +11,7 @@ import pytest
 
 from conftest import load_golden
 from oracle import ridge_oracle as O
+from parity import prove_fit_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -245,6 +246,51 @@ def test_statistics_kernels(ops):
     assert out[0] == 1.0 and out[1] == 0.0
 
 
+def test_empty_voxel_shard_single_alpha(ops):
+    """A rank whose voxel shard is empty (n_vox <= 128 * (world - 1): shard_bounds rounds blocks up to 128) still
+    owes the single_alpha all-reduce TRUE zeros (lit_argmax_alpha zeroes col_sums before its n_vox == 0 return),
+    and the whole engine runs on a zero-column shard next to a full one."""
+    import torch
+
+    from litcoder_core_b200.engine import FoldPlan, RidgeConfig, RidgeCVEngine
+
+    alphas = ops.upload_vector(np.logspace(-1, 3, 6).astype(np.float32), "f32")
+    for _ in range(3):  # fresh (uninitialised) allocations every time
+        junk = torch.full((64,), float("nan"), dtype=torch.float64, device=ops.device)
+        del junk
+        _, _, sums = ops.argmax_alpha(ops.empty(6, 0), 3, alphas, want_sums=True)
+        assert (sums.cpu().numpy()[:6] == 0.0).all()
+
+    class TwoRankSums:  # rank 1 of 2 with an empty shard: the all-reduce adds rank 0's sums
+        rank, world = 1, 2
+
+        def __init__(self, other):
+            self.other = other
+
+        def all_reduce_sum(self, arr):
+            return arr + self.other if arr.shape == self.other.shape else arr
+
+        def all_gather_concat(self, arr, counts=None):
+            return arr
+
+        def broadcast_inplace(self, buffers, src):
+            pass
+
+        def all_reduce_sum_inplace(self, buffers):
+            pass
+
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((120, 6)).astype(np.float32)
+    tr, te = np.arange(90), np.arange(90, 120)
+    plan = FoldPlan(tr, te, [(tr[:60], tr[60:]), (tr[30:], tr[:30])])
+    cfg = RidgeConfig(alphas=list(np.logspace(-1, 3, 6)), single_alpha=True, inner_solver="eig")
+    other = np.array([0.1, 0.9, 0.3, 0.2, 0.1, 0.0]) * 50
+    eng = RidgeCVEngine(ops, TwoRankSums(other))
+    res = eng.fit_shard(ops.upload_matrix(X), ops.empty(120, 0), [plan], cfg, n_vox_total=50)
+    ops.check_eig()
+    assert len(res.alpha) == 1  # ran through on zero voxels; the alpha is rank 0's argmax (slot 1)
+
+
 def test_pearson_pvalues_match_scipy(ops):
     import torch
 
@@ -323,34 +369,20 @@ RUNS = {
 
 @pytest.mark.parametrize("name", sorted(RUNS))
 def test_fit_predict_matches_reference_golden(ops, name):
+    """Whole fits against the per-fold observations of the UNMODIFIED reference (fit_predict_folds.npz): every alpha
+    that differs is proven a near-tie on the reference's own score curves, r / weights / BH masks are compared on ALL
+    voxels (tests/parity.py)."""
     import litcoder_core_b200 as L
+    from test_host_logic import _golden_args, check_against_reference_golden
 
-    g = load_golden("fit_predict.npz")
-    X, Y, alphas = g["X"], g["Y"], list(g["alphas"])  # np.float64 elements, as the generator passed them
-    kw = dict(RUNS[name])
-    tt = kw.pop("train_test")
-    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
-    common.update(kw)
+    g, X, Y, test, common = _golden_args(name)
     random.seed(7)
     np.random.seed(7)
     model = L.NestedCVModel(model_name="ridge_regression")
-    if tt:
-        m, w, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
-    else:
-        m, w, va = model.fit_predict(X[:400], Y[:400], **common)
+    m, w, va = model.fit_predict(X, Y, **test, **common)
     assert model.last_stats["launches"] > 0
-    ref_va, ref_r = g[f"{name}__best_alphas"], g[f"{name}__m__correlations"]
-    assert va.dtype == ref_va.dtype
-    same = np.isclose(va, ref_va, rtol=1e-6)
-    assert same.mean() >= (0.7 if name == "tt_rsq" else 0.9), (name, same.mean())
-    r = np.asarray(m["correlations"], dtype=np.float64)
-    np.testing.assert_allclose(r[same], ref_r[same], atol=1e-4)  # north-star tolerance
-    assert np.abs(r[same] - ref_r[same]).max() < 3e-5  # and what fp32 actually delivers
-    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
-    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
-    wref = g[f"{name}__weights"]
-    assert w.shape == wref.shape and w.dtype == wref.dtype
-    assert np.abs(w[:, same] - wref[:, same]).max() / np.abs(wref).max() < 1e-4
+    info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
+    assert info["disagreeing_alphas"] <= (0.3 if name == "tt_rsq" else 0.1) * info["voxel_folds"], info
 
 
 def _synthetic(rng, N, p, V, frac=0.3, noise=3.0):
@@ -374,21 +406,13 @@ def test_fit_predict_matches_oracle_midsize(ops):
     Y[:, 8] = Y[:, 9]
     kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 4, 12))
     random.seed(3)
-    m, w, a = L.fit_nested_cv(features=X, targets=Y, **kw)
-    random.seed(3)
-    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
-    same = np.isclose(a, ao, rtol=1e-6)
-    same[[5, 6]] = False
-    assert same.mean() > 0.97, same.mean()
-    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
-    assert np.abs(r[same] - ro[same]).max() < 1e-4
+    model = L.NestedCVModel("ridge_regression")
+    m, w, a = model.fit_predict(X, Y, **kw)
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 3, max_ambiguous=4, **kw)
+    assert info["disagreeing_alphas"] <= 0.03 * info["voxel_folds"], info
+    r = np.asarray(m["correlations"])
     assert r[5] == 0.0 and r[6] == 0.0 and m["p_values"][5] == 1.0
     assert r[8] == r[9]
-    assert np.abs(w[:, same] - wo[:, same]).max() < 1e-4 * np.abs(wo).max()
-    # significance: exact except for voxels whose alpha differs or that sit on the BH threshold
-    sig, sigo = np.asarray(m["significant_mask"]), np.asarray(mo["significant_mask"])
-    assert (sig != sigo)[same].sum() <= 2
-    assert abs(m["n_significant"] - mo["n_significant"]) <= 2 + (~same).sum()
 
 
 def test_full_width_properties(ops):
@@ -405,7 +429,10 @@ def test_full_width_properties(ops):
     alphas = np.logspace(-1, 8, 20)
     kw = dict(n_inner_folds=5, chunk_length=20, alphas=alphas)
     random.seed(5)
-    m, w, a = L.fit_nested_cv(features=X[:ntr], targets=Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], **kw)
+    model = L.NestedCVModel("ridge_regression")
+    model.record_inner_scores = True
+    m, w, a = model.fit_predict(X[:ntr], Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], **kw)
+    curves = model.last_fold_results["inner_scores"][0].astype(np.float64)  # (alphas x V) fold-mean inner scores
     r = np.asarray(m["correlations"])
     assert w.shape == (p, V) and np.isfinite(w).all() and (np.abs(r) <= 1).all()
     assert set(np.unique(a)).issubset(set(alphas.astype(np.float32)))
@@ -413,15 +440,21 @@ def test_full_width_properties(ops):
     scale = rng.uniform(0.5, 20.0, V).astype(np.float32)
     Y2 = Y[:, perm] * scale[None, :]
     random.seed(5)
-    m2, w2, a2 = L.fit_nested_cv(features=X[:ntr], targets=Y2[:ntr], X_test=X[ntr:], y_test=Y2[ntr:], **kw)
+    m2, w2, a2 = model.fit_predict(X[:ntr], Y2[:ntr], X_test=X[ntr:], y_test=Y2[ntr:], **kw)
+    curves2 = model.last_fold_results["inner_scores"][0].astype(np.float64)
     r2 = np.asarray(m2["correlations"])
-    same = a2 == a[perm]
-    # null voxels have flat inner-CV curves: the reference's own fp32 arithmetic re-selects ~9 % of the alphas
-    # when the responses are merely rescaled (oracle self-agreement 0.91 on data of this kind)
-    assert same.mean() > 0.8
+    # scores are invariant to voxel order and response scale up to fp32 rounding ...
+    assert np.abs(curves2 - curves[:, perm]).max() < 2e-6
+    # ... so an alpha may only change where the first run's own curve rates the two choices within that noise
+    idx1 = np.argmin(np.abs(np.log(alphas)[None, :] - np.log(a[perm].astype(np.float64))[:, None]), axis=1)
+    idx2 = np.argmin(np.abs(np.log(alphas)[None, :] - np.log(a2.astype(np.float64))[:, None]), axis=1)
+    dis = np.nonzero(idx1 != idx2)[0]
+    gap = curves[idx1[dis], perm[dis]] - curves[idx2[dis], perm[dis]]
+    assert len(dis) == 0 or gap.max() < 4e-6, (len(dis), gap.max())
+    same = idx1 == idx2
     assert np.abs(r2[same] - r[perm][same]).max() < 1e-4
-    assert abs(m2["n_significant"] - m["n_significant"]) <= 3
     np.testing.assert_allclose(w2[:, same], (w[:, perm] * scale[None, :])[:, same], rtol=0, atol=2e-4 * np.abs(w2).max())
+    assert abs(m2["n_significant"] - m["n_significant"]) <= max(3, len(dis))
 
 
 def test_full_width_matches_oracle(ops):
@@ -436,17 +469,12 @@ def test_full_width_matches_oracle(ops):
     ntr = 7520
     kw = dict(n_inner_folds=5, chunk_length=20, alphas=np.logspace(-1, 8, 20))
     random.seed(9)
-    m, w, a = L.fit_nested_cv(features=X[:ntr], targets=Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], **kw)
-    random.seed(9)
-    mo, wo, ao = O.fit_predict(X[:ntr], Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], vectorised_stats=True, **kw)
-    same = np.isclose(a, ao, rtol=1e-6)
-    same[7] = False
-    assert same.mean() > 0.9, same.mean()
-    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
-    assert np.abs(r[same] - ro[same]).max() < 1e-4, np.abs(r[same] - ro[same]).max()
-    assert np.abs(w[:, same] - wo[:, same]).max() < 2e-4 * np.abs(wo).max()
-    assert abs(m["n_significant"] - mo["n_significant"]) <= 1 + (~same).sum()
-    assert r[7] == 0.0 and m["p_values"][7] == 1.0
+    model = L.NestedCVModel("ridge_regression")
+    m, w, a = model.fit_predict(X[:ntr], Y[:ntr], X_test=X[ntr:], y_test=Y[ntr:], **kw)
+    info = prove_fit_parity(model.last_fold_results, m, w, X[:ntr], Y[:ntr], 9, X_test=X[ntr:], y_test=Y[ntr:],
+                            w_tol=2e-4, max_ambiguous=3, **kw)
+    assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], info
+    assert m["correlations"][7] == 0.0 and m["p_values"][7] == 1.0
 
 
 def test_wide_design_matches_oracle(ops):
@@ -458,14 +486,10 @@ def test_wide_design_matches_oracle(ops):
     N, p, V = 2226, 3072, 1000
     X, Y = _synthetic(rng, N, p, V, frac=0.5, noise=4.0)
     kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 8, 20), folding_type="kfold_trimmed")
-    m, w, a = L.fit_nested_cv(features=X, targets=Y, **kw)
-    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
-    same = np.isclose(a, ao, rtol=1e-6)
-    assert same.mean() > 0.9, same.mean()
-    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
-    assert np.abs(r[same] - ro[same]).max() < 1e-4, np.abs(r[same] - ro[same]).max()
-    assert np.abs(w[:, same] - wo[:, same]).max() < 2e-4 * np.abs(wo).max()
-    assert abs(m["n_significant"] - mo["n_significant"]) <= 2 + (~same).sum()
+    model = L.NestedCVModel("ridge_regression")
+    m, w, a = model.fit_predict(X, Y, **kw)
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 0, w_tol=2e-4, max_ambiguous=4, **kw)
+    assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], info
 
 
 @pytest.mark.parametrize("name", ["tall", "dupcol", "wide"])
@@ -563,16 +587,15 @@ def test_fit_predict_eig_solver_matches_reference_golden(ops):
     very small alphas; the default golden tests above exercise the GEMM-only route."""
     import litcoder_core_b200 as L
 
-    g = load_golden("fit_predict.npz")
-    X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
+    from test_host_logic import _golden_args, check_against_reference_golden
+
+    g, X, Y, test, common = _golden_args("cv_default")
     random.seed(7)
-    m, w, va = L.NestedCVModel("ridge_regression").fit_predict(X[:400], Y[:400], folding_type="chunked", n_outer_folds=4,
-                                                               n_inner_folds=3, chunk_length=10, alphas=alphas,
-                                                               inner_solver="eig")
-    ref_va, ref_r = g["cv_default__best_alphas"], g["cv_default__m__correlations"]
-    same = np.isclose(va, ref_va, rtol=1e-6)
-    assert same.mean() >= 0.9
-    assert np.abs(np.asarray(m["correlations"])[same] - ref_r[same]).max() < 3e-5
+    np.random.seed(7)
+    model = L.NestedCVModel("ridge_regression")
+    m, w, va = model.fit_predict(X, Y, inner_solver="eig", **common)
+    info = check_against_reference_golden("cv_default", model.last_fold_results, m, w, va)
+    assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], info
 
 
 @pytest.mark.parametrize("N,p,V,kw", [
@@ -597,22 +620,21 @@ def test_ragged_shapes_and_fold_types_match_oracle(ops, N, p, V, kw):
         kw["groups"] = np.repeat(np.arange(16), 10)[:N]
     random.seed(4)
     np.random.seed(4)
-    m, w, a = L.fit_nested_cv(features=X, targets=Y, **kw)
-    random.seed(4)
-    np.random.seed(4)
-    mo, wo, ao = O.fit_predict(X, Y, **kw)
+    model = L.NestedCVModel("ridge_regression")
+    m, w, a = model.fit_predict(X, Y, **kw)
     assert w.shape == (p, V) and a.shape == (V,) and len(m["correlations"]) == V
-    same = np.isclose(a, ao, rtol=1e-6)
-    r, ro = np.asarray(m["correlations"]), np.asarray(mo["correlations"], dtype=np.float64)
     if p == 1:
-        # one feature: the prediction is a multiple of x for every alpha, so all alphas tie exactly and the
-        # selection is rounding noise in both implementations -- but r does not depend on it
-        assert np.abs(r - ro).max() < 1e-4
+        # one feature: the prediction is a multiple of x for every alpha, so all alphas tie exactly (the score
+        # curves are flat to rounding) and the selection is rounding noise in both implementations -- but r does
+        # not depend on it
+        random.seed(4)
+        np.random.seed(4)
+        mo, wo, ao = O.fit_predict(X, Y, **kw)
+        assert np.abs(np.asarray(m["correlations"]) - np.asarray(mo["correlations"], dtype=np.float64)).max() < 1e-4
         return
-    assert same.mean() >= 0.75, same.mean()
-    assert np.abs(r[same] - ro[same]).max() < 1e-4
-    assert np.abs(w[:, same] - wo[:, same]).max() <= 2e-4 * max(np.abs(wo).max(), 1e-6)
-    assert set(m) == set(mo)
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 4, w_tol=2e-4, **kw)
+    assert info["disagreeing_alphas"] <= 0.25 * info["voxel_folds"], info
+    assert set(m) == set(info["oracle"][0])
 
 
 def test_input_validation_and_dtypes(ops):
@@ -810,18 +832,16 @@ def test_series_moments_agree_on_fit(ops, monkeypatch):
         monkeypatch.setenv("LIT_SERIES_MOMENTS", flag)
         for prec in ("tf32x3", "f16x3"):
             random.seed(3)
-            m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, corr_precision=prec,
-                                                                             inner_solver="chebyshev", **kw)
-            out[flag, prec] = (np.asarray(m["correlations"]), w, np.asarray(a))
+            model = NestedCVModel("ridge_regression", ops=ops)
+            m, w, a = model.fit_predict(X, Y, corr_precision=prec, inner_solver="chebyshev", **kw)
+            out[flag, prec] = (np.asarray(m["correlations"]), w, np.asarray(a), model.last_fold_results, m)
     for prec in ("tf32x3", "f16x3"):
         same = out["0", prec][2] == out["1", prec][2]
         assert same.mean() > 0.97, same.mean()
         assert np.abs(out["0", prec][0][same] - out["1", prec][0][same]).max() < 2e-5
-    random.seed(3)
-    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
-    same = np.isclose(out["1", "f16x3"][2], ao)
-    assert same.mean() > 0.9, same.mean()
-    assert np.abs(out["1", "f16x3"][0][same] - np.asarray(mo["correlations"], dtype=np.float64)[same]).max() < 1e-4
+    for key in out:  # every variant is held to the oracle by the full proof
+        info = prove_fit_parity(out[key][3], out[key][4], out[key][1], X, Y, 3, max_ambiguous=4, **kw)
+        assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], (key, info)
 
 
 def test_leave_block_out_solver_kernels(ops):
@@ -962,27 +982,13 @@ def test_fit_predict_on_the_baseline_alpha_grid_matches_reference_golden(ops, na
     against the reference itself, at the tolerances of test_fit_predict_matches_reference_golden."""
     import litcoder_core_b200 as L
 
-    g0, g = load_golden("fit_predict.npz"), load_golden("fit_predict_grid20.npz")
-    X, Y, alphas = g0["X"], g0["Y"], g["alphas"].tolist()
-    kw = dict(GRID20[name])
-    tt = kw.pop("train_test")
-    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas, **kw)
+    from test_host_logic import _golden_args, check_against_reference_golden
+
+    g, X, Y, test, common = _golden_args(name)
     random.seed(7)
     np.random.seed(7)
     model = L.NestedCVModel(model_name="ridge_regression")
-    if tt:
-        m, w, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
-    else:
-        m, w, va = model.fit_predict(X[:400], Y[:400], **common)
-    assert model.last_stats["compact_stacks"] == (3 if tt else 12)
-    ref_va, ref_r = g[f"{name}__best_alphas"], g[f"{name}__m__correlations"]
-    assert va.dtype == ref_va.dtype
-    same = np.isclose(va, ref_va, rtol=1e-6)
-    assert same.mean() >= 0.9, (name, same.mean())
-    r = np.asarray(m["correlations"], dtype=np.float64)
-    np.testing.assert_allclose(r[same], ref_r[same], atol=1e-4)  # north-star tolerance
-    assert np.abs(r[same] - ref_r[same]).max() < 3e-5  # and what fp32 actually delivers
-    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
-    wref = g[f"{name}__weights"]
-    assert w.shape == wref.shape and w.dtype == wref.dtype
-    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()
+    m, w, va = model.fit_predict(X, Y, **test, **common)
+    assert model.last_stats["compact_stacks"] == (3 if test else 12)
+    info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
+    assert info["disagreeing_alphas"] <= 0.05 * info["voxel_folds"], info

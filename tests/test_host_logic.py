@@ -9,6 +9,7 @@ import pytest
 
 from conftest import load_golden, unpack_folds
 from fake_ops import FakeOps
+from parity import prove_fit_parity
 from oracle import ridge_oracle as O
 
 import litcoder_core_b200 as L
@@ -164,27 +165,61 @@ def _run_product(name, **extra):
     return g, model.fit_predict(X[:400], Y[:400], **common)
 
 
-@pytest.mark.parametrize("name", sorted(RUNS))
-def test_engine_on_fake_ops_matches_reference_golden(name):
-    g, (m, w, va) = _run_product(name)
-    ref_va = g[f"{name}__best_alphas"]
-    ref_r = g[f"{name}__m__correlations"]
+GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False),
+          "cv_grid20_single": dict(train_test=False, single_alpha=True)}
+
+
+def _golden_args(name):
+    """(golden file of the run, X, Y, test-set kwargs, fit_predict kwargs) of one of the 12 golden runs."""
+    g0 = load_golden("fit_predict.npz")
+    X, Y = g0["X"], g0["Y"]
+    if name in GRID20:
+        g, kw = load_golden("fit_predict_grid20.npz"), dict(GRID20[name])
+        alphas = g["alphas"].tolist()
+    else:
+        g, kw = g0, dict(RUNS[name])
+        alphas = list(g0["alphas"])  # np.float64 elements, as the generator passed them
+    tt = kw.pop("train_test")
+    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
+    common.update(kw)
+    test = dict(X_test=X[400:], y_test=Y[400:]) if tt else {}
+    return g, X[:400], Y[:400], test, common
+
+
+def check_against_reference_golden(name, fold_results, m, w, va, max_ambiguous=3):
+    """Shared by the oracle, CPU (fake ops) and GPU suites: parity PROOF (tests/parity.py) against the per-fold
+    observations of the unmodified reference (fit_predict_folds.npz), plus the return contract."""
+    from parity import golden_folds, prove_fit_parity
+
+    g, X, Y, test, common = _golden_args(name)
+    gf = load_golden("fit_predict_folds.npz")
+    ref_va, ref_r = g[f"{name}__best_alphas"], g[f"{name}__m__correlations"]
+    np.testing.assert_array_equal(gf[f"{name}__best_alphas"], ref_va)  # the recorded folds belong to this very run
     assert va.dtype == ref_va.dtype and va.shape == ref_va.shape
+    info = prove_fit_parity(fold_results, m, w, X, Y, 7, ref_folds=golden_folds(gf, name), max_ambiguous=max_ambiguous,
+                            **test, **common)
     same = np.isclose(va, ref_va, rtol=1e-6)
-    assert same.mean() >= (0.7 if name == "tt_rsq" else 0.9), (name, same.mean())
     r = np.asarray(m["correlations"], dtype=np.float64)
-    np.testing.assert_allclose(r[same], ref_r[same], atol=2e-5)
-    np.testing.assert_allclose(r, ref_r, atol=5e-3)
+    np.testing.assert_allclose(r[same], ref_r[same], atol=3e-5)
     assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
     assert list(m.keys())[:5] == ["median_score", "mean_score", "std_score", "min_score", "max_score"]
-    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
-    np.testing.assert_allclose(np.asarray(m["p_values"])[same], g[f"{name}__m__p_values"][same], rtol=2e-2, atol=1e-12)
-    if f"{name}__m__majority_significant_mask" in g.files:
-        assert np.mean(np.asarray(m["majority_significant_mask"]) == g[f"{name}__m__majority_significant_mask"]) > 0.97
     wref = g[f"{name}__weights"]
     assert w.shape == wref.shape and w.dtype == wref.dtype
-    err = np.abs(w[:, same] - wref[:, same]).max() / np.abs(wref).max()
-    assert err < 1e-4, (name, err)
+    if info["disagreeing_alphas"] == 0:  # then everything must match the reference's returned values directly
+        assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= info["ambiguous_bh"]
+        assert np.abs(w - wref).max() < 1e-4 * np.abs(wref).max()
+    return info
+
+
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_engine_on_fake_ops_matches_reference_golden(name):
+    g, X, Y, test, common = _golden_args(name)
+    random.seed(7)
+    np.random.seed(7)
+    model = NestedCVModel("ridge_regression", ops=FakeOps())
+    m, w, va = model.fit_predict(X, Y, **test, **common)
+    info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
+    assert info["disagreeing_alphas"] <= (0.3 if name == "tt_rsq" else 0.1) * info["voxel_folds"]
 
 
 @pytest.mark.parametrize("name", ["tt_default", "cv_default"])
@@ -244,20 +279,18 @@ def test_engine_edge_cases_on_fake_ops():
     Y[:, 8] = 2.5
     Y[:, 9] = Y[:, 10]
     random.seed(1)
-    m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(
-        X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6))
+    model = NestedCVModel("ridge_regression", ops=FakeOps())
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6))
+    m, w, a = model.fit_predict(X, Y, **kw)
     r = np.asarray(m["correlations"])
     assert np.isfinite(r).all() and np.isfinite(w).all()
     assert r[7] == 0.0 and r[8] == 0.0  # pearsonr -> NaN -> 0.0 (nested_cv.py:435)
     assert m["p_values"][7] == 1.0 and m["p_values"][8] == 1.0  # all folds 1.0 -> Fisher shortcut 1.0
     assert r[9] == r[10] and a[9] == a[10]
     assert not m["significant_mask"][7]
-    random.seed(1)
-    mo, wo, ao = O.fit_predict(X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6))
-    same = np.isclose(a, ao)
-    same[[7, 8]] = False  # the reference picks alphas for constant voxels from rounding noise
-    assert same.mean() > 0.8
-    np.testing.assert_allclose(r[same], np.asarray(mo["correlations"], dtype=np.float64)[same], atol=5e-5)
+    # every alpha that differs from the oracle's is a proven near-tie; r, weights, masks on ALL voxels (parity.py)
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 1, w_tol=2e-4, **kw)
+    assert info["disagreeing_alphas"] <= 0.2 * info["voxel_folds"]
 
 
 # ------------------------------------------------------------------------------------------ stand-alone ridge kernels
@@ -336,7 +369,8 @@ def test_dual_form_matches_oracle_on_fake_ops(N, p, label):
     kw = dict(n_outer_folds=5, n_inner_folds=4, chunk_length=5, alphas=np.logspace(-1, 3, 6))
     random.seed(2)
     ops = FakeOps()
-    m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, **kw)
+    model = NestedCVModel("ridge_regression", ops=ops)
+    m, w, a = model.fit_predict(X, Y, **kw)
     n_o = (N // 5 // 5) * 5 * 4
     if label == "dual everywhere":
         assert max(ops.eig_sizes) <= n_o < p
@@ -344,13 +378,8 @@ def test_dual_form_matches_oracle_on_fake_ops(N, p, label):
         assert set(ops.eig_sizes) == {p}
     else:
         assert p in ops.eig_sizes and min(ops.eig_sizes) < p
-    random.seed(2)
-    mo, wo, ao = O.fit_predict(X, Y, **kw)
-    same = np.isclose(a, ao)
-    assert same.mean() > 0.85, (label, same.mean())
-    np.testing.assert_allclose(np.asarray(m["correlations"])[same], np.asarray(mo["correlations"], dtype=np.float64)[same],
-                               atol=5e-5)
-    assert np.abs(w[:, same] - wo[:, same]).max() <= 2e-4 * np.abs(wo).max()
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 2, w_tol=2e-4, **kw)
+    assert info["disagreeing_alphas"] <= 0.15 * info["voxel_folds"], (label, info["disagreeing_alphas"])
     # and the dual path agrees with the primal path on the same problem
     orig = E.RidgeConfig.__init__
 
@@ -473,34 +502,19 @@ GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False
 def test_engine_on_the_baseline_alpha_grid_matches_reference_golden(name, solver):
     """The reference's own output on np.logspace(-1, 8, 20) (fit_predict_grid20.npz): with the default solver the
     inner folds run the compact stack (16 series alphas) and the leave-block-out solves (4 small alphas)."""
-    g0, g = load_golden("fit_predict.npz"), load_golden("fit_predict_grid20.npz")
-    X, Y, alphas = g0["X"], g0["Y"], g["alphas"].tolist()
-    kw = dict(GRID20[name])
-    tt = kw.pop("train_test")
-    common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas,
-                  inner_solver=solver, **kw)
+    g, X, Y, test, common = _golden_args(name)
+    tt = bool(test)
     ops = FakeOps()
     random.seed(7)
     np.random.seed(7)
     model = NestedCVModel("ridge_regression", ops=ops)
-    if tt:
-        m, w, va = model.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
-    else:
-        m, w, va = model.fit_predict(X[:400], Y[:400], **common)
+    m, w, va = model.fit_predict(X, Y, inner_solver=solver, **test, **common)
     # 4 small alphas per leave-block-out fold; in train/test mode one of the 3 inner folds validates on 140 of 400
     # rows (more than half of its 260 training rows), is not downdated and keeps the direct solve
     n_lbo_folds = 2 if tt else 12
     assert getattr(ops, "lbo_solved", 0) == (4 * n_lbo_folds if solver == "auto" else 0)
-    ref_va = g[f"{name}__best_alphas"]
-    assert va.dtype == ref_va.dtype and va.shape == ref_va.shape
-    same = np.isclose(va, ref_va, rtol=1e-6)
-    assert same.mean() >= 0.95, (name, same.mean())
-    r = np.asarray(m["correlations"], dtype=np.float64)
-    np.testing.assert_allclose(r[same], g[f"{name}__m__correlations"][same], atol=2e-5)
-    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
-    assert m["n_significant"] == int(g[f"{name}__m__n_significant"])
-    wref = g[f"{name}__weights"]
-    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()
+    info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
+    assert info["disagreeing_alphas"] <= 0.05 * info["voxel_folds"]
 
 
 def _structure_golden():

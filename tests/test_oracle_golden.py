@@ -221,6 +221,34 @@ RUNS = {
 }
 
 
+def _prove_oracle_against_reference(name, g, X, Y, test, common):
+    """The oracle held to the per-fold observations of the unmodified reference (fit_predict_folds.npz) by the same
+    proof the product has to pass (tests/parity.py): every alpha that differs is a near-tie on the REFERENCE's own
+    score curves, r on all voxels, BH masks exact off the threshold band."""
+    from parity import fold_results_of_oracle, golden_folds, prove_fit_parity
+
+    gf = load_golden("fit_predict_folds.npz")
+    details = []
+    random.seed(7)
+    np.random.seed(7)
+    m, w, va = O.fit_predict(X, Y, details=details, **test, **common)  # SciPy loops, as the reference
+    ref_va = g[f"{name}__best_alphas"]
+    np.testing.assert_array_equal(gf[f"{name}__best_alphas"], ref_va)
+    assert va.dtype == ref_va.dtype and va.shape == ref_va.shape
+    info = prove_fit_parity(fold_results_of_oracle(details, common.get("alpha_fdr", 0.05)), m, w, X, Y, 7,
+                            ref_folds=golden_folds(gf, name), max_ambiguous=2, **test, **common)
+    same = np.isclose(va, ref_va, rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(m["correlations"], dtype=np.float64)[same], g[f"{name}__m__correlations"][same],
+                               atol=2e-5)
+    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
+    wref = g[f"{name}__weights"]
+    assert w.shape == wref.shape and w.dtype == wref.dtype
+    if info["disagreeing_alphas"] == 0:
+        assert m["n_significant"] == int(g[f"{name}__m__n_significant"])
+        assert np.abs(w - wref).max() < 1e-4 * np.abs(wref).max()
+    return info
+
+
 @pytest.mark.parametrize("name", sorted(RUNS))
 def test_fit_predict_matches_reference(name):
     g = load_golden("fit_predict.npz")
@@ -229,28 +257,11 @@ def test_fit_predict_matches_reference(name):
     tt = kw.pop("train_test")
     common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
     common.update(kw)
-    random.seed(7)
-    np.random.seed(7)
-    if tt:
-        m, w, va = O.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
-    else:
-        m, w, va = O.fit_predict(X[:400], Y[:400], **common)
-    ref_va = g[f"{name}__best_alphas"]
-    ref_r = g[f"{name}__m__correlations"]
-    # alpha selection: identical except where fp32 noise decides between near-tied alphas
-    agree = np.mean(np.isclose(va, ref_va, rtol=1e-6))
-    # (the R^2 metric takes sqrt(|Rsq|) of values that are pure rounding noise for null voxels,
-    #  so many more voxels are near-ties there)
-    assert agree >= (0.7 if name == "tt_rsq" else 0.9), (name, agree)
-    same = np.isclose(va, ref_va, rtol=1e-6)
-    np.testing.assert_allclose(np.asarray(m["correlations"], dtype=np.float64)[same], ref_r[same], atol=2e-5)
-    np.testing.assert_allclose(np.asarray(m["correlations"], dtype=np.float64), ref_r, atol=5e-3)
-    assert set(m.keys()) == {k.split("__m__")[1] for k in g.files if k.startswith(f"{name}__m__")}
-    assert abs(m["n_significant"] - int(g[f"{name}__m__n_significant"])) <= 1
-    wref = g[f"{name}__weights"]
-    assert w.shape == wref.shape and w.dtype == wref.dtype
-    err = np.abs(w[:, same] - wref[:, same]).max() / np.abs(wref).max()
-    assert err < 1e-4, (name, err)
+    test = dict(X_test=X[400:], y_test=Y[400:]) if tt else {}
+    info = _prove_oracle_against_reference(name, g, X[:400], Y[:400], test, common)
+    # (the R^2 metric takes sqrt(|Rsq|) of values that are pure rounding noise for null voxels, so many more voxels
+    #  are near-ties there -- each of them proven to be one)
+    assert info["disagreeing_alphas"] <= (0.3 if name == "tt_rsq" else 0.1) * info["voxel_folds"]
 
 
 def _structure_inputs():
@@ -297,16 +308,6 @@ def test_fit_predict_on_the_baseline_alpha_grid_matches_reference(name):
     kw = dict(GRID20[name])
     tt = kw.pop("train_test")
     common = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas, **kw)
-    random.seed(7)
-    np.random.seed(7)
-    if tt:
-        m, w, va = O.fit_predict(X[:400], Y[:400], X_test=X[400:], y_test=Y[400:], **common)
-    else:
-        m, w, va = O.fit_predict(X[:400], Y[:400], **common)
-    same = np.isclose(va, g[f"{name}__best_alphas"], rtol=1e-6)
-    assert same.mean() >= 0.95, (name, same.mean())
-    r = np.asarray(m["correlations"], dtype=np.float64)
-    np.testing.assert_allclose(r[same], g[f"{name}__m__correlations"][same], atol=2e-5)
-    assert m["n_significant"] == int(g[f"{name}__m__n_significant"])
-    wref = g[f"{name}__weights"]
-    assert np.abs(w[:, same] - wref[:, same]).max() < 1e-4 * np.abs(wref).max()
+    test = dict(X_test=X[400:], y_test=Y[400:]) if tt else {}
+    info = _prove_oracle_against_reference(name, g, X[:400], Y[:400], test, common)
+    assert info["disagreeing_alphas"] <= 0.05 * info["voxel_folds"]
