@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LITRIDGE_ABI_VERSION 4
+#define LITRIDGE_ABI_VERSION 5
 
 const char* lit_last_error(void);
 int lit_abi_version(void);
@@ -237,6 +237,37 @@ int lit_lanczos_lambda_max(const float* G, long ld, int n, int steps, float* vec
  * batch * (2*steps + 4) doubles; lam_out_f64: batch doubles.  steps <= n. */
 int lit_lanczos_lambda_max_batched(const float* const* G, int batch, long ld, int n, int steps, float* vec_scratch,
                                    double* scal_scratch, double* lam_out_f64, void* stream);
+/* `batch` equally shaped products D_b = alpha * A_b B_b^T + beta * Cin_b in ONE launch (3xTF32 split pairs):
+ * operand b lives at base + b * bs_x floats (bs_a, bs_b, bs_c, bs_d; 16-byte multiples).  tri_k != 0: B is upper
+ * triangular in the sense B[n][k] == 0 for k < n (the rows of an inverse Cholesky factor), so the K loop of a tile
+ * starts at its first row of B.  Serves the batched direct solver below; same arithmetic as lit_gemm_tf32x3_nt. */
+int lit_gemm_tf32x3_nt_batched(const float* A_hi, const float* A_lo, long lda, long bs_a, const float* B_hi,
+                               const float* B_lo, long ldb, long bs_b, int M, int N, int K, float alpha, const float* Cin,
+                               long ldc, long bs_c, float beta, float* D, float* D_lo, long ldd, long bs_d, int batch,
+                               int tri_k, void* stream);
+/* Batched direct solve of the small-alpha systems of the inner folds:  M_b = R_b (G_b + a2_b I)^-1  for up to 128
+ * systems of one size at once (G_b: n x n symmetric, pitch ldg; R_b: m_b x n, pitch ldr, m_b <= mp), by a blocked
+ * Cholesky factorisation of the augmented matrix [G + a2 I; R; I] whose panel and trailing updates are batched
+ * tcgen05 GEMMs (chol_solver.cu).  G_h, R_h, m_h, a2_h are HOST arrays of length nb.
+ * lit_spd_solve_workspace reports the sizes: F (fp32 work matrix) f_floats, S_hi / S_lo (its TF32 planes) s_floats
+ * each, Dg_hi / Dg_lo dg_floats each; pitch ldw (= n rounded up to 128) and rows_total (= 2 ldw + mp) per system.
+ * On return system b (at + b * rows_total * ldw floats) holds  Y_b = R_b L^-T  in rows [ldw, ldw + mp)  and
+ * W_b = L^-T (upper triangular)  in rows [ldw + mp, rows_total)  of S, so that
+ *     M_b = Y_b W_b^T = lit_gemm_tf32x3_nt_batched(A = Y, B = W, K = N = n, tri_k = 1).
+ * info[b] (device ints) != 0: system b was not positive definite.
+ * Replaces the per-alpha `(PVh * D) @ UR` factors of ridge_regression.py:115-120 for the alphas that do not ride
+ * the Neumann series (round 1 solved them with ~66 Chebyshev GEMM steps per fold). */
+int lit_spd_solve_workspace(int nb, int n, int mp, size_t* f_floats, size_t* s_floats, size_t* dg_floats, long* ldw,
+                            long* rows_total);
+int lit_spd_solve_batched(int nb, int n, int mp, const void* const* G_h, long ldg, const void* const* R_h, long ldr,
+                          const int* m_h, const float* a2_h, float* F, float* S_hi, float* S_lo, float* Dg_hi,
+                          float* Dg_lo, int* info, void* stream);
+/* A-posteriori check of such solutions on one deterministic +-1 probe vector x per system:
+ *   numden[2 b] = || M_b (G_b x + a2_b x) - R_b x ||^2,  numden[2 b + 1] = || R_b x ||^2   (M_b at M + b * m_stride,
+ * pitch ldm); scratch: nb * n floats.  Read back with the fit's final synchronisation (DeviceOps.check_solver). */
+int lit_spd_probe_residual(int nb, int n, const void* const* G_h, long ldg, const void* const* R_h, long ldr,
+                           const int* m_h, const float* a2_h, const float* M, long ldm, long m_stride, float* scratch,
+                           double* numden, void* stream);
 /* One Chebyshev step on (rows x cols) row-matrices of pitch ld:
  *   d = c1*d + c2*r (also written as the split pair d_hi/d_lo),  x += d,  t = r - a2*d;
  * `first` != 0 treats d and x as zero on input.  The caller then forms r = t - d G with lit_gemm_tf32x3_nt. */

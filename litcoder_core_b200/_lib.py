@@ -11,10 +11,10 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblitridge.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _l, _i, _f, _d, _sz = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_double, C.c_size_t
-_psz, _pi = C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+_psz, _pi, _pl = C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_long)
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); order mirrors include/litridge.h
 PROTOTYPES = {
@@ -56,6 +56,11 @@ PROTOTYPES = {
     "lit_lanczos_downsample": [_vp, _i, _l, _l, _l, _vp, _vp, _l, _d, _d, _i, _vp, _vp, _vp, _l, _vp],
     "lit_lanczos_lambda_max": [_vp, _l, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "lit_lanczos_lambda_max_batched": [_vp, _i, _l, _i, _i, _vp, _vp, _vp, _vp],
+    "lit_gemm_tf32x3_nt_batched": [_vp, _vp, _l, _l, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _l, _l, _f, _vp, _vp, _l, _l,
+                                   _i, _i, _vp],
+    "lit_spd_solve_workspace": [_i, _i, _i, _psz, _psz, _psz, _pl, _pl],
+    "lit_spd_solve_batched": [_i, _i, _i, _vp, _l, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "lit_spd_probe_residual": [_i, _i, _vp, _l, _vp, _l, _vp, _vp, _vp, _l, _l, _vp, _vp, _vp],
     "lit_cheb_update": [_vp, _vp, _vp, _vp, _vp, _vp, _l, _l, _l, _f, _f, _f, _i, _vp],
     "lit_poly_combine": [_vp, _vp, _i, _l, _l, _l, _l, _vp, _vp, _i, _vp, _vp, _l, _vp],
     "lit_series_stack": [_vp, _vp, _l, _l, _l, _vp, _l, _vp, _vp, _l, _vp],

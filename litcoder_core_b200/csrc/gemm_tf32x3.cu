@@ -77,6 +77,13 @@ struct GemmParams {
   // points and emits the 4 sums T_q y and the 10 sums T_q T_q' (q <= q') into series_part[part*14 + j][ld_part].
   int series_tile0;
   float* series_part;
+  // Batched launches (EPI_STORE): `batch` equally shaped problems; operand b lives at base + b * stride (the
+  // strides of A and B are part of their 3-D tensor maps), D / D_lo at + b * bs_d floats, Cin at + b * bs_c.
+  int batch;
+  long bs_d, bs_c;
+  // tri_k: B is upper triangular in the sense B[n][k] == 0 for k < n (rows of an inverse Cholesky factor):
+  // the K loop of a tile starts at its first B row instead of 0.
+  int tri_k;
 };
 
 // F16_ = 0: operands are fp32 planes holding TF32 values (kind::tf32, 8 values of K per MMA);
@@ -98,7 +105,9 @@ struct GemmShape {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered chunk accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;  // store epilogue: one 32 x 32 fp32 block per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + STAGING_BYTES;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 128 + EPI_WARPS * 32;
   static constexpr int COLS = BN / 2;  // accumulator columns owned by one epilogue thread
@@ -115,6 +124,15 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   const int r = tile - g * gsz;
   mt = first_m + r % gm;
   nt = r / gm;
+}
+
+// Batched tile index -> (batch, m tile, n tile); first k-block of the tile (tri_k: see GemmParams).
+template <int BN, int BK>
+__device__ __forceinline__ void batch_tile_coords(const GemmParams& p, int tile, int& b, int& mt, int& nt, int& kb_begin) {
+  const int per = p.num_m_tiles * p.num_n_tiles;
+  b = tile / per;
+  tile_coords(p, tile - b * per, mt, nt);
+  kb_begin = p.tri_k ? min((nt * BN) / BK, p.num_k_blocks - 1) : 0;
 }
 
 template <int BN, int CG, int EPI, int F16 = 0>
@@ -161,10 +179,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.batch;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
-  const int num_chunks = (p.num_k_blocks + p.kc_blocks - 1) / p.kc_blocks;
 
   if (warp < 4) {
     // The data-movement / issue warps need few registers; hand the rest to the accumulating warps.
@@ -175,27 +192,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-          int mt, nt;
-          tile_coords(p, tile, mt, nt);
+          int b, mt, nt, kb_begin;
+          batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
           const int m_row = (mt * CG + (int)cta_rank) * S::BM;
           const int n_row = nt * BN + (int)cta_rank * S::B_ROWS;
-          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          for (int kb = kb_begin; kb < p.num_k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * S::STAGE_BYTES;
             const int k0 = kb * S::BK;
             if constexpr (CG == 1) {
               ptx::mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-              ptx::tma_load_2d(st, &tmAh, &full_bar[stage], k0, m_row);
-              ptx::tma_load_2d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
-              ptx::tma_load_2d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
-              ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+              ptx::tma_load_3d(st, &tmAh, &full_bar[stage], k0, m_row, b);
+              ptx::tma_load_3d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row, b);
+              ptx::tma_load_3d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, b);
+              ptx::tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, b);
             } else {
               // Both CTAs load their halves; all bytes are accounted on the leader's barrier.
               if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
-              ptx::tma_load_2d_2sm(st, &tmAh, &full_bar[stage], k0, m_row);
-              ptx::tma_load_2d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row);
-              ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row);
-              ptx::tma_load_2d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row);
+              ptx::tma_load_3d_2sm(st, &tmAh, &full_bar[stage], k0, m_row, b);
+              ptx::tma_load_3d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row, b);
+              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, b);
+              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, b);
             }
             if (++stage == S::STAGES) {
               stage = 0;
@@ -212,7 +229,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         uint32_t phase = 0;
         uint32_t cc = 0;  // running chunk counter: TMEM buffer = cc & 1
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-          for (int kb0 = 0; kb0 < p.num_k_blocks; kb0 += p.kc_blocks, ++cc) {
+          int b, mt, nt, kb_begin;
+          batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+          for (int kb0 = kb_begin; kb0 < p.num_k_blocks; kb0 += p.kc_blocks, ++cc) {
             const uint32_t buf = cc & 1u;
             ptx::mbar_wait(&tmem_empty_bar[buf], ((cc >> 1) & 1u) ^ 1u);
             ptx::tc_fence_after();
@@ -262,8 +281,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     uint32_t cc = 0;
     float acc[COLS];
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
-      int mt, nt;
-      tile_coords(p, tile, mt, nt);
+      int b, mt, nt, kb_begin;
+      batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+      const int num_chunks = (p.num_k_blocks - kb_begin + p.kc_blocks - 1) / p.kc_blocks;
+      if constexpr (EPI == EPI_STORE) {
+        // Cin of this tile towards L2 now: it is read only after the tile's MMAs, several microseconds from here
+        if (p.Cin) {
+          const long prow = (long)(mt * CG + (int)cta_rank) * S::BM + quad * 32 + lane;
+          const long pcol = (long)nt * BN + half * COLS;
+          if (prow < p.M) {
+            const float* pc = p.Cin + b * p.bs_c + prow * p.ldc + pcol;
+#pragma unroll
+            for (int q = 0; q < COLS / 32; ++q)
+              if (pcol + 32 * q < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + 32 * q));
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
       for (int c = 0; c < num_chunks; ++c, ++cc) {
@@ -297,62 +330,99 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       const long row = (long)(mt * CG + (int)cta_rank) * S::BM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       if constexpr (EPI == EPI_STORE) {
-        const long n_base = (long)nt * BN + half * COLS;
-        if (row_ok) {
-          float* drow = p.D + row * p.ldd + n_base;
-          float* lrow = p.D_lo ? p.D_lo + row * p.ldd + n_base : nullptr;
-          const float* crow = p.Cin ? p.Cin + row * p.ldc + n_base : nullptr;
-          const float* srow = p.scale_n ? p.scale_n + n_base : nullptr;
-          const float am = p.scale_m ? p.alpha * __ldg(p.scale_m + row) : p.alpha;
+        // The accumulator arrives one ROW per thread (TMEM lane = row).  Written that way, a warp store touches 32
+        // rows with 16 bytes each: measured 1.4 TB/s of partial-sector writes, which bounded every small-K launch
+        // (the trailing updates of the Cholesky solver).  So every 32 x 32 block of the warp's tile goes through a
+        // 4 KB shared-memory staging buffer (XOR-swizzled 16-byte chunks: conflict-free both ways) and comes back
+        // with 8 lanes per row: a warp load of Cin / store of D then moves four complete 128-byte row segments.
+        // The loops over column blocks and row groups are deliberately NOT unrolled: the round-1 epilogue was
+        // ~3,600 straight-line instructions per thread and tile, and ncu showed the small-K launches stalled on
+        // instruction fetch (icache hit rate 68 %); only the staging stores need compile-time register indices.
+        float* stg = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + 256) + ew * 1024;
+        const long row0 = (long)(mt * CG + (int)cta_rank) * S::BM + quad * 32;
+        const int rsub = lane >> 3, chunk = lane & 7;
+        const float sm_own = (p.scale_m && row_ok) ? __ldg(p.scale_m + row) : 1.f;
+        const bool has_c = p.Cin != nullptr, has_lo = p.D_lo != nullptr;
+        const float* cb = has_c ? p.Cin + b * p.bs_c : nullptr;
+        float* db = p.D + b * p.bs_d;
+        float* lb = has_lo ? p.D_lo + b * p.bs_d : nullptr;
+        const uint32_t my_sts = ptx::smem_u32(stg + lane * 32);
+#pragma unroll 1
+        for (int cc = 0; cc < COLS / 32; ++cc) {
 #pragma unroll
-          for (int j = 0; j < COLS; j += 4) {
-            if (n_base + j >= p.N) break;
-            float o[4];
-            if (n_base + j + 3 < p.N) {
-              float a4[4] = {am, am, am, am};
-              if (srow) {  // the scale vector is padded to a multiple of 4 entries by its producer
-                const float4 sv = __ldg(reinterpret_cast<const float4*>(srow + j));
-                a4[0] *= sv.x, a4[1] *= sv.y, a4[2] *= sv.z, a4[3] *= sv.w;
-              }
-              if (crow) {
-                const float4 cv = *reinterpret_cast<const float4*>(crow + j);
-                o[0] = a4[0] * acc[j] + p.beta * cv.x;
-                o[1] = a4[1] * acc[j + 1] + p.beta * cv.y;
-                o[2] = a4[2] * acc[j + 2] + p.beta * cv.z;
-                o[3] = a4[3] * acc[j + 3] + p.beta * cv.w;
-              } else {
+          for (int c2 = 0; c2 < COLS / 32; ++c2) {
+            if (c2 == cc) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) o[q] = a4[q] * acc[j + q];
+              for (int c = 0; c < 8; ++c)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_sts + (((c ^ (lane & 7)) << 4))),
+                             "f"(acc[c2 * 32 + 4 * c]), "f"(acc[c2 * 32 + 4 * c + 1]), "f"(acc[c2 * 32 + 4 * c + 2]),
+                             "f"(acc[c2 * 32 + 4 * c + 3])
+                             : "memory");
+            }
+          }
+          __syncwarp();
+          const long col = (long)nt * BN + half * COLS + cc * 32 + chunk * 4;
+          const bool col_ok = col < p.N, vec_ok = col + 3 < p.N;
+          float sn[4] = {1.f, 1.f, 1.f, 1.f};
+          if (p.scale_n) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col + q < p.N) sn[q] = __ldg(p.scale_n + col + q);
+          }
+          {
+            constexpr int i0 = 0;
+            // all Cin rows of the block are loaded before its first store (D may alias Cin: in-place updates;
+            // 8 independent 128-byte row segments in flight per quarter warp)
+            float4 cv[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+              const long rw = row0 + 4 * (i0 + ii) + rsub;
+              cv[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_c && rw < p.M && col_ok) {
+                const float* cp = cb + rw * p.ldc + col;
+                if (vec_ok) {
+                  cv[ii] = *reinterpret_cast<const float4*>(cp);
+                } else {
+                  cv[ii].x = cp[0];
+                  if (col + 1 < p.N) cv[ii].y = cp[1];
+                  if (col + 2 < p.N) cv[ii].z = cp[2];
+                }
               }
-              if (lrow) {
-                float h[4], l[4];
+            }
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) {
+              const int r = 4 * (i0 + ii) + rsub;
+              const long rw = row0 + r;
+              const float am = p.alpha * __shfl_sync(0xffffffffu, sm_own, r);
+              const float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((chunk ^ (r & 7)) << 2));
+              if (rw >= p.M || !col_ok) continue;
+              float h[4] = {am * sn[0] * v.x + p.beta * cv[ii].x, am * sn[1] * v.y + p.beta * cv[ii].y,
+                            am * sn[2] * v.z + p.beta * cv[ii].z, am * sn[3] * v.w + p.beta * cv[ii].w};
+              float l[4] = {0.f, 0.f, 0.f, 0.f};
+              if (has_lo) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  h[q] = ptx::to_tf32(o[q]);
-                  l[q] = ptx::to_tf32(o[q] - h[q]);
+                  const float o = h[q];
+                  h[q] = ptx::to_tf32(o);
+                  l[q] = ptx::to_tf32(o - h[q]);
                 }
-                *reinterpret_cast<float4*>(drow + j) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(lrow + j) = make_float4(l[0], l[1], l[2], l[3]);
-              } else {
-                *reinterpret_cast<float4*>(drow + j) = make_float4(o[0], o[1], o[2], o[3]);
               }
-            } else {
+              float* dp = db + rw * p.ldd + col;
+              if (vec_ok) {
+                *reinterpret_cast<float4*>(dp) = make_float4(h[0], h[1], h[2], h[3]);
+                if (has_lo) *reinterpret_cast<float4*>(lb + rw * p.ldd + col) = make_float4(l[0], l[1], l[2], l[3]);
+              } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (n_base + j + q < p.N) {
-                  float x = (srow ? am * __ldg(srow + j + q) : am) * acc[j + q];
-                  if (crow) x += p.beta * crow[j + q];
-                  if (lrow) {
-                    const float h = ptx::to_tf32(x);
-                    drow[j + q] = h;
-                    lrow[j + q] = ptx::to_tf32(x - h);
-                  } else {
-                    drow[j + q] = x;
+                for (int q = 0; q < 4; ++q) {
+                  if (col + q < p.N) {
+                    dp[q] = h[q];
+                    if (has_lo) lb[rw * p.ldd + col + q] = l[q];
                   }
                 }
               }
             }
           }
+          __syncwarp();  // the staging buffer is rewritten by the next column block
         }
       } else {
         // Fused per-voxel reduction: rows = voxels, columns = time points of one alpha group.
@@ -440,7 +510,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // Tensor map of a row-major [rows][k] fp32 matrix (row pitch ld floats); box = box_rows x 32 floats.
-static int make_operand_map(CUtensorMap* tm, const void* base, long rows, long k, long ld, int box_rows, int f16 = 0) {
+static int make_operand_map(CUtensorMap* tm, const void* base, long rows, long k, long ld, int box_rows, int f16 = 0,
+                            int batch = 1, long batch_stride = 0) {
   auto enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -450,11 +521,13 @@ static int make_operand_map(CUtensorMap* tm, const void* base, long rows, long k
   const int elem = f16 ? 2 : 4;
   LIT_REQUIRE((ld * elem) % 16 == 0 && ld >= k, "GEMM operand pitch must be a multiple of 16 bytes and >= K (ld=%ld K=%ld)",
               ld, k);
-  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+  if (batch <= 1 || batch_stride <= 0) batch_stride = (rows > 0 ? rows : 1) * ld;  // a single matrix: any valid stride
+  LIT_REQUIRE((batch_stride * elem) % 16 == 0, "GEMM batch stride must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)(batch > 0 ? batch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * elem, (cuuint64_t)batch_stride * elem};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / elem), (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base),
                    dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -495,14 +568,15 @@ static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it 
 
 template <int BN, int CG, int EPI, int F16 = 0>
 static int launch_gemm(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
-                       GemmParams p, cudaStream_t stream) {
+                       GemmParams p, cudaStream_t stream, long bs_a = 0, long bs_b = 0) {
   using S = GemmShape<BN, CG, F16>;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   int rc;
-  if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM, F16))) return rc;
-  if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM, F16))) return rc;
-  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS, F16))) return rc;
-  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS, F16))) return rc;
+  if (p.batch < 1) p.batch = 1;
+  if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM, F16, p.batch, bs_a))) return rc;
+  if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM, F16, p.batch, bs_a))) return rc;
+  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS, F16, p.batch, bs_b))) return rc;
+  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS, F16, p.batch, bs_b))) return rc;
 
   p.num_m_tiles = (p.M + S::BM * CG - 1) / (S::BM * CG);
   p.num_n_tiles = (p.N + BN - 1) / BN;
@@ -510,7 +584,7 @@ static int launch_gemm(const void* A_hi, const void* A_lo, long lda, const void*
   if (p.num_k_blocks < 1) p.num_k_blocks = 1;  // K == 0 still zero-initialises the accumulator via OOB fill
   if (p.group_m <= 0) p.group_m = group_m_default(CG);
   if (p.kc_blocks <= 0) p.kc_blocks = kc_blocks_default();  // 4 k-blocks: K = 128 (tf32) / 256 (fp16), 48 accumulations either way
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.batch;
   if (tiles == 0) return LIT_OK;
 
   auto kfn = gemm_tf32x3_kernel<BN, CG, EPI, F16>;
@@ -585,6 +659,48 @@ extern "C" int lit_gemm_tf32x3_nt(const float* A_hi, const float* A_lo, long lda
       set_error("unknown GEMM variant %d", variant);
       return LIT_ERR_INVALID;
   }
+}
+
+// `batch` equally shaped products D_b = alpha * A_b B_b^T + beta * Cin_b in ONE launch (3xTF32): operand b lives at
+// base + b * bs_x floats.  Used by the batched Cholesky inner solver (chol_solver.cu) and the stacked Neumann powers.
+namespace lit {
+int gemm_nt_batched(const float* A_hi, const float* A_lo, long lda, long bs_a, const float* B_hi, const float* B_lo,
+                    long ldb, long bs_b, int M, int N, int K, float alpha, const float* Cin, long ldc, long bs_c,
+                    float beta, float* D, float* D_lo, long ldd, long bs_d, int batch, int tri_k, cudaStream_t s) {
+  LIT_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "negative GEMM extent");
+  LIT_REQUIRE(ldd % 4 == 0 && ldd >= N && bs_d % 4 == 0, "output pitch / batch stride must be multiples of 4 floats");
+  LIT_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "output must be 16-byte aligned");
+  LIT_REQUIRE(!Cin || (ldc % 4 == 0 && bs_c % 4 == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0), "Cin alignment");
+  LIT_REQUIRE(!D_lo || (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0, "D_lo alignment");
+  LIT_REQUIRE(!tri_k || N <= K + 255, "tri_k needs a square-ish B (N <= K)");
+  if (M == 0 || N == 0 || batch == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.D = D;
+  p.D_lo = D_lo;
+  p.ldd = ldd;
+  p.Cin = Cin;
+  p.ldc = ldc;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.batch = batch;
+  p.bs_d = bs_d;
+  p.bs_c = bs_c;
+  p.tri_k = tri_k;
+  if (N <= 128) return launch_gemm<128, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s, bs_a, bs_b);  // panels
+  if (M > 128) return launch_gemm<256, 2, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s, bs_a, bs_b);
+  return launch_gemm<256, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s, bs_a, bs_b);
+}
+}  // namespace lit
+
+extern "C" int lit_gemm_tf32x3_nt_batched(const float* A_hi, const float* A_lo, long lda, long bs_a, const float* B_hi,
+                                          const float* B_lo, long ldb, long bs_b, int M, int N, int K, float alpha,
+                                          const float* Cin, long ldc, long bs_c, float beta, float* D, float* D_lo,
+                                          long ldd, long bs_d, int batch, int tri_k, void* stream) {
+  return lit::gemm_nt_batched(A_hi, A_lo, lda, bs_a, B_hi, B_lo, ldb, bs_b, M, N, K, alpha, Cin, ldc, bs_c, beta, D, D_lo,
+                              ldd, bs_d, batch, tri_k, static_cast<cudaStream_t>(stream));
 }
 
 // D = alpha * A B^T + beta * Cin on fp16 split pairs (lit_split_f16; one scale per row of A and per row of B, whose

@@ -22,6 +22,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
+from .engine import SolverAccuracyError
 
 _vp = C.c_void_p
 
@@ -174,6 +175,8 @@ class DeviceOps:
         self._corr_log: List[tuple] = []  # (start, stop, flops) of every fused prediction+correlation GEMM
         self._staging: List[object] = []
         self._timed: Dict[str, List[tuple]] = {}
+        self._solver_checks: List[tuple] = []  # (probe residuals, pivot flags) of the direct inner solves
+        self.last_solver_residual = 0.0
 
     @property
     def stream(self) -> int:
@@ -852,6 +855,121 @@ class DeviceOps:
                 Q = self.gemm(Q, Gs, split_out=True, ld_out=ld)
                 self.axpy(1.0, Q, self._view_rows(block, (len(cheb) + q) * n_rows, n_rows))
         return block
+
+    # ------------------------------------------------------------------ batched direct inner solver
+    SOLVER_TOL = 2e-4  # a-posteriori probe residual above which a direct solve is rejected (check_solver)
+    SPD_MAX_BATCH = 128
+
+    def solve_blocks_many(self, jobs, series_ratio: float = 60.0) -> list:
+        """The compact solution blocks of SEVERAL GEMM-only folds at once (layout of solve_blocks).  jobs: dicts with
+        G (fp32 Mat p x p), Pc (fp32 Mat n_rows x p), n_rows, lam_max, a2 (list).  The small-alpha systems of all
+        jobs -- up to 128 per launch -- go through the batched blocked Cholesky solver (lit_spd_solve_batched: every
+        panel / trailing update is ONE batched tcgen05 GEMM for all systems), followed by one batched product per
+        job and a probe-vector residual check that is read back by check_solver()."""
+        t = self.torch
+        blocks, parts = [], []
+        for job in jobs:
+            cheb, series = self.solver_partition(job["lam_max"], job["a2"], series_ratio)
+            n_rows, p = job["n_rows"], job["G"].rows
+            block = self.zeros((len(cheb) + (3 if series else 0)) * n_rows, p)
+            if job["Pc"].ld != block.ld or job["G"].ld != block.ld:
+                raise ValueError("solve_blocks_many: G, Pc and the block must share one pitch")
+            blocks.append(block)
+            parts.append((cheb, series))
+        s = _vp(self.stream)
+        # ---- small alphas: chunks of whole jobs, at most SPD_MAX_BATCH systems each
+        i0 = 0
+        while i0 < len(jobs):
+            i1, nsys = i0, 0
+            while i1 < len(jobs) and (i1 == i0 or nsys + len(parts[i1][0]) <= self.SPD_MAX_BATCH) \
+                    and jobs[i1]["G"].rows == jobs[i0]["G"].rows:
+                nsys += len(parts[i1][0])
+                i1 += 1
+            if nsys > self.SPD_MAX_BATCH:
+                raise ValueError("solve_blocks_many: more than 128 solved alphas in one fold")
+            if nsys:
+                self._spd_chunk(jobs[i0:i1], blocks[i0:i1], [c for c, _ in parts[i0:i1]], nsys, s)
+            i0 = i1
+        # ---- shared powers of the Neumann series
+        for job, block, (cheb, series) in zip(jobs, blocks, parts):
+            if series:
+                Gs = self.split(job["G"])
+                Q = self.split(job["Pc"])
+                for q in range(3):
+                    Q = self.gemm(Q, Gs, split_out=True, ld_out=block.ld)
+                    self.axpy(1.0, Q, self._view_rows(block, (len(cheb) + q) * job["n_rows"], job["n_rows"]))
+        return blocks
+
+    def _spd_chunk(self, jobs, blocks, chebs, nsys: int, s) -> None:
+        t = self.torch
+        p = jobs[0]["G"].rows
+        mp = max(j["n_rows"] for j in jobs)
+        fF, fS, fD, ldw, rows = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_long(0), C.c_long(0)
+        check(self.lib.lit_spd_solve_workspace(nsys, p, mp, C.byref(fF), C.byref(fS), C.byref(fD), C.byref(ldw),
+                                               C.byref(rows)), "spd_solve_workspace")
+        ldw, rows = ldw.value, rows.value
+        f32 = dict(dtype=t.float32, device=self.device)
+        F = t.empty((fF.value,), **f32)
+        S_hi, S_lo = t.empty((fS.value,), **f32), t.empty((fS.value,), **f32)
+        Dg_hi, Dg_lo = t.empty((fD.value,), **f32), t.empty((fD.value,), **f32)
+        info = t.empty((nsys,), dtype=t.int32, device=self.device)
+        Gp, Rp, mh, a2h = (C.c_void_p * nsys)(), (C.c_void_p * nsys)(), (C.c_int * nsys)(), (C.c_float * nsys)()
+        k = 0
+        for job, cheb in zip(jobs, chebs):
+            for j in cheb:
+                Gp[k], Rp[k], mh[k], a2h[k] = job["G"].hi.data_ptr(), job["Pc"].hi.data_ptr(), job["n_rows"], job["a2"][j]
+                k += 1
+        ldg, ldr = jobs[0]["G"].ld, jobs[0]["Pc"].ld
+        with self.timed("spd_solve"):
+            check(self.lib.lit_spd_solve_batched(nsys, p, mp, C.cast(Gp, _vp), ldg, C.cast(Rp, _vp), ldr,
+                                                 C.cast(mh, _vp), C.cast(a2h, _vp), _vp(F.data_ptr()),
+                                                 _vp(S_hi.data_ptr()), _vp(S_lo.data_ptr()), _vp(Dg_hi.data_ptr()),
+                                                 _vp(Dg_lo.data_ptr()), _vp(info.data_ptr()), s), "spd_solve_batched")
+            steps = ldw // 128
+            self.launches += 1 + 4 * steps
+            self.gemm_flops += sum(2.0 * nsys * (rows - 128 * (j + 1)) * 128 * (128 + max(ldw - 128 * (j + 1), 0))
+                                   for j in range(steps))
+            sys_stride = rows * ldw
+            k = 0
+            for job, block, cheb in zip(jobs, blocks, chebs):
+                nc, n_rows = len(cheb), job["n_rows"]
+                if not nc:
+                    continue
+                y0 = (k * sys_stride + ldw * ldw) * 4  # rows [ldw, ldw + mp): Y = R L^-T
+                w0 = (k * sys_stride + (ldw + mp) * ldw) * 4  # rows [ldw + mp, rows): W = L^-T
+                check(self.lib.lit_gemm_tf32x3_nt_batched(
+                    _vp(S_hi.data_ptr() + y0), _vp(S_lo.data_ptr() + y0), ldw, sys_stride,
+                    _vp(S_hi.data_ptr() + w0), _vp(S_lo.data_ptr() + w0), ldw, sys_stride, n_rows, p, p, 1.0, _vp(0), 0, 0,
+                    0.0, _vp(block.hi.data_ptr()), _vp(0), block.ld, n_rows * block.ld, nc, 1, s), "gemm_nt_batched")
+                self.launches += 1
+                self.gemm_flops += 1.0 * nc * n_rows * p * p  # upper-triangular W: half of 2 m n^2
+                scratch, rel = t.empty((nc * p,), **f32), t.empty((2 * nc,), dtype=t.float64, device=self.device)
+                check(self.lib.lit_spd_probe_residual(
+                    nc, p, _vp(C.addressof(Gp) + 8 * k), ldg, _vp(C.addressof(Rp) + 8 * k), ldr,
+                    _vp(C.addressof(mh) + 4 * k), _vp(C.addressof(a2h) + 4 * k), _vp(block.hi.data_ptr()), block.ld,
+                    n_rows * block.ld, _vp(scratch.data_ptr()), _vp(rel.data_ptr()), s), "spd_probe_residual")
+                self.launches += 2
+                self._solver_checks.append((rel, info[k:k + nc]))
+                k += nc
+
+    def check_solver(self) -> None:
+        """Raise SolverAccuracyError if a direct inner solve since the last check was not positive definite or
+        failed its a-posteriori probe (synchronises; called once per fit next to check_eig)."""
+        checks, self._solver_checks = self._solver_checks, []
+        if not checks:
+            return
+        self.torch.cuda.synchronize(self.device)
+        worst, bad = 0.0, 0
+        for rel, info in checks:
+            nd = rel.cpu().numpy().reshape(-1, 2)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                r = np.where(nd[:, 1] > 0, np.sqrt(nd[:, 0] / nd[:, 1]), np.where(nd[:, 0] > 0, np.inf, 0.0))
+            worst = max(worst, float(np.max(r)) if np.isfinite(r).all() else float("inf"))
+            bad += int((info.cpu().numpy() != 0).sum())
+        self.last_solver_residual = worst
+        if bad or not (worst <= self.SOLVER_TOL):
+            raise SolverAccuracyError(f"direct inner solve rejected: {bad} systems not positive definite, worst probe "
+                                      f"residual {worst:.3e} (tolerance {self.SOLVER_TOL:.1e})")
 
     SERIES_MIN_ALPHAS = 5  # the compact stack pays once more alphas ride the series than it has terms (4)
 

@@ -49,6 +49,10 @@ logger = logging.getLogger(__name__)
 EPS = 1e-8  # ridge_utils.z_score / DataNormalizer eps
 
 
+class SolverAccuracyError(RuntimeError):
+    """A GEMM-only inner solve failed its a-posteriori check (DeviceOps.check_solver)."""
+
+
 @dataclass
 class RidgeConfig:
     alphas: Sequence[float]
@@ -83,6 +87,10 @@ class RidgeConfig:
     leave_block_out: bool = True
     # several ranks: each forms the outer Gram / kernel matrix over its slice of the contraction axis, one all-reduce
     row_shard_gram: bool = False
+    # GEMM-only folds: solve the small alphas with the batched blocked-Cholesky solver (DeviceOps.solve_blocks_many:
+    # all systems of this rank's folds together, a few batched launches per 128-column panel) instead of Chebyshev
+    # iteration; supersedes leave_block_out (no dependence on the outer fold's eigendecomposition)
+    direct_solver: bool = True
     # keep the fold-mean inner score curves (n_alphas x V_r per outer fold) for the caller (tests: near-tie proofs)
     record_scores: bool = False
 
@@ -233,7 +241,8 @@ class RidgeCVEngine:
             else:
                 d["cheb"] = self._use_chebyshev(cfg)
                 need_G = mine  # the Gram is only needed by the rank that solves this fold
-                d["lbo"] = bool(d["cheb"] and cfg.leave_block_out and d["R"] is not None and G_o is not None
+                d["lbo"] = bool(d["cheb"] and cfg.leave_block_out and not cfg.direct_solver and d["R"] is not None
+                                and G_o is not None
                                 and len(d["R_rows"]) == len(d["val_rows"])
                                 and np.array_equal(np.sort(d["R_rows"]), np.sort(d["val_rows"])))
                 if d["R"] is not None and G_o is not None:
@@ -395,10 +404,25 @@ class RidgeCVEngine:
             # every rank holds every lambda_max after the all-reduce: all of them raise together (an owner-only
             # check would leave the other ranks waiting in the broadcast of the fold's solution block)
             self._check_lmax(float(v), cfg)
-        if comm.world > 1:
+        if cfg.direct_solver:
+            # every fold this rank owns, all outer folds at once: batched Cholesky solves (32 systems per launch)
+            with ops.timed("phase_inner_solve"):
+                self._solve_direct([(X, d) for X, d in jobs if d["owner"] == comm.rank], cfg)
+        elif comm.world > 1:
             for X, d in jobs:
                 if d["owner"] == comm.rank and not d.get("lbo"):  # leave-block-out folds: see _prepare_lbo
                     d["block"] = self._solve_blocks(X, d, cfg.alphas, cfg)
+
+    def _solve_direct(self, pairs, cfg: RidgeConfig) -> None:
+        ops = self.ops
+        jobs = []
+        for X, d in pairs:
+            lam_max = float(d["lmax"])
+            jobs.append(dict(G=d["G"], Pc=self._centred_val_design(X, d), n_rows=len(d["val_rows"]), lam_max=lam_max,
+                             a2=self._scaled_alphas_sq(lam_max, cfg.alphas, cfg)))
+        for (X, d), block in zip(pairs, ops.solve_blocks_many(jobs)):
+            d["block"] = block
+            d["G"] = None
 
     @staticmethod
     def _same_shape_groups(items):

@@ -26,7 +26,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
-from .engine import FoldPlan, RidgeConfig, RidgeCVEngine, SingleProcess
+from .engine import FoldPlan, RidgeConfig, RidgeCVEngine, SingleProcess, SolverAccuracyError
 from .folding import create_folds
 
 logger = logging.getLogger(__name__)
@@ -321,10 +321,27 @@ class NestedCVModel:
             Y = self._to_device(ops, targets, c0, c1)
             Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
 
+        cfg.direct_solver = os.environ.get("LIT_DIRECT_SOLVER", "1") != "0"  # development override
         engine = RidgeCVEngine(ops, comm)
         with ops.timed("fit"):
             res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox, y_ready=y_ready)
         ops.check_eig()
+        # a-posteriori check of the GEMM-only inner solves (probe residuals + pivot flags, read back here): a rejected
+        # solve on ANY rank sends every rank back through the eigendecomposition route
+        failed = 0.0
+        try:
+            ops.check_solver()
+        except SolverAccuracyError as e:
+            logger.warning("%s -- refitting with inner_solver='eig'", e)
+            failed = 1.0
+        if comm.world > 1:
+            failed = float(comm.all_reduce_sum(np.array([failed]))[0])
+        if failed:
+            del res, engine
+            cfg.inner_solver = "eig"
+            engine = RidgeCVEngine(ops, comm)
+            res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox)
+            ops.check_eig()
 
         # ---- per-voxel vectors back to the host, gathered over ranks ----
         with ops.timed("d2h"):

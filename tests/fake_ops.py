@@ -387,6 +387,20 @@ class FakeOps:
         self.solver_calls = getattr(self, "solver_calls", 0) + 1
         return FMat(out)
 
+    def solve_blocks_many(self, jobs, series_ratio=60.0):
+        """DeviceOps.solve_blocks_many: the batched direct (Cholesky) solver -- exact solves here."""
+        out = []
+        for job in jobs:
+            assert not job["G"].is_split and not job["Pc"].is_split
+            out.append(self.solve_blocks(self.split(job["G"]), job["Pc"], job["n_rows"], job["lam_max"], job["a2"],
+                                         series_ratio))
+            self.direct_solved = getattr(self, "direct_solved", 0) + len(
+                self.solver_partition(job["lam_max"], job["a2"], series_ratio)[0])
+        return out
+
+    def check_solver(self):
+        pass
+
     @staticmethod
     def _lbo_lo(lbo, a2):
         """Lower end of the spectral interval the device's Chebyshev iteration assumes for I - H_a."""

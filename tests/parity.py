@@ -103,13 +103,32 @@ def fold_results_of_oracle(details, alpha_fdr=0.05):
             "masks": np.stack([O.fdr_bh(np.asarray(d["p"]), alpha_fdr)[0] for d in details])}
 
 
+def _bh_check(p_star, lo, hi, mask, alpha_fdr, cut, what):
+    """Compare a product BH mask with the oracle's decisions on p_star; returns the ambiguous-voxel mask.
+    cut = None: the voxels at hand are ALL voxels of the fit (BH is recomputed on p_star).  cut = (k, V): they are a
+    STRIPE of a larger fit that rejected k of V hypotheses, so the cut k alpha / V comes from the full fit (the band
+    allows k to move by 0.1 %)."""
+    if cut is None:
+        amb = _bh_ambiguous(lo, hi, p_star, alpha_fdr)
+        star = O.fdr_bh(p_star, alpha_fdr)[0]
+    else:
+        tau = cut[0] * alpha_fdr / cut[1]
+        amb = (lo <= tau * 1.001) & (hi >= tau * 0.999)
+        star = p_star <= tau
+    bad = (np.asarray(mask, dtype=bool) != star) & ~amb
+    assert not bad.any(), f"{what}: {int(bad.sum())} BH decisions differ away from the threshold"
+    return amb, star
+
+
 def prove_fit_parity(fold_results, metrics, weights, features, targets, seed, X_test=None, y_test=None, ref_folds=None,
-                     w_tol=1e-4, r_tol=R_TOL, r_fp32=R_FP32, max_ambiguous=None, **kw):
+                     w_tol=1e-4, r_tol=R_TOL, r_fp32=R_FP32, max_ambiguous=None, bh_cuts=None, **kw):
     """Run the oracle on the same inputs / seed and prove parity of a fit (see the module docstring).
     fold_results: NestedCVModel.last_fold_results of the fit that returned (metrics, weights); kw: the fit_predict
     keyword arguments both sides received.  ref_folds: per-fold observations of the UNMODIFIED reference
     (golden_folds); when given, alphas, score curves, r and p of the reference itself are what the product is held
-    to, and the oracle only supplies the refits at the product's alphas.  Returns a dict of what was observed."""
+    to, and the oracle only supplies the refits at the product's alphas.  bh_cuts: when `targets` is a voxel STRIPE
+    of a larger fit, {"V": total voxels, "folds": [k per outer fold], "final": k}: the numbers of hypotheses the full
+    fit rejected (Benjamini-Hochberg is global over voxels).  Returns a dict of what was observed."""
     alphas = kw.get("alphas")
     alphas = np.logspace(-1, 8, 10) if alphas is None else alphas
     use_corr, single = kw.get("use_corr", True), kw.get("single_alpha", False)
@@ -147,10 +166,8 @@ def prove_fit_parity(fold_results, metrics, weights, features, targets, seed, X_
         max_dr = max(max_dr, float(dr.max()))
         n_te = d["Yte"].shape[0]
         lo, hi = p_of_r(np.abs(rs) + r_fp32, n_te), p_of_r(np.maximum(np.abs(rs) - r_fp32, 0.0), n_te)
-        amb = _bh_ambiguous(lo, hi, ps, alpha_fdr)
-        mask_star = O.fdr_bh(ps, alpha_fdr)[0]
-        bad = (fr["masks"][f] != mask_star) & ~amb
-        assert not bad.any(), f"outer fold {f}: {int(bad.sum())} BH decisions differ away from the threshold"
+        _bh_check(ps, lo, hi, fr["masks"][f], alpha_fdr, None if bh_cuts is None else (bh_cuts["folds"][f], bh_cuts["V"]),
+                  f"outer fold {f}")
         r_star.append(rs), p_star.append(ps), w_star.append(ws)
     # aggregation (nested_cv.py:276-296)
     r_star, p_star = np.asarray(r_star), np.asarray(p_star)
@@ -167,18 +184,16 @@ def prove_fit_parity(fold_results, metrics, weights, features, targets, seed, X_
                                                      for f in range(n_folds)]))
     r_out = np.asarray(metrics["correlations"], dtype=np.float64)
     assert np.abs(r_out - corr).max() < r_fp32
-    amb = _bh_ambiguous(lo, hi, comb, alpha_fdr)
-    sig_star = O.fdr_bh(comb, alpha_fdr)[0]
     sig = np.asarray(metrics["significant_mask"], dtype=bool)
-    bad = (sig != sig_star) & ~amb
-    assert not bad.any(), f"{int(bad.sum())} final BH decisions differ away from the threshold"
+    amb, sig_star = _bh_check(comb, lo, hi, sig, alpha_fdr, None if bh_cuts is None else (bh_cuts["final"], bh_cuts["V"]),
+                              "combined p-values")
     assert int(sig[~amb].sum()) == int(sig_star[~amb].sum())  # n_significant exact off the threshold band
-    assert abs(metrics["n_significant"] - int(sig_star.sum())) <= int(amb.sum())
+    assert abs(int(sig.sum()) - int(sig_star.sum())) <= int(amb.sum())
     if max_ambiguous is not None:
         assert int(amb.sum()) <= max_ambiguous, f"{int(amb.sum())} voxels sit on the BH threshold"
     werr = float(np.abs(np.asarray(weights, dtype=np.float64) - w_ref).max() / max(np.abs(w_ref).max(), 1e-30))
     assert werr < w_tol, f"weights differ by {werr:.3e} of max|W| on some voxel"
     return {"disagreeing_alphas": n_dis, "voxel_folds": V * n_folds, "max_dr": max_dr, "ambiguous_bh": int(amb.sum()),
-            "n_significant": int(metrics["n_significant"]), "n_significant_oracle": int(mo["n_significant"]),
+            "n_significant": int(sig.sum()), "n_significant_oracle": int(mo["n_significant"]),
             "n_significant_at_product_alphas": int(sig_star.sum()), "weights_rel_err": werr,
             "oracle": (mo, wo, ao), "details": details}

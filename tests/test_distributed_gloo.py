@@ -49,7 +49,7 @@ def _worker(rank, world, port, single_alpha, out_dir, row_shard_gram=False, wide
         assert model.last_stats["world"] == world and model.last_stats["voxels_this_rank"] in (256, 44)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
                  p=np.asarray(m["p_values"]), sig=np.asarray(m["significant_mask"]), n_sig=m["n_significant"],
-                 lbo_solved=getattr(ops, "lbo_solved", 0), solver_calls=getattr(ops, "solver_calls", 0))
+                 lbo_solved=getattr(ops, "direct_solved", 0), solver_calls=getattr(ops, "solver_calls", 0))
     finally:
         dist.destroy_process_group()
 
@@ -67,10 +67,10 @@ def test_two_ranks_match_single_process(tmp_path, single_alpha):
     m, w, a = NestedCVModel("ridge_regression", ops=FakeOps()).fit_predict(
         X, Y, n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 3, 6), single_alpha=single_alpha)
     mp.spawn(_worker, args=(2, _free_port(), single_alpha, str(tmp_path)), nprocs=2, join=True)
-    # the 9 inner folds are leave-block-out folds, each solved once, by its owner (2 small alphas each)
+    # the 9 inner folds are solved once each, by their owners, with the batched direct solver (3 small alphas each)
     per_rank = [np.load(tmp_path / f"rank{rank}.npz") for rank in range(2)]
     assert sum(int(g["solver_calls"]) for g in per_rank) == 9 and all(int(g["solver_calls"]) >= 3 for g in per_rank)
-    assert sum(int(g["lbo_solved"]) for g in per_rank) == 18
+    assert sum(int(g["lbo_solved"]) for g in per_rank) == 27
     for rank in range(2):
         g = per_rank[rank]
         np.testing.assert_array_equal(g["a"], a)
@@ -131,7 +131,7 @@ def _worker_5x5(rank, world, port, out_dir):
         ops = FakeOps()
         m, w, a = NestedCVModel("ridge_regression", ops=ops, comm=TorchDistComm()).fit_predict(X, Y, **_KW_5X5)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), r=np.asarray(m["correlations"]), w=w, a=a,
-                 n_sig=m["n_significant"], lbo=getattr(ops, "lbo_solved", 0), eig=ops.eig_calls,
+                 n_sig=m["n_significant"], lbo=getattr(ops, "direct_solved", 0), eig=ops.eig_calls,
                  solves=getattr(ops, "solver_calls", 0))
     finally:
         dist.destroy_process_group()
@@ -139,7 +139,7 @@ def _worker_5x5(rank, world, port, out_dir):
 
 def test_four_ranks_bench_layout(tmp_path):
     """The BASELINE layout (5 x 5 chunked folds, 20 alphas: 4 solved + 16 series alphas per inner fold) on 4 ranks:
-    25 leave-block-out solves and 5 outer decompositions dealt out evenly, compact stacks broadcast, same result."""
+    25 batched direct solves and 5 outer decompositions dealt out evenly, compact stacks broadcast, same result."""
     import torch.multiprocessing as mp
 
     sys.path.insert(0, HERE)

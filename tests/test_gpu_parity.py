@@ -592,6 +592,103 @@ def test_gemm_only_inner_solver_kernels(ops):
         assert err < 5e-6, (j, alphas[j], err)
 
 
+@pytest.mark.parametrize("tri_k", [0, 1])
+def test_gemm_batched_matches_fp64(ops, tri_k):
+    """lit_gemm_tf32x3_nt_batched: 5 equally shaped products in one launch (3-D tensor maps), with Cin / beta, and the
+    triangular K-loop start used for the inverse Cholesky factors."""
+    import ctypes as C
+
+    import torch
+
+    rng = np.random.default_rng(77 + tri_k)
+    nb, M, N, K = 5, 300, 520, 520
+    A = rng.standard_normal((nb, M, K)).astype(np.float32)
+    B = rng.standard_normal((nb, N, K)).astype(np.float32)
+    if tri_k:
+        B = np.triu(B)  # B[n][k] == 0 for k < n
+    Cin = rng.standard_normal((nb, M, N)).astype(np.float32)
+    ld = 544
+    dev = ops.device
+
+    def planes(x, rows):
+        full = np.zeros((nb, rows + 3, ld), dtype=np.float32)  # batch stride deliberately larger than the matrix
+        full[:, :rows, : x.shape[2]] = x
+        t = torch.from_numpy(full).to(dev)
+        hi = (t.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)  # rna to tf32 (positive half-ulp bias ok)
+        lo = t - hi
+        lo = (lo.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)
+        return hi.contiguous(), lo.contiguous(), (rows + 3) * ld
+
+    Ah, Al, sa = planes(A, M)
+    Bh, Bl, sb = planes(B, N)
+    Ct = torch.zeros((nb, M, ld), dtype=torch.float32, device=dev)
+    Ct[:, :, :N] = torch.from_numpy(Cin).to(dev)
+    D = torch.empty((nb, M, ld), dtype=torch.float32, device=dev)
+    vp = C.c_void_p
+    rc = ops.lib.lit_gemm_tf32x3_nt_batched(vp(Ah.data_ptr()), vp(Al.data_ptr()), ld, sa, vp(Bh.data_ptr()),
+                                            vp(Bl.data_ptr()), ld, sb, M, N, K, -0.5, vp(Ct.data_ptr()), ld, M * ld, 2.0,
+                                            vp(D.data_ptr()), vp(0), ld, M * ld, nb, tri_k, vp(ops.stream))
+    assert rc == 0, ops.lib.lit_last_error()
+    got = D.cpu().numpy()[:, :, :N].astype(np.float64)
+    Aeff = (Ah + Al).cpu().numpy()[:, :M, :K].astype(np.float64)
+    Beff = (Bh + Bl).cpu().numpy()[:, :N, :K].astype(np.float64)
+    ref = -0.5 * np.einsum("bmk,bnk->bmn", Aeff, Beff) + 2.0 * Cin.astype(np.float64)
+    scale = np.einsum("bmk,bnk->bmn", np.abs(Aeff), np.abs(Beff)).max()
+    assert np.abs(got - ref).max() < 2e-6 * scale, np.abs(got - ref).max() / scale
+
+
+@pytest.mark.parametrize("p,rows", [(512, (300, 333, 300)), (200, (70,)), (3072, (1500, 1520))])
+def test_direct_solver_matches_fp64(ops, p, rows):
+    """DeviceOps.solve_blocks_many (batched blocked Cholesky of [G + a^2 I; P_c; I] on the tensor cores) against
+    fp64 LAPACK: several folds with different validation-row counts, a feature count that is not a multiple of the
+    128-column panel, the BASELINE shape; the a-posteriori probe passes, and a non-positive-definite system is flagged."""
+    from litcoder_core_b200.engine import SolverAccuracyError
+
+    rng = np.random.default_rng(p)
+    n = max(2 * p, 1000)
+    X = rng.standard_normal((n, p)).astype(np.float32)
+    for t in range(1, n):
+        X[t] = 0.6 * X[t - 1] + 0.8 * X[t]
+    for j in range(1, p):
+        X[:, j] = 0.5 * X[:, j - 1] + 0.87 * X[:, j]
+    alphas = np.logspace(-1, 8, 20)
+    jobs, refs = [], []
+    for f, m in enumerate(rows):
+        Xf = X[f * 50: n - 100 * f]
+        G = Xf.T.astype(np.float64) @ Xf.astype(np.float64)
+        G32 = G.astype(np.float32)
+        lmax = float(np.linalg.eigvalsh(G)[-1])
+        Pc = rng.standard_normal((m, p)).astype(np.float32)
+        Pc -= Pc.mean(0)
+        a2 = [(a ** 2) * lmax for a in alphas]
+        jobs.append(dict(G=ops.upload_matrix(G32), Pc=ops.upload_matrix(Pc), n_rows=m, lam_max=lmax, a2=a2))
+        refs.append((G32.astype(np.float64), Pc.astype(np.float64), a2))
+    blocks = ops.solve_blocks_many(jobs)
+    ops.check_solver()
+    assert ops.last_solver_residual < 2e-5, ops.last_solver_residual
+    for job, block, (G, Pc, a2) in zip(jobs, blocks, refs):
+        m = job["n_rows"]
+        got = ops.download_matrix(block).astype(np.float64)
+        cheb, series = ops.solver_partition(job["lam_max"], a2)
+        assert len(cheb) == 4 and got.shape[0] == 7 * m
+        for i, j in enumerate(cheb):
+            exact = np.linalg.solve(G + a2[j] * np.eye(p), Pc.T).T
+            err = np.abs(got[i * m:(i + 1) * m] - exact).max() / np.abs(exact).max()
+            assert err < 1e-5, (p, m, j, err)
+        Q = Pc
+        for q in range(3):
+            Q = Q @ G
+            blk = got[(4 + q) * m:(5 + q) * m]
+            assert np.abs(blk - Q).max() < 2e-5 * np.abs(Q).max()
+    # an indefinite "Gram": flagged by the pivot check and rejected by check_solver
+    Gbad = refs[0][0].astype(np.float32).copy()
+    Gbad[np.arange(p), np.arange(p)] -= 2.0 * refs[0][2][0] + 0.5 * np.float32(jobs[0]["lam_max"])
+    bad = dict(jobs[0], G=ops.upload_matrix(Gbad))
+    ops.solve_blocks_many([bad])
+    with pytest.raises(SolverAccuracyError):
+        ops.check_solver()
+
+
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
     """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
     very small alphas; the default golden tests above exercise the GEMM-only route."""
@@ -916,20 +1013,20 @@ def test_leave_block_out_agrees_on_fit(ops, monkeypatch):
     X, Y = _synthetic(rng, 800, 160, 900)
     kw = dict(n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 8, 20))
     out = {}
-    for flag in ("0", "1"):
+    for direct, flag in (("0", "0"), ("0", "1"), ("1", "0")):  # Chebyshev p x p, leave-block-out, batched Cholesky
+        monkeypatch.setenv("LIT_DIRECT_SOLVER", direct)
         monkeypatch.setenv("LIT_LEAVE_BLOCK_OUT", flag)
         random.seed(5)
-        m, w, a = NestedCVModel("ridge_regression", ops=ops).fit_predict(X, Y, inner_solver="chebyshev", **kw)
-        out[flag] = (np.asarray(m["correlations"]), w, np.asarray(a))
-    same = out["0"][2] == out["1"][2]
-    assert same.mean() > 0.97, same.mean()
-    assert np.abs(out["0"][0][same] - out["1"][0][same]).max() < 2e-5
-    random.seed(5)
-    mo, wo, ao = O.fit_predict(X, Y, vectorised_stats=True, **kw)
-    same = np.isclose(out["1"][2], ao)
-    assert same.mean() > 0.9, same.mean()
-    assert np.abs(out["1"][0][same] - np.asarray(mo["correlations"], dtype=np.float64)[same]).max() < 1e-4
-    assert np.abs(out["1"][1][:, same] - wo[:, same]).max() < 1e-4 * np.abs(wo).max()
+        model = NestedCVModel("ridge_regression", ops=ops)
+        m, w, a = model.fit_predict(X, Y, inner_solver="chebyshev", **kw)
+        out[direct, flag] = (np.asarray(m["correlations"]), w, np.asarray(a))
+        # every route is held to the oracle by the full proof (near-ties proven, all voxels compared)
+        info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 5, max_ambiguous=4, **kw)
+        assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], (direct, flag, info)
+    for key in (("0", "1"), ("1", "0")):
+        same = out["0", "0"][2] == out[key][2]
+        assert same.mean() > 0.97, same.mean()
+        assert np.abs(out["0", "0"][0][same] - out[key][0][same]).max() < 2e-5
 
 
 def test_structure_kernels_match_reference_trainer(ops):

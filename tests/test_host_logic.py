@@ -453,6 +453,7 @@ def test_leave_block_out_matches_chebyshev_route_on_fake_ops(monkeypatch):
     g = load_golden("fit_predict.npz")
     X, Y, alphas = g["X"], g["Y"], g["alphas"].tolist()
     kw = dict(folding_type="chunked", n_outer_folds=4, n_inner_folds=3, chunk_length=10, alphas=alphas)
+    monkeypatch.setenv("LIT_DIRECT_SOLVER", "0")  # the round-1 iterative routes (kept as options)
     out = {}
     for flag in ("0", "1"):
         monkeypatch.setenv("LIT_LEAVE_BLOCK_OUT", flag)
@@ -488,7 +489,7 @@ def test_leave_block_out_matches_chebyshev_route_on_fake_ops(monkeypatch):
     tr_o, te = np.arange(300), np.arange(300, 400)
     for val, n_lbo in ((np.arange(250, 300), 0), (np.arange(200, 300), 3)):
         ops = FakeOps()
-        cfg = E.RidgeConfig(alphas=alphas, inner_solver="chebyshev", n_outer_folds=1)
+        cfg = E.RidgeConfig(alphas=alphas, inner_solver="chebyshev", n_outer_folds=1, direct_solver=False)
         RidgeCVEngine(ops).fit_shard(FMat(X[:400]), FMat(Y[:400]), [FoldPlan(tr_o, te, [(np.arange(200), val)])], cfg)
         assert getattr(ops, "lbo_solved", 0) == n_lbo and ops.solver_calls == 1
 
@@ -501,7 +502,7 @@ GRID20 = {"tt_grid20": dict(train_test=True), "cv_grid20": dict(train_test=False
 @pytest.mark.parametrize("solver", ["auto", "eig"])
 def test_engine_on_the_baseline_alpha_grid_matches_reference_golden(name, solver):
     """The reference's own output on np.logspace(-1, 8, 20) (fit_predict_grid20.npz): with the default solver the
-    inner folds run the compact stack (16 series alphas) and the leave-block-out solves (4 small alphas)."""
+    inner folds run the compact stack (16 series alphas) and the batched direct solves (4 small alphas)."""
     g, X, Y, test, common = _golden_args(name)
     tt = bool(test)
     ops = FakeOps()
@@ -509,10 +510,9 @@ def test_engine_on_the_baseline_alpha_grid_matches_reference_golden(name, solver
     np.random.seed(7)
     model = NestedCVModel("ridge_regression", ops=ops)
     m, w, va = model.fit_predict(X, Y, inner_solver=solver, **test, **common)
-    # 4 small alphas per leave-block-out fold; in train/test mode one of the 3 inner folds validates on 140 of 400
-    # rows (more than half of its 260 training rows), is not downdated and keeps the direct solve
-    n_lbo_folds = 2 if tt else 12
-    assert getattr(ops, "lbo_solved", 0) == (4 * n_lbo_folds if solver == "auto" else 0)
+    # the 4 small alphas of every inner fold go through the batched direct (Cholesky) solver, all folds at once
+    assert getattr(ops, "direct_solved", 0) == (4 * (3 if tt else 12) if solver == "auto" else 0)
+    assert getattr(ops, "lbo_solved", 0) == 0
     info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
     assert info["disagreeing_alphas"] <= 0.05 * info["voxel_folds"]
 
