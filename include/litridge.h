@@ -126,7 +126,7 @@ int lit_split_tf32(const float* src, long rows, long cols, long ld_src, float* h
 int lit_transpose_f32(const float* src, long rows, long cols, long ld_src, float* dst, float* dst_lo, long ld_dst,
                       void* stream);
 /* dst[i][:] = src[idx[i]][:] for i < n_idx, zero rows for n_idx <= i < n_rows_out.
- * idx == NULL means the identity (a padded copy).  Optional split output.
+ * idx == NULL means the identity (a padded copy); a negative idx[i] gives a zero row.  Optional split output.
  * Replaces the fancy-index gathers at nested_cv.py:200-201,371-374. */
 int lit_gather_rows_f32(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, float* dst,
                         float* dst_lo, long ld_dst, long n_rows_out, void* stream);
@@ -245,6 +245,21 @@ int lit_gemm_tf32x3_nt_batched(const float* A_hi, const float* A_lo, long lda, l
                                const float* B_lo, long ldb, long bs_b, int M, int N, int K, float alpha, const float* Cin,
                                long ldc, long bs_c, float beta, float* D, float* D_lo, long ldd, long bs_d, int batch,
                                int tri_k, void* stream);
+/* Grouped product for the eigendecomposition-free outer fit:  D[rows of tile t] = A[rows of tile t] * B_g^T  with
+ * g = tile_group[t] (DEVICE int32 per 256-row tile of A; negative: skip), B a stack of n_groups (N x K) split pairs at
+ * stride bs_b floats.  A holds the cross products X^T y of the voxels SORTED by their selected alpha (lit_group_plan),
+ * B_g = (X^T X + a_g^2 I)^-1: the weights of ridge_torch (ridge_regression.py:52-61: one dense product per unique
+ * alpha over the voxels that selected it) without an eigendecomposition and without a host round trip for the
+ * group sizes.  M must be a multiple of 256. */
+int lit_gemm_tf32x3_nt_grouped(const float* A_hi, const float* A_lo, long lda, const float* B_hi, const float* B_lo,
+                               long ldb, long bs_b, int n_groups, int M, int N, int K, const int32_t* tile_group,
+                               float* D, float* D_lo, long ldd, void* stream);
+/* Deterministic counting sort of n_vox voxels by idx[v] in [0, n_groups <= 32) into a layout whose groups are padded to
+ * multiples of `tile` rows: pos[v] = grouped row of voxel v; perm[s] = voxel at grouped row s or -1 (s < rows_cap);
+ * tile_group[t] = group of row tile t or -1 (t < rows_cap / tile).  rows_cap >= round_up(n_vox, tile) + n_groups * tile.
+ * Replaces the torch.unique / boolean-mask selection of ridge_regression.py:52-58. */
+int lit_group_plan(const int32_t* idx, long n_vox, int n_groups, int tile, long rows_cap, int32_t* pos, int32_t* perm,
+                   int32_t* tile_group, void* stream);
 /* Batched direct solve of the small-alpha systems of the inner folds:  M_b = R_b (G_b + a2_b I)^-1  for up to 128
  * systems of one size at once (G_b: n x n symmetric, pitch ldg; R_b: m_b x n, pitch ldr, m_b <= mp), by a blocked
  * Cholesky factorisation of the augmented matrix [G + a2 I; R; I] whose panel and trailing updates are batched

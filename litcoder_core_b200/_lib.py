@@ -58,6 +58,8 @@ PROTOTYPES = {
     "lit_lanczos_lambda_max_batched": [_vp, _i, _l, _i, _i, _vp, _vp, _vp, _vp],
     "lit_gemm_tf32x3_nt_batched": [_vp, _vp, _l, _l, _vp, _vp, _l, _l, _i, _i, _i, _f, _vp, _l, _l, _f, _vp, _vp, _l, _l,
                                    _i, _i, _vp],
+    "lit_gemm_tf32x3_nt_grouped": [_vp, _vp, _l, _vp, _vp, _l, _l, _i, _i, _i, _i, _vp, _vp, _vp, _l, _vp],
+    "lit_group_plan": [_vp, _l, _i, _i, _l, _vp, _vp, _vp, _vp],
     "lit_spd_solve_workspace": [_i, _i, _i, _psz, _psz, _psz, _pl, _pl],
     "lit_spd_solve_batched": [_i, _i, _i, _vp, _l, _vp, _l, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "lit_spd_probe_residual": [_i, _i, _vp, _l, _vp, _l, _vp, _vp, _vp, _l, _l, _vp, _vp, _vp],

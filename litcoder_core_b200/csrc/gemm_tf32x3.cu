@@ -84,6 +84,10 @@ struct GemmParams {
   // tri_k: B is upper triangular in the sense B[n][k] == 0 for k < n (rows of an inverse Cholesky factor):
   // the K loop of a tile starts at its first B row instead of 0.
   int tri_k;
+  // Grouped launches (EPI_STORE): A and D are single matrices whose row tiles (of BM * CG rows) belong to groups;
+  // row tile mt multiplies B operand number tile_group[mt] (B is a stack of n_groups matrices whose stride is part of
+  // its 3-D tensor map); tile_group[mt] < 0: nothing to do for that row tile.
+  const int* tile_group;
 };
 
 // F16_ = 0: operands are fp32 planes holding TF32 values (kind::tf32, 8 values of K per MMA);
@@ -127,12 +131,14 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
 }
 
 // Batched tile index -> (batch, m tile, n tile); first k-block of the tile (tri_k: see GemmParams).
+// Returns the index of the B operand (= b for batched launches, the row tile's group for grouped ones; < 0: skip).
 template <int BN, int BK>
-__device__ __forceinline__ void batch_tile_coords(const GemmParams& p, int tile, int& b, int& mt, int& nt, int& kb_begin) {
+__device__ __forceinline__ int batch_tile_coords(const GemmParams& p, int tile, int& b, int& mt, int& nt, int& kb_begin) {
   const int per = p.num_m_tiles * p.num_n_tiles;
   b = tile / per;
   tile_coords(p, tile - b * per, mt, nt);
   kb_begin = p.tri_k ? min((nt * BN) / BK, p.num_k_blocks - 1) : 0;
+  return p.tile_group ? __ldg(p.tile_group + mt) : b;
 }
 
 template <int BN, int CG, int EPI, int F16 = 0>
@@ -193,7 +199,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         uint32_t phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
           int b, mt, nt, kb_begin;
-          batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+          const int bb = batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+          if (bb < 0) continue;
           const int m_row = (mt * CG + (int)cta_rank) * S::BM;
           const int n_row = nt * BN + (int)cta_rank * S::B_ROWS;
           for (int kb = kb_begin; kb < p.num_k_blocks; ++kb) {
@@ -204,15 +211,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
               ptx::mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
               ptx::tma_load_3d(st, &tmAh, &full_bar[stage], k0, m_row, b);
               ptx::tma_load_3d(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row, b);
-              ptx::tma_load_3d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, b);
-              ptx::tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, b);
+              ptx::tma_load_3d(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, bb);
+              ptx::tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, bb);
             } else {
               // Both CTAs load their halves; all bytes are accounted on the leader's barrier.
               if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
               ptx::tma_load_3d_2sm(st, &tmAh, &full_bar[stage], k0, m_row, b);
               ptx::tma_load_3d_2sm(st + S::A_BYTES, &tmAl, &full_bar[stage], k0, m_row, b);
-              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, b);
-              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, b);
+              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES, &tmBh, &full_bar[stage], k0, n_row, bb);
+              ptx::tma_load_3d_2sm(st + 2 * S::A_BYTES + S::B_BYTES, &tmBl, &full_bar[stage], k0, n_row, bb);
             }
             if (++stage == S::STAGES) {
               stage = 0;
@@ -230,7 +237,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         uint32_t cc = 0;  // running chunk counter: TMEM buffer = cc & 1
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
           int b, mt, nt, kb_begin;
-          batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+          if (batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin) < 0) continue;
           for (int kb0 = kb_begin; kb0 < p.num_k_blocks; kb0 += p.kc_blocks, ++cc) {
             const uint32_t buf = cc & 1u;
             ptx::mbar_wait(&tmem_empty_bar[buf], ((cc >> 1) & 1u) ^ 1u);
@@ -282,7 +289,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
     float acc[COLS];
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       int b, mt, nt, kb_begin;
-      batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin);
+      if (batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin) < 0) continue;
       const int num_chunks = (p.num_k_blocks - kb_begin + p.kc_blocks - 1) / p.kc_blocks;
       if constexpr (EPI == EPI_STORE) {
         // Cin of this tile towards L2 now: it is read only after the tile's MMAs, several microseconds from here
@@ -568,15 +575,16 @@ static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it 
 
 template <int BN, int CG, int EPI, int F16 = 0>
 static int launch_gemm(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
-                       GemmParams p, cudaStream_t stream, long bs_a = 0, long bs_b = 0) {
+                       GemmParams p, cudaStream_t stream, long bs_a = 0, long bs_b = 0, int n_groups = 0) {
   using S = GemmShape<BN, CG, F16>;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   int rc;
   if (p.batch < 1) p.batch = 1;
+  const int b_count = n_groups > 0 ? n_groups : p.batch;  // grouped: B is a stack of n_groups matrices, A / D are single
   if ((rc = make_operand_map(&tmAh, A_hi, p.M, p.K, lda, S::BM, F16, p.batch, bs_a))) return rc;
   if ((rc = make_operand_map(&tmAl, A_lo, p.M, p.K, lda, S::BM, F16, p.batch, bs_a))) return rc;
-  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS, F16, p.batch, bs_b))) return rc;
-  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS, F16, p.batch, bs_b))) return rc;
+  if ((rc = make_operand_map(&tmBh, B_hi, p.N, p.K, ldb, S::B_ROWS, F16, b_count, bs_b))) return rc;
+  if ((rc = make_operand_map(&tmBl, B_lo, p.N, p.K, ldb, S::B_ROWS, F16, b_count, bs_b))) return rc;
 
   p.num_m_tiles = (p.M + S::BM * CG - 1) / (S::BM * CG);
   p.num_n_tiles = (p.N + BN - 1) / BN;
@@ -694,6 +702,32 @@ int gemm_nt_batched(const float* A_hi, const float* A_lo, long lda, long bs_a, c
   return launch_gemm<256, 1, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, s, bs_a, bs_b);
 }
 }  // namespace lit
+
+// Grouped product: D[rows of tile t] = A[rows of tile t] * B_{tile_group[t]}^T for the 256-row tiles of A (the
+// voxels of the outer fit, sorted by their selected alpha; B_g = (G + a_g^2 I)^-1).  tile_group lives on the DEVICE,
+// so no host synchronisation is needed to learn the group sizes; tiles with a negative group are skipped.
+extern "C" int lit_gemm_tf32x3_nt_grouped(const float* A_hi, const float* A_lo, long lda, const float* B_hi,
+                                          const float* B_lo, long ldb, long bs_b, int n_groups, int M, int N, int K,
+                                          const int32_t* tile_group, float* D, float* D_lo, long ldd, void* stream) {
+  LIT_REQUIRE(M >= 0 && N >= 0 && K >= 0 && n_groups >= 1, "gemm_grouped: bad extents");
+  LIT_REQUIRE(M % 256 == 0, "gemm_grouped: the row count must be padded to a multiple of the 256-row tile");
+  LIT_REQUIRE(tile_group != nullptr, "gemm_grouped: tile_group missing");
+  LIT_REQUIRE(ldd % 4 == 0 && ldd >= N && (reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm_grouped: output alignment");
+  LIT_REQUIRE(!D_lo || (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0, "D_lo alignment");
+  if (M == 0 || N == 0) return LIT_OK;
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.D = D;
+  p.D_lo = D_lo;
+  p.ldd = ldd;
+  p.alpha = 1.f;
+  p.batch = 1;
+  p.tile_group = tile_group;
+  return launch_gemm<256, 2, EPI_STORE>(A_hi, A_lo, lda, B_hi, B_lo, ldb, p, static_cast<cudaStream_t>(stream), 0, bs_b,
+                                        n_groups);
+}
 
 extern "C" int lit_gemm_tf32x3_nt_batched(const float* A_hi, const float* A_lo, long lda, long bs_a, const float* B_hi,
                                           const float* B_lo, long ldb, long bs_b, int M, int N, int K, float alpha,

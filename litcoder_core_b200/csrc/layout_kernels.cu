@@ -100,7 +100,7 @@ struct GatherOp {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r < n_idx) {
         const long sr = idx ? (long)idx[r] : r;
-        x = *reinterpret_cast<const float4*>(src + sr * ld_src + c);
+        if (sr >= 0) x = *reinterpret_cast<const float4*>(src + sr * ld_src + c);  // negative index: a zero row
       }
       if (dst_lo) {
         float4 h, l;
@@ -121,7 +121,7 @@ struct GatherOp {
       float x = 0.f;
       if (r < n_idx) {
         const long sr = idx ? (long)idx[r] : r;
-        x = src[sr * ld_src + c];
+        if (sr >= 0) x = src[sr * ld_src + c];
       }
       if (dst_lo) {
         const float h = ptx::to_tf32(x);

@@ -440,9 +440,86 @@ __global__ void argmax_alpha_kernel(const float* __restrict__ corr_sum, long ld_
   }
 }
 
+// Deterministic counting sort of the voxels by their selected alpha index (one block: V is ~1e5 and the keys < 32).
+//   pos[v]         row of voxel v in the grouped layout: groups in index order, each padded to a multiple of `tile` rows
+//   perm[s]        voxel at grouped row s, -1 for padding rows                  (s < rows_cap)
+//   tile_group[t]  group of the t-th row tile, -1 past the last group           (t < rows_cap / tile)
+__global__ void __launch_bounds__(1024) group_plan_kernel(const int32_t* __restrict__ idx, long n_vox, int n_groups,
+                                                          int tile, long rows_cap, int32_t* __restrict__ pos,
+                                                          int32_t* __restrict__ perm, int32_t* __restrict__ tile_group) {
+  extern __shared__ int cnt[];  // [n_groups][1024] per-thread counts -> offsets inside the group
+  __shared__ int warp_tot[32];
+  __shared__ long start[33];
+  const int t = threadIdx.x;
+  const long chunk = (n_vox + 1023) / 1024;
+  const long v0 = t * chunk, v1 = min(n_vox, v0 + chunk);
+  for (int g = 0; g < n_groups; ++g) cnt[g * 1024 + t] = 0;
+  for (long v = v0; v < v1; ++v) {
+    const int g = min(max(idx[v], 0), n_groups - 1);
+    cnt[g * 1024 + t]++;
+  }
+  for (long s = t; s < rows_cap; s += 1024) perm[s] = -1;
+  __syncthreads();
+  if (t == 0) start[0] = 0;
+  for (int g = 0; g < n_groups; ++g) {  // exclusive scan of the group's counts over the threads
+    const int c = cnt[g * 1024 + t];
+    int x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((t & 31) >= o) x += y;
+    }
+    if ((t & 31) == 31) warp_tot[t >> 5] = x;
+    __syncthreads();
+    if (t < 32) {
+      int w = warp_tot[t];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (t >= o) w += y;
+      }
+      warp_tot[t] = w;  // inclusive
+    }
+    __syncthreads();
+    const int before = (t >> 5) ? warp_tot[(t >> 5) - 1] : 0;
+    cnt[g * 1024 + t] = before + x - c;
+    if (t == 0) start[g + 1] = start[g] + ((long)(warp_tot[31] + tile - 1) / tile) * tile;
+    __syncthreads();
+  }
+  for (long v = v0; v < v1; ++v) {
+    const int g = min(max(idx[v], 0), n_groups - 1);
+    const long s = start[g] + cnt[g * 1024 + t]++;
+    pos[v] = (int32_t)s;
+    perm[s] = (int32_t)v;
+  }
+  for (long tl = t; tl < rows_cap / tile; tl += 1024) {
+    const long r = tl * tile;
+    int g = -1;
+    for (int q = 0; q < n_groups; ++q)
+      if (r >= start[q] && r < start[q + 1]) g = q;
+    tile_group[tl] = g;
+  }
+}
+
 }  // namespace lit
 
 using namespace lit;
+
+extern "C" int lit_group_plan(const int32_t* idx, long n_vox, int n_groups, int tile, long rows_cap, int32_t* pos,
+                              int32_t* perm, int32_t* tile_group, void* stream) {
+  LIT_REQUIRE(n_vox >= 0 && n_groups >= 1 && n_groups <= 32 && tile >= 1, "group_plan: bad extents");
+  LIT_REQUIRE(rows_cap % tile == 0 && rows_cap >= ((n_vox + tile - 1) / tile + n_groups) * tile,
+              "group_plan: rows_cap must be a multiple of the tile and >= round_up(n_vox, tile) + n_groups * tile");
+  static bool attr_set = false;
+  const int smem = n_groups * 1024 * (int)sizeof(int);
+  if (!attr_set) {
+    LIT_CUDA_CHECK(cudaFuncSetAttribute(group_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));
+    attr_set = true;
+  }
+  group_plan_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(idx, n_vox, n_groups, tile, rows_cap, pos, perm, tile_group);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
 
 extern "C" int lit_col_stats(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, int ddof,
                              float* mean, float* stdv, double* scratch, void* stream) {

@@ -952,6 +952,97 @@ class DeviceOps:
                 self._solver_checks.append((rel, info[k:k + nc]))
                 k += nc
 
+    # ------------------------------------------------------------------ eigendecomposition-free outer fit
+    GROUP_TILE = 256  # rows per tile of the grouped GEMM (one CTA pair)
+
+    def outer_inverses(self, G: Mat, lam_max: float, a2_list, series_ratio: float = 60.0):
+        """(G + a^2 I)^-1 for every alpha of the grid as ONE stack of split pairs [n_alphas][p][ld] (the B operands of
+        gemm_grouped).  The alphas below the series threshold go through the batched Cholesky solver (elimination of
+        [G + a^2 I; I] gives W = L^-T, then W W^T); the others are 4-term Neumann polynomials in G, G^2, G^3.
+        Replaces the per-unique-alpha `Vh.T @ diag(S / (S^2 + a^2))` of ridge_regression.py:56-61 (no SVD / syevd)."""
+        t = self.torch
+        p, ld = G.rows, G.ld
+        nA = len(a2_list)
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        f32 = dict(dtype=t.float32, device=self.device)
+        inv_hi, inv_lo = t.empty((nA, p, ld), **f32), t.empty((nA, p, ld), **f32)
+        s = _vp(self.stream)
+        if cheb:
+            nsys = len(cheb)
+            fF, fS, fD, ldw, rows = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_long(0), C.c_long(0)
+            check(self.lib.lit_spd_solve_workspace(nsys, p, 0, C.byref(fF), C.byref(fS), C.byref(fD), C.byref(ldw),
+                                                   C.byref(rows)), "spd_solve_workspace")
+            ldw, rows = ldw.value, rows.value
+            F = t.empty((fF.value,), **f32)
+            S_hi, S_lo = t.empty((fS.value,), **f32), t.empty((fS.value,), **f32)
+            Dg_hi, Dg_lo = t.empty((fD.value,), **f32), t.empty((fD.value,), **f32)
+            info = t.empty((nsys,), dtype=t.int32, device=self.device)
+            Gp, Rp, mh, a2h = (C.c_void_p * nsys)(), (C.c_void_p * nsys)(), (C.c_int * nsys)(), (C.c_float * nsys)()
+            for k, j in enumerate(cheb):
+                Gp[k], Rp[k], mh[k], a2h[k] = G.hi.data_ptr(), G.hi.data_ptr(), 0, a2_list[j]
+            with self.timed("spd_solve"):
+                check(self.lib.lit_spd_solve_batched(nsys, p, 0, C.cast(Gp, _vp), ld, C.cast(Rp, _vp), ld,
+                                                     C.cast(mh, _vp), C.cast(a2h, _vp), _vp(F.data_ptr()),
+                                                     _vp(S_hi.data_ptr()), _vp(S_lo.data_ptr()), _vp(Dg_hi.data_ptr()),
+                                                     _vp(Dg_lo.data_ptr()), _vp(info.data_ptr()), s), "spd_solve_batched")
+                self.launches += 1 + 4 * (ldw // 128)
+                sys_stride = rows * ldw
+                w0 = ldw * ldw * 4  # rows [ldw, 2 ldw): W = L^-T
+                contiguous = list(cheb) == list(range(cheb[0], cheb[0] + nsys))
+                for k0, k1 in ([(0, nsys)] if contiguous else [(k, k + 1) for k in range(nsys)]):
+                    j0 = cheb[k0]
+                    check(self.lib.lit_gemm_tf32x3_nt_batched(
+                        _vp(S_hi.data_ptr() + w0 + k0 * sys_stride * 4), _vp(S_lo.data_ptr() + w0 + k0 * sys_stride * 4),
+                        ldw, sys_stride, _vp(S_hi.data_ptr() + w0 + k0 * sys_stride * 4),
+                        _vp(S_lo.data_ptr() + w0 + k0 * sys_stride * 4), ldw, sys_stride, p, p, p, 1.0, _vp(0), 0, 0, 0.0,
+                        _vp(inv_hi.data_ptr() + j0 * p * ld * 4), _vp(inv_lo.data_ptr() + j0 * p * ld * 4), ld, p * ld,
+                        k1 - k0, 1, s), "gemm_nt_batched")
+                    self.launches += 1
+            self._solver_checks.append((None, info))
+        if series:
+            Gs = self.split(G)
+            G2 = self.gemm(Gs, Gs, split_out=True, ld_out=ld)
+            G3 = self.gemm(G2, Gs, split_out=True, ld_out=ld)
+            eye = t.eye(p, ld, **f32)  # plumbing: the q = 0 term of the series
+            hi = (C.c_void_p * 4)(eye.data_ptr(), Gs.hi.data_ptr(), G2.hi.data_ptr(), G3.hi.data_ptr())
+            lo = (C.c_void_p * 4)(0, Gs.lo.data_ptr(), G2.lo.data_ptr(), G3.lo.data_ptr())
+            coef = np.array([[(-1.0) ** q / float(a2_list[j]) ** (q + 1) for q in range(4)] for j in series],
+                            dtype=np.float64)
+            d_coef = self.upload_vector(coef.reshape(-1), "f64")
+            d_slots = self.upload_vector(np.asarray(series), "i32")
+            check(self.lib.lit_poly_combine(C.cast(hi, _vp), C.cast(lo, _vp), 4, ld, p, p, p, _vp(d_coef.data_ptr()),
+                                            _vp(d_slots.data_ptr()), len(series), _vp(inv_hi.data_ptr()),
+                                            _vp(inv_lo.data_ptr()), ld, s), "poly_combine")
+            self.launches += 1
+        return (inv_hi, inv_lo, nA, p, ld)
+
+    def group_plan(self, idx, n_vox: int, n_groups: int):
+        """Counting sort of the voxels by alpha index (lit_group_plan): (pos, perm, tile_group, rows_cap)."""
+        tile = self.GROUP_TILE
+        cap = (-(-max(n_vox, 1) // tile) + n_groups) * tile
+        pos, perm, tg = self.vec(n_vox, "i32"), self.vec(cap, "i32"), self.vec(cap // tile, "i32")
+        check(self.lib.lit_group_plan(_vp(idx.data_ptr()), n_vox, n_groups, tile, cap, _vp(pos.data_ptr()),
+                                      _vp(perm.data_ptr()), _vp(tg.data_ptr()), _vp(self.stream)), "group_plan")
+        self.launches += 1
+        return pos, perm, tg, cap
+
+    def gemm_grouped(self, A: Mat, inv, tile_group, split_out: bool = True) -> Mat:
+        """out[rows of tile t] = A[rows of tile t] @ inv[tile_group[t]]^T (lit_gemm_tf32x3_nt_grouped)."""
+        inv_hi, inv_lo, nA, p, ld = inv
+        if A.cols != p or not A.is_split or A.rows % self.GROUP_TILE:
+            raise ValueError("gemm_grouped: A must be a split pair of tile-padded rows with p columns")
+        out = self.empty(A.rows, p, split=split_out)
+        self._apply_sm_limit()
+        with self.timed("gemm"):
+            check(self.lib.lit_gemm_tf32x3_nt_grouped(
+                _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(inv_hi.data_ptr()), _vp(inv_lo.data_ptr()), ld,
+                p * ld, nA, A.rows, p, p, _vp(tile_group.data_ptr()), _vp(out.hi.data_ptr()),
+                _vp(out.lo.data_ptr() if split_out else 0), out.ld, _vp(self.stream)), "gemm_grouped")
+        self.launches += 1
+        self.store_gemms += 1
+        self.gemm_flops += 2.0 * A.rows * p * p
+        return out
+
     def check_solver(self) -> None:
         """Raise SolverAccuracyError if a direct inner solve since the last check was not positive definite or
         failed its a-posteriori probe (synchronises; called once per fit next to check_eig)."""
@@ -961,11 +1052,13 @@ class DeviceOps:
         self.torch.cuda.synchronize(self.device)
         worst, bad = 0.0, 0
         for rel, info in checks:
+            bad += int((info.cpu().numpy() != 0).sum())
+            if rel is None:
+                continue
             nd = rel.cpu().numpy().reshape(-1, 2)
             with np.errstate(divide="ignore", invalid="ignore"):
                 r = np.where(nd[:, 1] > 0, np.sqrt(nd[:, 0] / nd[:, 1]), np.where(nd[:, 0] > 0, np.inf, 0.0))
             worst = max(worst, float(np.max(r)) if np.isfinite(r).all() else float("inf"))
-            bad += int((info.cpu().numpy() != 0).sum())
         self.last_solver_residual = worst
         if bad or not (worst <= self.SOLVER_TOL):
             raise SolverAccuracyError(f"direct inner solve rejected: {bad} systems not positive definite, worst probe "

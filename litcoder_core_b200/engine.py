@@ -39,7 +39,7 @@ flow can be unit-tested on CPU with a NumPy stand-in (tests/fake_ops.py).
 from __future__ import annotations
 
 import logging
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -91,6 +91,10 @@ class RidgeConfig:
     # all systems of this rank's folds together, a few batched launches per 128-column panel) instead of Chebyshev
     # iteration; supersedes leave_block_out (no dependence on the outer fold's eigendecomposition)
     direct_solver: bool = True
+    # primal outer folds under the same conditions: weights without an eigendecomposition -- (G_o + a^2 I)^-1 per grid
+    # alpha (batched Cholesky / Neumann polynomials, DeviceOps.outer_inverses) and ONE grouped GEMM over the voxels
+    # sorted by their selected alpha (DeviceOps.gemm_grouped); no syevd is left on the default path
+    direct_outer: bool = True
     # keep the fold-mean inner score curves (n_alphas x V_r per outer fold) for the caller (tests: near-tie proofs)
     record_scores: bool = False
 
@@ -255,14 +259,18 @@ class RidgeCVEngine:
                     d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if need_G else ops.empty(p, p))
             inners.append(d)
         outer["owner"] = self._next_outer_owner()
-        if not outer["dual"]:
+        outer["direct"] = bool(not outer["dual"] and cfg.direct_outer and cfg.direct_solver and self._use_chebyshev(cfg))
+        if outer["direct"]:
+            outer["G"] = outer["G_keep"] = G_o  # no decomposition: the Gram itself is what the outer fit uses
+            outer["cheb"] = True  # lambda_max by Lanczos with the inner folds' (see _finish_design)
+        elif not outer["dual"]:
             outer["G"] = ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o
             outer["G_keep"] = G_o
         # Queue the eigendecompositions this rank owns (inner folds first: they are needed first).  With
         # several ranks every eigenproblem is solved once, by rank (job index mod world), and broadcast when
         # it is consumed: X is replicated, so the 30 decompositions of a fit would otherwise be redundant.
         for d in inners + [outer]:
-            if d.get("cheb"):
+            if d.get("cheb"):  # (a direct outer fold counts as one: no decomposition of its own)
                 # GEMM-only fold: lambda_max by Lanczos now (read back once for all folds by fit_shard)
                 d["lam"], d["ticket"] = None, None
                 d["lmax_dev"] = None  # all folds' Lanczos runs advance together: see _finish_design
@@ -384,17 +392,20 @@ class RidgeCVEngine:
         return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2,
                                   series_moments=cfg.series_moments)
 
-    def _finish_design(self, groups, cfg: RidgeConfig) -> None:
+    def _finish_design(self, groups, cfg: RidgeConfig, outers=None) -> None:
         """After the design side of every plan is queued: read the Lanczos lambda_max of all GEMM-only folds back
         in ONE synchronisation (and, with several ranks, exchange them in ONE all-reduce), then -- with several
         ranks -- solve this rank's folds right away so that no rank waits for another one's solve when the fold
         is consumed.  groups: list of (X, inners)."""
         ops, comm = self.ops, self.comm
         jobs = [(X, d) for X, inners in groups for d in inners if d.get("cheb")]
+        n_inner_jobs = len(jobs)
+        jobs += [(None, o) for o in (outers or []) if o.get("direct")]  # every rank needs every outer lambda_max
         if not jobs:
             return
         vals = np.zeros(len(jobs), dtype=np.float64)
-        for idx in self._same_shape_groups([(i, d["G"]) for i, (_, d) in enumerate(jobs) if d["owner"] == comm.rank]):
+        mine = lambda i, d: d["owner"] == comm.rank  # noqa: E731  (outer folds: their owner, then all-reduced)
+        for idx in self._same_shape_groups([(i, d["G"]) for i, (_, d) in enumerate(jobs) if mine(i, d)]):
             got = np.asarray(ops.download(ops.lambda_max_batched([jobs[i][1]["G"] for i in idx]))).reshape(-1)
             vals[idx] = got[: len(idx)]
         if comm.world > 1:
@@ -404,8 +415,9 @@ class RidgeCVEngine:
             # every rank holds every lambda_max after the all-reduce: all of them raise together (an owner-only
             # check would leave the other ranks waiting in the broadcast of the fold's solution block)
             self._check_lmax(float(v), cfg)
+        jobs = jobs[:n_inner_jobs]
         if cfg.direct_solver:
-            # every fold this rank owns, all outer folds at once: batched Cholesky solves (32 systems per launch)
+            # every fold this rank owns, all outer folds at once: batched Cholesky solves (128 systems per launch)
             with ops.timed("phase_inner_solve"):
                 self._solve_direct([(X, d) for X, d in jobs if d["owner"] == comm.rank], cfg)
         elif comm.world > 1:
@@ -530,11 +542,13 @@ class RidgeCVEngine:
     def _select_alphas(self, corr_sum, n_folds: int, alphas_dev, cfg: RidgeConfig, n_vox_total: int):
         """nested_cv._find_best_alphas :391-413 -> device vector of per-voxel alpha values."""
         ops = self.ops
-        _, alpha_v, sums = ops.argmax_alpha(corr_sum, n_folds, alphas_dev, want_sums=cfg.single_alpha)
+        best, alpha_v, sums = ops.argmax_alpha(corr_sum, n_folds, alphas_dev, want_sums=cfg.single_alpha)
         if cfg.single_alpha:
             tot = self.comm.all_reduce_sum(np.asarray(ops.download(sums), dtype=np.float64)[: len(cfg.alphas)])
             j = int(np.argmax((tot / float(n_vox_total)).astype(np.float32)))
             alpha_v = ops.upload_vector(np.full(corr_sum.cols, np.float32(cfg.alphas[j]), dtype=np.float32), "f32")
+            best = ops.upload_vector(np.full(corr_sum.cols, j, dtype=np.int32), "i32")
+        self._best_idx = best  # alpha INDEX per voxel (the grouped outer fit sorts the voxels by it)
         return alpha_v
 
     # ------------------------------------------------------------------------------------------
@@ -557,6 +571,15 @@ class RidgeCVEngine:
         """ridge_torch (ridge_regression.py:29-63) for every voxel at once -> W^T (V_r x p split).
         Primal: W^T = ZS V^T.  Dual: W^T = ZS (X_tr^T U)^T with U the eigenvectors of X_tr X_tr^T."""
         ops = self.ops
+        if outer.get("direct") and getattr(self, "_best_idx", None) is not None:
+            # ridge_torch without a decomposition: W^T[v] = C^T[v] (G_o + a_v^2 I)^-1, one grouped GEMM over the voxels
+            # sorted by alpha index (a_v = alpha_v * S[0] of the OUTER training set, S[0]^2 = lambda_max by Lanczos)
+            lam_max = float(outer["lmax"])
+            inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))
+            pos, perm, tile_group, cap = ops.group_plan(self._best_idx, Ct_o.rows, len(cfg.alphas))
+            sorted_ct = ops.gather_rows(Ct_o, perm, cap, split=True)
+            return ops.gather_rows(ops.gemm_grouped(sorted_ct, inv, tile_group, split_out=False), pos, Ct_o.rows,
+                                   split=True)
         ZS, G = self._shrunk_coefficients(X, Y, sp, outer, Ct_o, alpha_v, cfg)
         if outer["dual"]:
             XoT = ops.gather_rows_T_split(X, sp["train"], len(sp["train_rows"]))  # (p x n_o)
@@ -598,6 +621,7 @@ class RidgeCVEngine:
         """ridge_corr_torch (ridge_regression.py:66-141): XX / YY hold the training rows followed by the
         prediction rows; returns the (n_alphas x V) score matrix (device)."""
         ops = self.ops
+        cfg = replace(cfg, direct_outer=False)  # alphas arrive as values here: the decomposition route
         sp = self._single_split(n_train, XX.rows - n_train, cfg)
         outer, inners = self._design_side(XX, sp, cfg)
         self._finish_design([(XX, inners)], cfg)
@@ -609,6 +633,7 @@ class RidgeCVEngine:
     def ridge_weights(self, X, Y, alpha_v, cfg: RidgeConfig):
         """ridge_torch (ridge_regression.py:9-63): returns W^T (V x p, split pair) on the device."""
         ops = self.ops
+        cfg = replace(cfg, direct_outer=False)  # alphas arrive as values here: the decomposition route
         sp = self._single_split(X.rows, 0, cfg)
         outer, _ = self._design_side(X, sp, cfg)
         Ct_o = None
@@ -624,6 +649,7 @@ class RidgeCVEngine:
         Returns the (1 x V) score (device); NaNs are kept, as in the reference."""
         ops = self.ops
         n_va = XX.rows - n_train
+        cfg = replace(cfg, direct_outer=False)  # alphas arrive as values here: the decomposition route
         sp = self._single_split(n_train, n_va, cfg, inner=False)
         outer, _ = self._design_side(XX, sp, cfg)
         val = sp["test"]
@@ -671,6 +697,7 @@ class RidgeCVEngine:
         X (N x p) and Y (N x V_r) are device matrices.  In train/test mode there is one plan whose
         test_rows index X_test / Y_test; in nested mode test rows index X / Y themselves."""
         ops = self.ops
+        self._best_idx = None
         alphas = np.asarray(cfg.alphas, dtype=np.float64)
         alphas_f32 = ops.upload_vector(alphas.astype(np.float32), "f32")
         alphas_f64 = ops.upload_vector(alphas, "f64")
@@ -689,7 +716,7 @@ class RidgeCVEngine:
                 Xs, Xts = self._normalised(X, Xte_src, sp["train_rows"], sp["train"], cfg.normalize_features,
                                            same_source)
                 prepared.append((Xs, Xts) + self._design_side(Xs, sp, cfg))
-            self._finish_design([(pr[0], pr[3]) for pr in prepared], cfg)
+            self._finish_design([(pr[0], pr[3]) for pr in prepared], cfg, outers=[pr[2] for pr in prepared])
         ops.wait_copy(y_ready)  # the responses may still be in flight on the copy stream: first use is below
         for plan, sp in zip(plans, staged):
             Xs, Xts, outer, inners = prepared.pop(0)

@@ -322,6 +322,7 @@ class NestedCVModel:
             Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
 
         cfg.direct_solver = os.environ.get("LIT_DIRECT_SOLVER", "1") != "0"  # development override
+        cfg.direct_outer = os.environ.get("LIT_DIRECT_OUTER", "1") != "0"  # development override
         engine = RidgeCVEngine(ops, comm)
         with ops.timed("fit"):
             res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox, y_ready=y_ready)

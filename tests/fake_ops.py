@@ -128,7 +128,11 @@ class FakeOps:
     def gather_rows(self, src, idx, n, rows_out=None, split=False):
         rows_out = n if rows_out is None else rows_out
         out = np.zeros((rows_out, src.cols), dtype=F32)
-        out[:n] = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
+        if idx is None:
+            out[:n] = src.a[:n]
+        else:
+            ix = np.asarray(idx[:n], dtype=np.int64)
+            out[:n][ix >= 0] = src.a[ix[ix >= 0]]  # a negative index gives a zero row
         return FMat(out, split)
 
     def transpose(self, src, split=False):
@@ -400,6 +404,49 @@ class FakeOps:
 
     def check_solver(self):
         pass
+
+    GROUP_TILE = 256
+
+    def outer_inverses(self, G, lam_max, a2_list, series_ratio=60.0):
+        """DeviceOps.outer_inverses: (G + a^2 I)^-1 per alpha (exact / the 4-term Neumann polynomial for the series)."""
+        Gd = G.a.astype(np.float64)
+        p = Gd.shape[0]
+        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        out = np.zeros((len(a2_list), p, p), dtype=F32)
+        for j in cheb:
+            out[j] = np.linalg.inv(Gd + float(a2_list[j]) * np.eye(p)).astype(F32)
+        if series:
+            powers = [np.eye(p), Gd, (Gd @ Gd).astype(F32).astype(np.float64)]
+            powers.append((powers[2] @ Gd).astype(F32).astype(np.float64))
+            for j in series:
+                a2 = float(a2_list[j])
+                out[j] = sum((-1.0) ** q / a2 ** (q + 1) * powers[q] for q in range(4)).astype(F32)
+        self.outer_direct = getattr(self, "outer_direct", 0) + 1
+        return out
+
+    def group_plan(self, idx, n_vox, n_groups):
+        tile = self.GROUP_TILE
+        idx = np.asarray(idx)[:n_vox].astype(np.int64)
+        cap = (-(-max(n_vox, 1) // tile) + n_groups) * tile
+        pos, perm, tg = np.zeros(n_vox, np.int32), np.full(cap, -1, np.int32), np.full(cap // tile, -1, np.int32)
+        start = 0
+        for g in range(n_groups):
+            members = np.nonzero(idx == g)[0]
+            pos[members] = start + np.arange(len(members))
+            perm[start:start + len(members)] = members
+            n_tiles = -(-len(members) // tile)
+            tg[start // tile:start // tile + n_tiles] = g
+            start += n_tiles * tile
+        return pos, perm, tg, cap
+
+    def gemm_grouped(self, A, inv, tile_group, split_out=True):
+        tile = self.GROUP_TILE
+        out = np.zeros((A.rows, A.cols), dtype=F32)
+        for t, g in enumerate(np.asarray(tile_group)):
+            if g >= 0:
+                out[t * tile:(t + 1) * tile] = (A.a[t * tile:(t + 1) * tile].astype(np.float64)
+                                                @ inv[g].astype(np.float64).T).astype(F32)
+        return FMat(out, split=split_out)
 
     @staticmethod
     def _lbo_lo(lbo, a2):

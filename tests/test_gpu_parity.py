@@ -689,6 +689,54 @@ def test_direct_solver_matches_fp64(ops, p, rows):
         ops.check_solver()
 
 
+def test_direct_outer_fit_kernels(ops):
+    """The eigendecomposition-free outer fit, piece by piece: lit_group_plan (deterministic counting sort + tile table),
+    DeviceOps.outer_inverses (batched Cholesky for the small alphas, Neumann polynomials for the large ones) and the
+    grouped GEMM against fp64: W^T[v] = C^T[v] (G + a_v^2 I)^-1."""
+    rng = np.random.default_rng(91)
+    p, V, A = 384, 5000, 20
+    X = rng.standard_normal((1500, p)).astype(np.float32)
+    for j in range(1, p):
+        X[:, j] = 0.5 * X[:, j - 1] + 0.87 * X[:, j]
+    G = (X.T.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
+    lmax = float(np.linalg.eigvalsh(G.astype(np.float64))[-1])
+    alphas = np.logspace(-1, 8, A)
+    a2 = [(a ** 2) * lmax for a in alphas]
+    idx = rng.integers(0, A, V).astype(np.int32)
+    idx[:700] = 3  # one big group; group 7 stays empty
+    idx[idx == 7] = 8
+    Ct = rng.standard_normal((V, p)).astype(np.float32)
+    # --- plan
+    d_idx = ops.upload_vector(idx, "i32")
+    pos, perm, tg, cap = ops.group_plan(d_idx, V, A)
+    pos, perm, tg = pos.cpu().numpy()[:V], perm.cpu().numpy()[:cap], tg.cpu().numpy()[: cap // 256]
+    assert cap % 256 == 0 and (perm[pos] == np.arange(V)).all() and (perm >= 0).sum() == V
+    s_idx = np.where(perm >= 0, idx[np.maximum(perm, 0)], -1)
+    for t in range(cap // 256):
+        blk = s_idx[t * 256:(t + 1) * 256]
+        assert set(blk[blk >= 0]) <= {tg[t]} and (tg[t] >= 0 or (blk < 0).all())
+    order = perm[perm >= 0]
+    assert (np.diff(idx[order]) >= 0).all()  # groups in index order ...
+    for g in range(A):
+        assert (np.diff(order[idx[order] == g]) > 0).all()  # ... and voxels in their original order inside a group
+    # --- inverses
+    inv = ops.outer_inverses(ops.upload_matrix(G), lmax, a2)
+    ops.check_solver()
+    inv_host = (inv[0] + inv[1]).cpu().numpy()[:, :, :p].astype(np.float64)
+    G64 = G.astype(np.float64)
+    for j in range(A):
+        exact = np.linalg.inv(G64 + a2[j] * np.eye(p))
+        assert np.abs(inv_host[j] - exact).max() < 2e-6 * np.abs(exact).max(), (j, alphas[j])
+    # --- grouped product, back in voxel order
+    sorted_ct = ops.gather_rows(ops.upload_matrix(Ct), ops.upload_vector(perm, "i32"), cap, split=True)
+    Ds = ops.gemm_grouped(sorted_ct, inv, ops.upload_vector(tg, "i32"), split_out=False)
+    Wt = _mat(ops, ops.gather_rows(Ds, ops.upload_vector(pos, "i32"), V, split=True)).astype(np.float64)
+    for g in np.unique(idx):
+        sel = idx == g
+        exact = Ct[sel].astype(np.float64) @ np.linalg.inv(G64 + a2[g] * np.eye(p))
+        assert np.abs(Wt[sel] - exact).max() < 5e-6 * np.abs(exact).max(), g
+
+
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
     """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
     very small alphas; the default golden tests above exercise the GEMM-only route."""

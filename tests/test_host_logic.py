@@ -374,10 +374,10 @@ def test_dual_form_matches_oracle_on_fake_ops(N, p, label):
     n_o = (N // 5 // 5) * 5 * 4
     if label == "dual everywhere":
         assert max(ops.eig_sizes) <= n_o < p
-    elif label == "primal everywhere":
-        assert set(ops.eig_sizes) == {p}
-    else:
-        assert p in ops.eig_sizes and min(ops.eig_sizes) < p
+    elif label == "primal everywhere":  # default route: batched direct solves inside, grouped direct fit outside
+        assert not ops.eig_sizes and ops.outer_direct == 5 and ops.direct_solved > 0
+    else:  # dual inner folds keep their n x n decompositions; the primal outer fit needs none
+        assert ops.eig_sizes and max(ops.eig_sizes) < p and ops.outer_direct == 5
     info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 2, w_tol=2e-4, **kw)
     assert info["disagreeing_alphas"] <= 0.15 * info["voxel_folds"], (label, info["disagreeing_alphas"])
     # and the dual path agrees with the primal path on the same problem
@@ -412,7 +412,8 @@ def test_inner_solvers_agree_on_fake_ops(name):
     random.seed(7)
     me, we, ae = NestedCVModel("ridge_regression", ops=ops_e).fit_predict(X[:400], Y[:400], inner_solver="eig", **kw)
     n_outer = 1 if name.startswith("tt") else 4
-    assert getattr(ops_c, "solver_calls", 0) == 3 * n_outer and ops_c.eig_calls == n_outer
+    # GEMM-only route: no decomposition at all (batched direct solves inside, grouped direct fit per outer fold)
+    assert getattr(ops_c, "solver_calls", 0) == 3 * n_outer and ops_c.eig_calls == 0 and ops_c.outer_direct == n_outer
     assert getattr(ops_e, "solver_calls", 0) == 0 and ops_e.eig_calls == 4 * n_outer
     same = np.isclose(ac, ae)
     assert same.mean() > 0.95
