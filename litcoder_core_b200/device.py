@@ -956,19 +956,27 @@ class DeviceOps:
     GROUP_TILE = 256  # rows per tile of the grouped GEMM (one CTA pair)
 
     def outer_inverses(self, G: Mat, lam_max: float, a2_list, series_ratio: float = 60.0):
-        """(G + a^2 I)^-1 for every alpha of the grid as ONE stack of split pairs [n_alphas][p][ld] (the B operands of
-        gemm_grouped).  The alphas below the series threshold go through the batched Cholesky solver (elimination of
-        [G + a^2 I; I] gives W = L^-T, then W W^T); the others are 4-term Neumann polynomials in G, G^2, G^3.
-        Replaces the per-unique-alpha `Vh.T @ diag(S / (S^2 + a^2))` of ridge_regression.py:56-61 (no SVD / syevd)."""
+        """(G + a^2 I)^-1 for every alpha of the grid: see outer_inverses_many."""
+        return self.outer_inverses_many([G], [lam_max], [a2_list], series_ratio)[0]
+
+    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio: float = 60.0) -> list:
+        """For each Gram G (fp32 Mat p x p; one per outer fold): (G + a^2 I)^-1 for every alpha of the grid as ONE stack
+        of split pairs [n_alphas][p][ld] (the B operands of gemm_grouped).  The alphas below the series threshold -- of
+        ALL Grams together -- go through the batched Cholesky solver (elimination of [G + a^2 I; I] gives W = L^-T,
+        then W W^T); the others are 4-term Neumann polynomials in G, G^2, G^3.  Replaces the per-unique-alpha
+        `Vh.T @ diag(S / (S^2 + a^2))` of ridge_regression.py:56-61 (no SVD / syevd)."""
         t = self.torch
-        p, ld = G.rows, G.ld
-        nA = len(a2_list)
-        cheb, series = self.solver_partition(lam_max, a2_list, series_ratio)
+        p, ld = Gs[0].rows, Gs[0].ld
+        if any(G.rows != p or G.ld != ld for G in Gs):
+            raise ValueError("outer_inverses_many: the Grams must share one size and pitch")
         f32 = dict(dtype=t.float32, device=self.device)
-        inv_hi, inv_lo = t.empty((nA, p, ld), **f32), t.empty((nA, p, ld), **f32)
         s = _vp(self.stream)
-        if cheb:
-            nsys = len(cheb)
+        parts = [self.solver_partition(lm, a2, series_ratio) for lm, a2 in zip(lam_maxs, a2_lists)]
+        out = [(t.empty((len(a2), p, ld), **f32), t.empty((len(a2), p, ld), **f32), len(a2), p, ld) for a2 in a2_lists]
+        systems = [(i, j) for i, (cheb, _) in enumerate(parts) for j in cheb]
+        for c0 in range(0, len(systems), self.SPD_MAX_BATCH):
+            chunk = systems[c0:c0 + self.SPD_MAX_BATCH]
+            nsys = len(chunk)
             fF, fS, fD, ldw, rows = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_long(0), C.c_long(0)
             check(self.lib.lit_spd_solve_workspace(nsys, p, 0, C.byref(fF), C.byref(fS), C.byref(fD), C.byref(ldw),
                                                    C.byref(rows)), "spd_solve_workspace")
@@ -978,8 +986,8 @@ class DeviceOps:
             Dg_hi, Dg_lo = t.empty((fD.value,), **f32), t.empty((fD.value,), **f32)
             info = t.empty((nsys,), dtype=t.int32, device=self.device)
             Gp, Rp, mh, a2h = (C.c_void_p * nsys)(), (C.c_void_p * nsys)(), (C.c_int * nsys)(), (C.c_float * nsys)()
-            for k, j in enumerate(cheb):
-                Gp[k], Rp[k], mh[k], a2h[k] = G.hi.data_ptr(), G.hi.data_ptr(), 0, a2_list[j]
+            for k, (i, j) in enumerate(chunk):
+                Gp[k], Rp[k], mh[k], a2h[k] = Gs[i].hi.data_ptr(), Gs[i].hi.data_ptr(), 0, a2_lists[i][j]
             with self.timed("spd_solve"):
                 check(self.lib.lit_spd_solve_batched(nsys, p, 0, C.cast(Gp, _vp), ld, C.cast(Rp, _vp), ld,
                                                      C.cast(mh, _vp), C.cast(a2h, _vp), _vp(F.data_ptr()),
@@ -987,34 +995,42 @@ class DeviceOps:
                                                      _vp(Dg_lo.data_ptr()), _vp(info.data_ptr()), s), "spd_solve_batched")
                 self.launches += 1 + 4 * (ldw // 128)
                 sys_stride = rows * ldw
-                w0 = ldw * ldw * 4  # rows [ldw, 2 ldw): W = L^-T
-                contiguous = list(cheb) == list(range(cheb[0], cheb[0] + nsys))
-                for k0, k1 in ([(0, nsys)] if contiguous else [(k, k + 1) for k in range(nsys)]):
-                    j0 = cheb[k0]
+                k = 0
+                while k < nsys:  # runs of consecutive alpha slots of one Gram share a batched launch
+                    k1 = k + 1
+                    while k1 < nsys and chunk[k1][0] == chunk[k][0] and chunk[k1][1] == chunk[k1 - 1][1] + 1:
+                        k1 += 1
+                    i, j0 = chunk[k]
+                    w0 = (k * sys_stride + ldw * ldw) * 4  # rows [ldw, 2 ldw) of system k: W = L^-T
                     check(self.lib.lit_gemm_tf32x3_nt_batched(
-                        _vp(S_hi.data_ptr() + w0 + k0 * sys_stride * 4), _vp(S_lo.data_ptr() + w0 + k0 * sys_stride * 4),
-                        ldw, sys_stride, _vp(S_hi.data_ptr() + w0 + k0 * sys_stride * 4),
-                        _vp(S_lo.data_ptr() + w0 + k0 * sys_stride * 4), ldw, sys_stride, p, p, p, 1.0, _vp(0), 0, 0, 0.0,
-                        _vp(inv_hi.data_ptr() + j0 * p * ld * 4), _vp(inv_lo.data_ptr() + j0 * p * ld * 4), ld, p * ld,
-                        k1 - k0, 1, s), "gemm_nt_batched")
+                        _vp(S_hi.data_ptr() + w0), _vp(S_lo.data_ptr() + w0), ldw, sys_stride,
+                        _vp(S_hi.data_ptr() + w0), _vp(S_lo.data_ptr() + w0), ldw, sys_stride, p, p, p, 1.0, _vp(0), 0, 0,
+                        0.0, _vp(out[i][0].data_ptr() + j0 * p * ld * 4), _vp(out[i][1].data_ptr() + j0 * p * ld * 4), ld,
+                        p * ld, k1 - k, 1, s), "gemm_nt_batched")
                     self.launches += 1
+                    self.gemm_flops += 1.0 * (k1 - k) * p * p * p
+                    k = k1
             self._solver_checks.append((None, info))
-        if series:
-            Gs = self.split(G)
-            G2 = self.gemm(Gs, Gs, split_out=True, ld_out=ld)
-            G3 = self.gemm(G2, Gs, split_out=True, ld_out=ld)
-            eye = t.eye(p, ld, **f32)  # plumbing: the q = 0 term of the series
-            hi = (C.c_void_p * 4)(eye.data_ptr(), Gs.hi.data_ptr(), G2.hi.data_ptr(), G3.hi.data_ptr())
-            lo = (C.c_void_p * 4)(0, Gs.lo.data_ptr(), G2.lo.data_ptr(), G3.lo.data_ptr())
-            coef = np.array([[(-1.0) ** q / float(a2_list[j]) ** (q + 1) for q in range(4)] for j in series],
+        eye = None
+        for i, (G, (cheb, series)) in enumerate(zip(Gs, parts)):
+            if not series:
+                continue
+            Gsp = self.split(G)
+            G2 = self.gemm(Gsp, Gsp, split_out=True, ld_out=ld)
+            G3 = self.gemm(G2, Gsp, split_out=True, ld_out=ld)
+            if eye is None:
+                eye = t.eye(p, ld, **f32)  # plumbing: the q = 0 term of the series
+            hi = (C.c_void_p * 4)(eye.data_ptr(), Gsp.hi.data_ptr(), G2.hi.data_ptr(), G3.hi.data_ptr())
+            lo = (C.c_void_p * 4)(0, Gsp.lo.data_ptr(), G2.lo.data_ptr(), G3.lo.data_ptr())
+            coef = np.array([[(-1.0) ** q / float(a2_lists[i][j]) ** (q + 1) for q in range(4)] for j in series],
                             dtype=np.float64)
             d_coef = self.upload_vector(coef.reshape(-1), "f64")
             d_slots = self.upload_vector(np.asarray(series), "i32")
             check(self.lib.lit_poly_combine(C.cast(hi, _vp), C.cast(lo, _vp), 4, ld, p, p, p, _vp(d_coef.data_ptr()),
-                                            _vp(d_slots.data_ptr()), len(series), _vp(inv_hi.data_ptr()),
-                                            _vp(inv_lo.data_ptr()), ld, s), "poly_combine")
+                                            _vp(d_slots.data_ptr()), len(series), _vp(out[i][0].data_ptr()),
+                                            _vp(out[i][1].data_ptr()), ld, s), "poly_combine")
             self.launches += 1
-        return (inv_hi, inv_lo, nA, p, ld)
+        return out
 
     def group_plan(self, idx, n_vox: int, n_groups: int):
         """Counting sort of the voxels by alpha index (lit_group_plan): (pos, perm, tile_group, rows_cap)."""

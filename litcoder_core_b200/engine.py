@@ -415,7 +415,17 @@ class RidgeCVEngine:
             # every rank holds every lambda_max after the all-reduce: all of them raise together (an owner-only
             # check would leave the other ranks waiting in the broadcast of the fold's solution block)
             self._check_lmax(float(v), cfg)
+        direct_outers = [o for _, o in jobs[n_inner_jobs:]]
         jobs = jobs[:n_inner_jobs]
+        if direct_outers:
+            # (G_o + a^2 I)^-1 for every outer fold and grid alpha, all Cholesky systems in one batch (every rank:
+            # 4 small systems per outer fold are cheaper than shipping 20 p x p inverses)
+            with ops.timed("phase_outer_inverses"):
+                lms = [float(o["lmax"]) for o in direct_outers]
+                invs = ops.outer_inverses_many([o["G_keep"] for o in direct_outers], lms,
+                                               [self._scaled_alphas_sq(lm, cfg.alphas, cfg) for lm in lms])
+            for o, inv in zip(direct_outers, invs):
+                o["inv"] = inv
         if cfg.direct_solver:
             # every fold this rank owns, all outer folds at once: batched Cholesky solves (128 systems per launch)
             with ops.timed("phase_inner_solve"):
@@ -574,8 +584,10 @@ class RidgeCVEngine:
         if outer.get("direct") and getattr(self, "_best_idx", None) is not None:
             # ridge_torch without a decomposition: W^T[v] = C^T[v] (G_o + a_v^2 I)^-1, one grouped GEMM over the voxels
             # sorted by alpha index (a_v = alpha_v * S[0] of the OUTER training set, S[0]^2 = lambda_max by Lanczos)
-            lam_max = float(outer["lmax"])
-            inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))
+            inv = outer.pop("inv", None)
+            if inv is None:
+                lam_max = float(outer["lmax"])
+                inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))
             pos, perm, tile_group, cap = ops.group_plan(self._best_idx, Ct_o.rows, len(cfg.alphas))
             sorted_ct = ops.gather_rows(Ct_o, perm, cap, split=True)
             return ops.gather_rows(ops.gemm_grouped(sorted_ct, inv, tile_group, split_out=False), pos, Ct_o.rows,

@@ -424,6 +424,9 @@ class FakeOps:
         self.outer_direct = getattr(self, "outer_direct", 0) + 1
         return out
 
+    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio=60.0):
+        return [self.outer_inverses(G, lm, a2, series_ratio) for G, lm, a2 in zip(Gs, lam_maxs, a2_lists)]
+
     def group_plan(self, idx, n_vox, n_groups):
         tile = self.GROUP_TILE
         idx = np.asarray(idx)[:n_vox].astype(np.int64)

@@ -726,7 +726,7 @@ def test_direct_outer_fit_kernels(ops):
     G64 = G.astype(np.float64)
     for j in range(A):
         exact = np.linalg.inv(G64 + a2[j] * np.eye(p))
-        assert np.abs(inv_host[j] - exact).max() < 2e-6 * np.abs(exact).max(), (j, alphas[j])
+        assert np.abs(inv_host[j] - exact).max() < 1e-5 * np.abs(exact).max(), (j, alphas[j])  # kappa = 101 at alpha 0.1
     # --- grouped product, back in voxel order
     sorted_ct = ops.gather_rows(ops.upload_matrix(Ct), ops.upload_vector(perm, "i32"), cap, split=True)
     Ds = ops.gemm_grouped(sorted_ct, inv, ops.upload_vector(tg, "i32"), split_out=False)
@@ -734,7 +734,7 @@ def test_direct_outer_fit_kernels(ops):
     for g in np.unique(idx):
         sel = idx == g
         exact = Ct[sel].astype(np.float64) @ np.linalg.inv(G64 + a2[g] * np.eye(p))
-        assert np.abs(Wt[sel] - exact).max() < 5e-6 * np.abs(exact).max(), g
+        assert np.abs(Wt[sel] - exact).max() < 2e-5 * np.abs(exact).max(), g
 
 
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
