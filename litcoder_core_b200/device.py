@@ -959,12 +959,23 @@ class DeviceOps:
         """(G + a^2 I)^-1 for every alpha of the grid: see outer_inverses_many."""
         return self.outer_inverses_many([G], [lam_max], [a2_list], series_ratio)[0]
 
-    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio: float = 60.0) -> list:
+    def outer_inverse_systems(self, lam_maxs, a2_lists, series_ratio: float = 60.0) -> list:
+        """(Gram index, alpha slot) of every inverse that needs a Cholesky solve, in the order outer_inverses_many
+        enumerates them (several ranks deal these out: `owned`)."""
+        return [(i, j) for i, (lm, a2) in enumerate(zip(lam_maxs, a2_lists))
+                for j in self.solver_partition(lm, a2, series_ratio)[0]]
+
+    def inverse_slot(self, inv, j: int) -> list:
+        """The two planes of alpha slot j of an inverse stack (for in-place collectives)."""
+        return [inv[0][j], inv[1][j]]
+
+    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio: float = 60.0, owned=None) -> list:
         """For each Gram G (fp32 Mat p x p; one per outer fold): (G + a^2 I)^-1 for every alpha of the grid as ONE stack
         of split pairs [n_alphas][p][ld] (the B operands of gemm_grouped).  The alphas below the series threshold -- of
         ALL Grams together -- go through the batched Cholesky solver (elimination of [G + a^2 I; I] gives W = L^-T,
         then W W^T); the others are 4-term Neumann polynomials in G, G^2, G^3.  Replaces the per-unique-alpha
-        `Vh.T @ diag(S / (S^2 + a^2))` of ridge_regression.py:56-61 (no SVD / syevd)."""
+        `Vh.T @ diag(S / (S^2 + a^2))` of ridge_regression.py:56-61 (no SVD / syevd).
+        owned: indices into outer_inverse_systems() to solve here (None = all); the other slots are left unwritten."""
         t = self.torch
         p, ld = Gs[0].rows, Gs[0].ld
         if any(G.rows != p or G.ld != ld for G in Gs):
@@ -974,6 +985,8 @@ class DeviceOps:
         parts = [self.solver_partition(lm, a2, series_ratio) for lm, a2 in zip(lam_maxs, a2_lists)]
         out = [(t.empty((len(a2), p, ld), **f32), t.empty((len(a2), p, ld), **f32), len(a2), p, ld) for a2 in a2_lists]
         systems = [(i, j) for i, (cheb, _) in enumerate(parts) for j in cheb]
+        if owned is not None:  # several ranks: this rank's share; the caller broadcasts the slots afterwards
+            systems = [sj for k, sj in enumerate(systems) if k in owned]
         for c0 in range(0, len(systems), self.SPD_MAX_BATCH):
             chunk = systems[c0:c0 + self.SPD_MAX_BATCH]
             nsys = len(chunk)

@@ -235,7 +235,11 @@ class RidgeCVEngine:
             d["cheb"] = False
             mine = d["owner"] == comm.rank
             if d["dual"]:
+                # kernel-matrix form: K = X_tr X_tr^T (n x n).  GEMM-only as well when the alphas allow it: the
+                # solves and the series then run on K instead of the Gram (see _inner_scores)
                 d["R"] = None
+                d["cheb"] = bool(cfg.direct_solver and self._use_chebyshev(cfg))
+                d["lbo"] = False
                 if mine:
                     XiR = ops.gather_rows(X, d["train"], n_i, split=True)  # (n_i x p)
                     d["G"] = ops.gemm(XiR, XiR)
@@ -259,9 +263,11 @@ class RidgeCVEngine:
                     d.update(XtT=XtT, XRt=None, G=ops.gemm(XtT, XtT) if need_G else ops.empty(p, p))
             inners.append(d)
         outer["owner"] = self._next_outer_owner()
-        outer["direct"] = bool(not outer["dual"] and cfg.direct_outer and cfg.direct_solver and self._use_chebyshev(cfg))
+        outer["direct"] = bool(cfg.direct_outer and cfg.direct_solver and self._use_chebyshev(cfg))
         if outer["direct"]:
-            outer["G"] = outer["G_keep"] = G_o  # no decomposition: the Gram itself is what the outer fit uses
+            # no decomposition: the Gram (primal) or kernel matrix (dual) itself is what the outer fit uses
+            outer["G_keep"] = outer["G"] if outer["dual"] else G_o
+            outer["G"] = outer["G_keep"]
             outer["cheb"] = True  # lambda_max by Lanczos with the inner folds' (see _finish_design)
         elif not outer["dual"]:
             outer["G"] = ops.copy(G_o) if any(d["R"] is not None for d in inners) else G_o
@@ -310,8 +316,16 @@ class RidgeCVEngine:
         return [(float(a) * float(s0)) ** 2 for a in alphas]
 
     def _centred_val_design(self, X, d):
+        """J P (n_v x p, primal) or J P X_tr^T (n_v x n, dual): the validation side of the fold's predictor, centred
+        over the validation rows so that predictions come out mean-free."""
         ops = self.ops
         n_va = len(d["val_rows"])
+        if d.get("dual"):
+            Pv = ops.gather_rows(X, d["val"], n_va, split=True)
+            XiR = ops.gather_rows(X, d["train"], len(d["train_rows"]), split=True)
+            Kvt = ops.gemm(Pv, XiR)  # (n_v x n), K = p
+            km, _ = ops.col_stats(Kvt, None, n_va, ddof=0)
+            return ops.gather_normalize(Kvt, None, n_va, km, None, 2, EPS)
         pm, _ = ops.col_stats(X, d["val"], n_va, ddof=0)
         return ops.gather_normalize(X, d["val"], n_va, pm, None, 2, EPS)  # (n_v x p) fp32
 
@@ -387,7 +401,8 @@ class RidgeCVEngine:
         a2 = self._scaled_alphas_sq(lam_max, alphas, cfg)
         if comm.world > 1:
             if block is None:
-                block = ops.zeros(ops.solver_block_rows(n_va, lam_max, a2), X.cols)
+                width = len(d["train_rows"]) if d.get("dual") else X.cols
+                block = ops.zeros(ops.solver_block_rows(n_va, lam_max, a2), width)
             comm.broadcast_inplace(ops.planes(block), src=d["owner"])
         return ops.assemble_stack(block, self._centred_val_design(X, d), n_va, rows_pad, lam_max, a2,
                                   series_moments=cfg.series_moments)
@@ -422,8 +437,15 @@ class RidgeCVEngine:
             # 4 small systems per outer fold are cheaper than shipping 20 p x p inverses)
             with ops.timed("phase_outer_inverses"):
                 lms = [float(o["lmax"]) for o in direct_outers]
-                invs = ops.outer_inverses_many([o["G_keep"] for o in direct_outers], lms,
-                                               [self._scaled_alphas_sq(lm, cfg.alphas, cfg) for lm in lms])
+                a2s = [self._scaled_alphas_sq(lm, cfg.alphas, cfg) for lm in lms]
+                owned = None
+                if comm.world > 1:  # the Cholesky systems are dealt out; their inverses travel by broadcast
+                    systems = ops.outer_inverse_systems(lms, a2s)
+                    owned = {k for k in range(len(systems)) if k % comm.world == comm.rank}
+                invs = ops.outer_inverses_many([o["G_keep"] for o in direct_outers], lms, a2s, owned=owned)
+                if comm.world > 1:
+                    for k, (i, j) in enumerate(systems):
+                        comm.broadcast_inplace(ops.inverse_slot(invs[i], j), src=k % comm.world)
             for o, inv in zip(direct_outers, invs):
                 o["inv"] = inv
         if cfg.direct_solver:
@@ -504,7 +526,13 @@ class RidgeCVEngine:
                 raise ValueError("inner fold needs >= 1 training and >= 2 validation samples")
             rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
             Pv = ops.gather_rows(X, d["val"], n_va, split=True)  # (n_v x p)
-            if d["dual"]:
+            if d["dual"] and d["cheb"]:
+                # dual GEMM-only fold: pred_a = [J K_vt (K_tt + a^2 I)^-1] Y_tr -- the stack lives in R^n and the
+                # "coefficients" are the training responses themselves (no cross product, no decomposition)
+                Zt = ops.gather_rows_T_split(Y, d["train"], n_tr)  # (V_r x n)
+                Lst = self._stack_from_blocks(X, d, n_alphas, rows_pad, cfg.alphas, cfg)
+                L = None
+            elif d["dual"]:
                 # dual form: Z^T = Y_tr^T U (V_r x n), L = (P X_tr^T) U (n_v x n); lam = eig(X_tr X_tr^T) = S^2
                 YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)  # (V_r x n)
                 Ut, _, lam = self._eig_ready(d)
@@ -581,6 +609,23 @@ class RidgeCVEngine:
         """ridge_torch (ridge_regression.py:29-63) for every voxel at once -> W^T (V_r x p split).
         Primal: W^T = ZS V^T.  Dual: W^T = ZS (X_tr^T U)^T with U the eigenvectors of X_tr X_tr^T."""
         ops = self.ops
+        if outer.get("direct") and outer["dual"] and getattr(self, "_best_idx", None) is not None:
+            # dual form: D^T[v] = y_v^T (K_o + a_v^2 I)^-1 (grouped GEMM over the sorted voxels), W^T = D^T X_tr
+            n_o = len(sp["train_rows"])
+            inv = outer.pop("inv", None)
+            if inv is None:
+                lam_max = float(outer["lmax"])
+                inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))
+            YoT = ops.gather_rows_T_split(Y, sp["train"], n_o)  # (V_r x n_o) split pair = fp32 exactly (hi + lo)
+            Yf = ops.zeros(YoT.rows, YoT.cols)
+            ops.axpy(1.0, YoT, Yf)
+            del YoT
+            pos, perm, tile_group, cap = ops.group_plan(self._best_idx, Yf.rows, len(cfg.alphas))
+            Dt = ops.gather_rows(ops.gemm_grouped(ops.gather_rows(Yf, perm, cap, split=True), inv, tile_group,
+                                                  split_out=False), pos, Yf.rows, split=True)
+            del Yf, inv
+            XoT = ops.gather_rows_T_split(X, sp["train"], n_o)  # (p x n_o)
+            return ops.gemm(Dt, XoT, split_out=True, precision=cfg.voxel_gemm_precision)
         if outer.get("direct") and getattr(self, "_best_idx", None) is not None:
             # ridge_torch without a decomposition: W^T[v] = C^T[v] (G_o + a_v^2 I)^-1, one grouped GEMM over the voxels
             # sorted by alpha index (a_v = alpha_v * S[0] of the OUTER training set, S[0]^2 = lambda_max by Lanczos)

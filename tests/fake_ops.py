@@ -424,8 +424,20 @@ class FakeOps:
         self.outer_direct = getattr(self, "outer_direct", 0) + 1
         return out
 
-    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio=60.0):
-        return [self.outer_inverses(G, lm, a2, series_ratio) for G, lm, a2 in zip(Gs, lam_maxs, a2_lists)]
+    def outer_inverse_systems(self, lam_maxs, a2_lists, series_ratio=60.0):
+        return [(i, j) for i, (lm, a2) in enumerate(zip(lam_maxs, a2_lists))
+                for j in self.solver_partition(lm, a2, series_ratio)[0]]
+
+    def inverse_slot(self, inv, j):
+        return [inv[j]]
+
+    def outer_inverses_many(self, Gs, lam_maxs, a2_lists, series_ratio=60.0, owned=None):
+        out = [self.outer_inverses(G, lm, a2, series_ratio) for G, lm, a2 in zip(Gs, lam_maxs, a2_lists)]
+        if owned is not None:  # the slots of other ranks arrive by broadcast: poison them here
+            for k, (i, j) in enumerate(self.outer_inverse_systems(lam_maxs, a2_lists, series_ratio)):
+                if k not in owned:
+                    out[i][j] = np.nan
+        return out
 
     def group_plan(self, idx, n_vox, n_groups):
         tile = self.GROUP_TILE

@@ -737,6 +737,30 @@ def test_direct_outer_fit_kernels(ops):
         assert np.abs(Wt[sel] - exact).max() < 2e-5 * np.abs(exact).max(), g
 
 
+@pytest.mark.parametrize("p", [5120, 16384])
+def test_dual_form_at_config3_and_config5_widths(ops, p):
+    """BASELINE config 3 / 5 feature widths (p = 5,120 / 16,384 > n): every fold runs in the kernel-matrix form --
+    batched Cholesky solves on K = X_tr X_tr^T inside, grouped direct fit outside, no decomposition -- and is held
+    to the oracle's thin SVDs (k = n components, ridge_utils.py:34-67) by the full proof."""
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(p)
+    N, V = 1500, 320
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    for t in range(1, N):  # temporally smooth rows, as FIR-delayed features are
+        X[t] = 0.5 * X[t - 1] + 0.87 * X[t]
+    W = (rng.standard_normal((p, V)) / np.sqrt(p)).astype(np.float32) * (rng.random(V) < 0.5)
+    Y = (X @ W + 2.0 * rng.standard_normal((N, V))).astype(np.float32)
+    Y[:, 3] = 0.25
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 8, 20))
+    random.seed(6)
+    model = L.NestedCVModel("ridge_regression")
+    m, w, a = model.fit_predict(X, Y, **kw)
+    assert model.last_timings.get("eig", 0.0) == 0.0  # no syevd ran
+    info = prove_fit_parity(model.last_fold_results, m, w, X, Y, 6, w_tol=2e-4, max_ambiguous=3, **kw)
+    assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], info
+
+
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
     """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
     very small alphas; the default golden tests above exercise the GEMM-only route."""
