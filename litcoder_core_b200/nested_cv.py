@@ -85,6 +85,22 @@ class TorchDistComm:
             self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, src) if self.group is not None else src,
                                  group=self.group)
 
+    def broadcast_async(self, buffers, src: int) -> list:
+        """broadcast_inplace without waiting: returns the work handles; `wait_all` makes the current stream (NCCL) or
+        the host (gloo) wait for them.  Lets the solution blocks of all inner folds travel while the GEMMs run."""
+        works = []
+        for b in buffers:
+            t = b if self._torch.is_tensor(b) else self._torch.from_numpy(b)
+            works.append(self._dist.broadcast(
+                t, src=self._dist.get_global_rank(self.group, src) if self.group is not None else src, group=self.group,
+                async_op=True))
+        return works
+
+    @staticmethod
+    def wait_all(works) -> None:
+        for w in works:
+            w.wait()
+
     def all_gather_concat(self, arr: np.ndarray, counts: Optional[Sequence[int]] = None) -> np.ndarray:
         """Concatenate the ranks' arrays along the LAST axis; counts[r] = last-axis length on rank r."""
         arr = np.ascontiguousarray(arr)

@@ -66,6 +66,13 @@ def main():
     corr.hi.normal_()
     timeit("argmax_alpha (20 x V)", A * V * 4 + V * 8, lambda: ops.argmax_alpha(corr, 5, al.float(), False), reps=5)
 
+    # round 2: operand re-split into fp16 pairs, the grouped outer fit's sort / gathers
+    timeit("split_f16 C^T (V x 3072) tf32 pair -> fp16 pair + row scales", V * p * (8 * 2 + 4), lambda: ops.split_f16(Zs, 1))
+    idx = ops.upload_vector(rng.integers(0, A, V), "i32")
+    pos, perm, tg, cap = ops.group_plan(idx, V, A)
+    timeit("group_plan: counting sort of V voxels by alpha index (1 block)", V * 4 * 3, lambda: ops.group_plan(idx, V, A))
+    timeit("gather_rows C^T by alpha group (V x 3072 f32 -> hi/lo, padded)", V * p * 4 * 3, lambda: ops.gather_rows(Ct, perm, cap, split=True))
+
     # feature construction: device-resident buffers through the C ABI (the API-level calls add H2D/D2H)
     nt, D = 9400, 768
     stim = torch.randn((nt, D), device="cuda")
