@@ -77,8 +77,12 @@ def load_reference() -> Optional[SimpleNamespace]:
         from encoding.features.FIR_expander import FIR
         from encoding.models.nested_cv import NestedCVModel
         from encoding.models.ridge_regression import ridge_corr_torch, ridge_torch
+        try:
+            from encoding.utils import ModelSaver  # the consumer of fit_predict's triple (utils.py:288-354)
+        except Exception:  # noqa: BLE001
+            ModelSaver = None
     finally:
         sys.path.remove(path)
     _loaded = SimpleNamespace(NestedCVModel=NestedCVModel, ridge_corr_torch=ridge_corr_torch, ridge_torch=ridge_torch,
-                              FIR=FIR, Downsampler=Downsampler, path=path)
+                              FIR=FIR, Downsampler=Downsampler, ModelSaver=ModelSaver, path=path)
     return _loaded

@@ -761,6 +761,56 @@ def test_dual_form_at_config3_and_config5_widths(ops, p):
     assert info["disagreeing_alphas"] <= 0.1 * info["voxel_folds"], info
 
 
+def test_results_hand_off_to_the_reference_consumers(ops, tmp_path):
+    """SURVEY 8f-4 on the GPU: a fit on an fsaverage5-sized problem (2 x 10,242 vertices), then exactly what the
+    reference's trainer does with the triple -- `log_metrics` (trainer.py:322-336: scalars, np.array of the lists,
+    the length checks of BrainPlotter.log_plots, plotting_utils.py:307-323) and `ModelSaver.save_encoding_model`
+    (utils.py:324-354; the UNMODIFIED class from baseline/_ref when the reference install travelled with the snapshot)."""
+    import json
+    import pickle
+
+    import litcoder_core_b200 as L
+    from oracle import ref_shim
+
+    rng = np.random.default_rng(17)
+    N, p, V = 900, 96, 2 * 10242
+    X, Y = _synthetic(rng, N, p, V, frac=0.3, noise=3.0)
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 8, 20))
+    random.seed(2)
+    metrics, weights, best_alphas = L.fit_nested_cv(features=X, targets=Y, **kw)
+    # trainer.log_metrics
+    for k in ("median_score", "mean_score", "std_score", "n_significant"):
+        assert np.isfinite(float(metrics[k]))
+    correlations = np.array(metrics["correlations"])
+    significant_mask = np.array(metrics["significant_mask"], dtype=bool)
+    assert isinstance(metrics["correlations"], list) and isinstance(metrics["significant_mask"], list)
+    assert correlations.shape[0] == 2 * 10242 and significant_mask.shape[0] == correlations.shape[0]  # log_plots' checks
+    assert int(metrics["n_significant"]) == int(significant_mask.sum()) > 0
+    # trainer.save_model -> ModelSaver.save_encoding_model
+    hyper = {"model_kwargs": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in kw.items()}, "fir_delays": [1, 2, 3, 4]}
+    ref = None
+    try:
+        ref = ref_shim.load_reference()
+    except Exception:  # noqa: BLE001
+        pass
+    if ref is not None and ref.ModelSaver is not None:
+        run_dir = ref.ModelSaver(base_dir=str(tmp_path)).save_encoding_model(weights, best_alphas, hyper, metrics,
+                                                                             save_weights=True)
+    else:  # the same three files, restated
+        run_dir = tmp_path / "run"
+        run_dir.mkdir()
+        json.dump(hyper, open(run_dir / "hyperparams.json", "w"), indent=2)
+        np.save(run_dir / "weights.npy", weights)
+        pickle.dump(metrics, open(run_dir / "metrics.pkl", "wb"))
+    back = pickle.load(open(run_dir / "metrics.pkl", "rb"))
+    assert back.keys() == metrics.keys() and back["correlations"] == metrics["correlations"]
+    w_back = np.load(run_dir / "weights.npy")
+    assert w_back.dtype == np.float32 and w_back.shape == (p, V)
+    np.testing.assert_array_equal(w_back, weights)
+    assert json.load(open(run_dir / "hyperparams.json"))["fir_delays"] == [1, 2, 3, 4]
+    assert best_alphas.shape == (V,) and best_alphas.dtype == np.float32
+
+
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
     """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
     very small alphas; the default golden tests above exercise the GEMM-only route."""
