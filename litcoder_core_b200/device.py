@@ -324,6 +324,31 @@ class DeviceOps:
             ticket.done.record()
         ticket.issued.set()
 
+    @contextlib.contextmanager
+    def side_stream(self):
+        """Run the enclosed work on a second compute stream (ordered after what is already queued on the current
+        one); yields a ticket for wait_copy.  Used to overlap the two serial panel chains of a fit (inner solves,
+        outer inverses): each is a sequence of short launches that leaves most of the GPU idle."""
+        t = self.torch
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = t.cuda.Stream(device=self.device)
+        ready = t.cuda.Event()
+        ready.record()
+        self._side_stream.wait_event(ready)
+        ticket = _EigTicket()
+        with t.cuda.stream(self._side_stream):
+            yield ticket
+            ticket.done = t.cuda.Event()
+            ticket.done.record()
+        ticket.issued.set()
+
+    def adopt(self, tensors) -> None:
+        """Tell the caching allocator that tensors allocated on another stream are now used on the current one."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for x in tensors:
+            if self.torch.is_tensor(x):
+                x.record_stream(cur)
+
     def wait_copy(self, ticket) -> None:
         if ticket is not None and ticket.done is not None:
             self.torch.cuda.current_stream(self.device).wait_event(ticket.done)

@@ -448,7 +448,8 @@ class RidgeCVEngine:
         if direct_outers:
             # (G_o + a^2 I)^-1 for every outer fold and grid alpha, all Cholesky systems in one batch (every rank:
             # 4 small systems per outer fold are cheaper than shipping 20 p x p inverses)
-            with ops.timed("phase_outer_inverses"):
+            # on a second stream: this chain of short launches and the inner solves' below run side by side
+            with ops.side_stream() as inv_ready, ops.timed("phase_outer_inverses"):
                 lms = [float(o["lmax"]) for o in direct_outers]
                 a2s = [self._scaled_alphas_sq(lm, cfg.alphas, cfg) for lm in lms]
                 owned = None
@@ -460,7 +461,8 @@ class RidgeCVEngine:
                     for k, (i, j) in enumerate(systems):
                         comm.broadcast_inplace(ops.inverse_slot(invs[i], j), src=k % comm.world)
             for o, inv in zip(direct_outers, invs):
-                o["inv"] = inv
+                o["inv"], o["inv_ready"] = inv, inv_ready
+                ops.adopt([x for x in inv if not isinstance(x, int)] if isinstance(inv, tuple) else [])
         if cfg.direct_solver:
             # every fold this rank owns, all outer folds at once: batched Cholesky solves (128 systems per launch)
             with ops.timed("phase_inner_solve"):
@@ -636,6 +638,7 @@ class RidgeCVEngine:
             # dual form: D^T[v] = y_v^T (K_o + a_v^2 I)^-1 (grouped GEMM over the sorted voxels), W^T = D^T X_tr
             n_o = len(sp["train_rows"])
             inv = outer.pop("inv", None)
+            ops.wait_copy(outer.pop("inv_ready", None))
             if inv is None:
                 lam_max = float(outer["lmax"])
                 inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))
@@ -653,6 +656,7 @@ class RidgeCVEngine:
             # ridge_torch without a decomposition: W^T[v] = C^T[v] (G_o + a_v^2 I)^-1, one grouped GEMM over the voxels
             # sorted by alpha index (a_v = alpha_v * S[0] of the OUTER training set, S[0]^2 = lambda_max by Lanczos)
             inv = outer.pop("inv", None)
+            ops.wait_copy(outer.pop("inv_ready", None))
             if inv is None:
                 lam_max = float(outer["lmax"])
                 inv = ops.outer_inverses(outer["G_keep"], lam_max, self._scaled_alphas_sq(lam_max, cfg.alphas, cfg))

@@ -72,6 +72,13 @@ class FakeOps:
     def copy_stream(self):
         yield None
 
+    @contextlib.contextmanager
+    def side_stream(self):
+        yield None
+
+    def adopt(self, tensors):
+        pass
+
     def wait_copy(self, ticket):
         pass
 
