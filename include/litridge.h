@@ -144,6 +144,10 @@ int lit_fill_f32(float* dst, size_t n, float value, void* stream);
  * host-side repack.  The host side of the copy may be pageable or pinned. */
 int lit_memcpy_2d(void* dst, size_t dpitch_bytes, const void* src, size_t spitch_bytes, size_t width_bytes,
                   size_t height, int kind, void* stream);
+/* 0 = pageable host memory, 1 = page-locked host memory, 2 = device / managed memory.  Pageable inputs of fit_predict
+ * (what np.vstack hands a drop-in caller; the reference copies them with torch.tensor at nested_cv.py:99-100) are
+ * staged through page-locked buffers by a background thread so that their upload overlaps the design-side work. */
+int lit_host_pointer_kind(const void* ptr);
 
 /* ------------------------------------------------------------------------------------------
  * Column statistics / normalisation  (ridge_utils.py:6-15 z_score, :70-180 DataNormalizer)

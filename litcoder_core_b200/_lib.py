@@ -37,6 +37,7 @@ PROTOTYPES = {
     "lit_axpy_f32": [_f, _vp, _vp, _l, _vp, _l, _l, _l, _vp],
     "lit_fill_f32": [_vp, _sz, _f, _vp],
     "lit_memcpy_2d": [_vp, _sz, _vp, _sz, _sz, _sz, _i, _vp],
+    "lit_host_pointer_kind": [_vp],
     "lit_col_stats": [_vp, _l, _vp, _l, _l, _i, _vp, _vp, _vp, _vp],
     "lit_gather_normalize_rows": [_vp, _l, _vp, _l, _l, _vp, _vp, _i, _f, _vp, _vp, _l, _l, _vp],
     "lit_syevd_workspace": [_i, _i, _i, _psz, _psz],

@@ -70,3 +70,15 @@ extern "C" int lit_memcpy_2d(void* dst, size_t dpitch_bytes, const void* src, si
                                    static_cast<cudaStream_t>(stream)));
   return LIT_OK;
 }
+
+// 0 = ordinary pageable host memory, 1 = page-locked (pinned / registered) host memory, 2 = device or managed memory.
+extern "C" int lit_host_pointer_kind(const void* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();  // clear the sticky "invalid value" some drivers return for unregistered pointers
+    return 0;
+  }
+  if (a.type == cudaMemoryTypeHost) return 1;
+  if (a.type == cudaMemoryTypeUnregistered) return 0;
+  return 2;
+}

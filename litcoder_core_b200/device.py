@@ -307,6 +307,76 @@ class DeviceOps:
             self.launches += 1
         return out
 
+    BG_UPLOAD_MIN_BYTES = 256 << 20  # pageable float32 blocks at least this large are uploaded by a helper thread
+    BG_CHUNK_BYTES = 64 << 20
+    BG_COPY_THREADS = 4
+
+    def upload_matrix_bg(self, host, col_start: int = 0, col_stop: Optional[int] = None):
+        """upload_matrix for the responses: returns (Mat, ticket) at once; the copy runs on the copy stream behind
+        the work already queued on the current stream and must be awaited with wait_copy(ticket).
+        A large PAGEABLE float32 array (what a drop-in caller passes) would make cudaMemcpy2DAsync block the calling
+        thread at ~10 GB/s, so a helper thread stages it through three page-locked 64 MB buffers -- filled by 4 threads
+        in parallel -- and issues truly asynchronous copies: the upload then overlaps the design side of the fit."""
+        t = self.torch
+        arr = host if isinstance(host, np.ndarray) else None
+        big = (arr is not None and arr.ndim == 2 and arr.dtype == np.float32 and arr.flags.c_contiguous
+               and arr.nbytes >= self.BG_UPLOAD_MIN_BYTES and self.lib.lit_host_pointer_kind(_vp(arr.ctypes.data)) == 0)
+        if not big:
+            with self.copy_stream() as ticket:
+                out = self.upload_matrix(np.asarray(host), col_start, col_stop)
+            return out, ticket
+        n, c_all = arr.shape
+        col_stop = c_all if col_stop is None else col_stop
+        cols = col_stop - col_start
+        out = self.empty(n, cols)
+        if self._copy_stream is None:
+            self._copy_stream = t.cuda.Stream(device=self.device)
+        ready = t.cuda.Event()
+        ready.record()
+        self._copy_stream.wait_event(ready)
+        ticket = _EigTicket()
+        self.h2d_bytes += n * cols * 4
+        if n == 0 or cols == 0:
+            ticket.issued.set()
+            return out, ticket
+        threading.Thread(target=self._bg_upload, name="litridge-h2d", daemon=True,
+                         args=(arr, col_start, cols, out, ticket)).start()
+        return out, ticket
+
+    def _bg_upload(self, arr, col_start: int, cols: int, out: Mat, ticket) -> None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        t = self.torch
+        try:
+            t.cuda.set_device(self.device)
+            if getattr(self, "_bg_bufs", None) is None:
+                self._bg_bufs = [t.empty((self.BG_CHUNK_BYTES // 4,), dtype=t.float32, pin_memory=True) for _ in range(3)]
+                self._bg_pool = ThreadPoolExecutor(self.BG_COPY_THREADS, thread_name_prefix="litridge-stage")
+            stream = self._copy_stream
+            n = arr.shape[0]
+            rows_per = max(1, (self.BG_CHUNK_BYTES // 4) // cols)
+            free = [None] * len(self._bg_bufs)
+            for k, r0 in enumerate(range(0, n, rows_per)):
+                b = k % len(self._bg_bufs)
+                if free[b] is not None:
+                    free[b].synchronize()  # the DMA that last read this staging buffer has finished
+                nr = min(rows_per, n - r0)
+                view = self._bg_bufs[b].numpy()[: nr * cols].reshape(nr, cols)
+                step = -(-nr // self.BG_COPY_THREADS)
+                futs = [self._bg_pool.submit(np.copyto, view[s0:s0 + step], arr[r0 + s0:r0 + s0 + step, col_start:col_start + cols])
+                        for s0 in range(0, nr, step)]
+                for f in futs:
+                    f.result()
+                check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr() + r0 * out.ld * 4), out.ld * 4, _vp(view.ctypes.data),
+                                             cols * 4, cols * 4, nr, 1, _vp(stream.cuda_stream)), "memcpy_2d(H2D)")
+                free[b] = t.cuda.Event()
+                free[b].record(stream)
+            ticket.done = t.cuda.Event()
+            ticket.done.record(stream)
+        except BaseException as e:  # surfaced by wait_copy
+            ticket.error = e
+        ticket.issued.set()
+
     @contextlib.contextmanager
     def copy_stream(self):
         """Run the enclosed uploads on a dedicated copy stream (ordered after the work already queued on the
@@ -350,7 +420,12 @@ class DeviceOps:
                 x.record_stream(cur)
 
     def wait_copy(self, ticket) -> None:
-        if ticket is not None and ticket.done is not None:
+        if ticket is None:
+            return
+        ticket.issued.wait()  # a background upload may still be issuing its copies
+        if ticket.error is not None:
+            raise ticket.error
+        if ticket.done is not None:
             self.torch.cuda.current_stream(self.device).wait_event(ticket.done)
 
     def wrap(self, tensor) -> Mat:

@@ -333,9 +333,13 @@ class NestedCVModel:
             Xt = self._to_device(ops, X_test) if train_test_mode else None
         # The design side (Grams, lambda_max, eigendecompositions) needs X only: the responses -- 97 % of the
         # input bytes -- travel on a copy stream meanwhile and are awaited right before their first use.
-        with ops.copy_stream() as y_ready:
-            Y = self._to_device(ops, targets, c0, c1)
-            Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
+        if isinstance(targets, np.ndarray) and not train_test_mode and hasattr(ops, "upload_matrix_bg"):
+            Y, y_ready = ops.upload_matrix_bg(targets, c0, c1)  # pageable arrays: staged by a helper thread
+            Yt = None
+        else:
+            with ops.copy_stream() as y_ready:
+                Y = self._to_device(ops, targets, c0, c1)
+                Yt = self._to_device(ops, y_test, c0, c1) if train_test_mode else None
 
         cfg.direct_solver = os.environ.get("LIT_DIRECT_SOLVER", "1") != "0"  # development override
         cfg.direct_outer = os.environ.get("LIT_DIRECT_OUTER", "1") != "0"  # development override

@@ -811,6 +811,35 @@ def test_results_hand_off_to_the_reference_consumers(ops, tmp_path):
     assert best_alphas.shape == (V,) and best_alphas.dtype == np.float32
 
 
+def test_pageable_responses_are_staged_in_the_background(ops):
+    """A large pageable float32 response matrix (what np.vstack hands a drop-in caller) is uploaded by a helper thread
+    through page-locked staging buffers while the design side runs (DeviceOps.upload_matrix_bg): same results as with
+    the arrays resident on the device, bit for bit; column blocks (voxel shards) are honoured."""
+    import torch
+
+    import litcoder_core_b200 as L
+
+    rng = np.random.default_rng(5)
+    N, p, V = 720, 24, 100_000  # 288 MB of responses: above the 256 MB threshold
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    Y = rng.standard_normal((N, V), dtype=np.float32)
+    Y[:, :2000] += (X @ rng.standard_normal((p, 2000))).astype(np.float32)
+    assert ops.lib.lit_host_pointer_kind(Y.ctypes.data) == 0 and Y.nbytes >= ops.BG_UPLOAD_MIN_BYTES
+    pinned = torch.empty((4, 4), dtype=torch.float32, pin_memory=True)
+    assert ops.lib.lit_host_pointer_kind(pinned.data_ptr()) == 1
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=20, alphas=np.logspace(-1, 4, 8))
+    random.seed(1)
+    m1, w1, a1 = L.fit_nested_cv(features=X, targets=Y, **kw)
+    random.seed(1)
+    m2, w2, a2 = L.fit_nested_cv(features=torch.from_numpy(X).cuda(), targets=torch.from_numpy(Y).cuda(), **kw)
+    np.testing.assert_array_equal(a1, a2)
+    np.testing.assert_array_equal(np.asarray(m1["correlations"]), np.asarray(m2["correlations"]))
+    np.testing.assert_array_equal(w1, w2)
+    block, ticket = ops.upload_matrix_bg(Y, 4096, 4096 + 70_000)
+    ops.wait_copy(ticket)
+    np.testing.assert_array_equal(ops.download_matrix(block), Y[:, 4096:4096 + 70_000])
+
+
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
     """The eigendecomposition route stays available (inner_solver="eig") and is what runs for un-normalised or
     very small alphas; the default golden tests above exercise the GEMM-only route."""
