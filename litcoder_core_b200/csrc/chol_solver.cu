@@ -127,26 +127,59 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(const float* __restrict_
     X[i * LD + j] = 0.f;
   }
   __syncthreads();
-  const int ty = tid >> 4, tx = tid & 15;
-  for (int k = 0; k < NB; ++k) {
-    if (tid == 0) {
-      float d = A[k * LD + k];
-      if (!(d > 0.f)) {  // not positive definite (or NaN): flag it, keep going on a harmless pivot
-        bad = k + 1;
-        d = 1.f;
+  // Blocked right-looking Cholesky with 32-wide sub-panels: 3 block barriers per sub-panel instead of 3 per column
+  // (the first version of this kernel spent most of its 156 us in 384 __syncthreads).
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int c0 = 0; c0 < NB; c0 += 32) {
+    // (1) 32 x 32 diagonal sub-block by one warp, left-looking: at step j lane i forms
+    //     L[i][j] = (a[i][j] - sum_{k<j} L[i][k] L[j][k]) / L[j][j]  from rows i and j in shared memory
+    if (warp == 0) {
+      const int ri = (c0 + lane) * LD + c0;
+      for (int j = 0; j < 32; ++j) {
+        const int rj = (c0 + j) * LD + c0;
+        float sacc = A[ri + j];
+        for (int k = 0; k < j; ++k) sacc = fmaf(-A[ri + k], A[rj + k], sacc);
+        float dk = __shfl_sync(0xffffffffu, sacc, j);
+        if (!(dk > 0.f)) {  // not positive definite (or NaN): flag it, keep going on a harmless pivot
+          if (lane == 0) bad = c0 + j + 1;
+          dk = 1.f;
+        }
+        const float piv = sqrtf(dk);
+        if (lane >= j) A[ri + j] = (lane == j) ? piv : sacc / piv;
+        __syncwarp();
       }
-      A[k * LD + k] = sqrtf(d);
     }
     __syncthreads();
-    const float inv = 1.f / A[k * LD + k];
-    for (int i = k + 1 + tid; i < NB; i += 256) A[i * LD + k] *= inv;
-    __syncthreads();
-    // trailing update of the lower triangle: A[i][j] -= A[i][k] A[j][k],  k < j <= i
-    for (int i = k + 1 + ty; i < NB; i += 16) {
-      const float aik = A[i * LD + k];
-      for (int j = k + 1 + tx; j <= i; j += 16) A[i * LD + j] = fmaf(-aik, A[j * LD + k], A[i * LD + j]);
+    const int below = NB - c0 - 32;  // rows under the sub-block
+    if (below > 0) {
+      // (2) sub-panel: one thread per row r solves x L_D^T = A[r][c0 : c0+32] in place
+      if (tid < below) {
+        const int rr = (c0 + 32 + tid) * LD + c0;
+        for (int j = 0; j < 32; ++j) {
+          const int rj = (c0 + j) * LD + c0;
+          float sacc = A[rr + j];
+          for (int k = 0; k < j; ++k) sacc = fmaf(-A[rr + k], A[rj + k], sacc);
+          A[rr + j] = sacc / A[rj + j];
+        }
+      }
+      __syncthreads();
+      // (3) trailing update of the lower triangle below / right of the sub-panel: rank-32, 16 x 16 threads, each
+      //     thread owns the elements (i0 + ty + 16 m, i0 + tx + 16 n)
+      const int i0 = c0 + 32, ty = tid >> 4, tx = tid & 15;
+      for (int m = 0; m * 16 < below; ++m) {
+        const int i = i0 + ty + 16 * m;
+        for (int n2 = 0; n2 <= m; ++n2) {
+          const int j = i0 + tx + 16 * n2;
+          if (i < NB && j <= i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc = fmaf(A[i * LD + c0 + k], A[j * LD + c0 + k], acc);
+            A[i * LD + j] -= acc;
+          }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // L^-1 in 32 x 32 blocks.  (a) the four diagonal blocks by forward substitution, one column per thread:
   //   X[i][c] = (delta_ic - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i]

@@ -363,7 +363,8 @@ class DeviceOps:
                 nr = min(rows_per, n - r0)
                 view = self._bg_bufs[b].numpy()[: nr * cols].reshape(nr, cols)
                 step = -(-nr // self.BG_COPY_THREADS)
-                futs = [self._bg_pool.submit(np.copyto, view[s0:s0 + step], arr[r0 + s0:r0 + s0 + step, col_start:col_start + cols])
+                futs = [self._bg_pool.submit(np.copyto, view[s0:min(s0 + step, nr)],
+                                             arr[r0 + s0:r0 + min(s0 + step, nr), col_start:col_start + cols])
                         for s0 in range(0, nr, step)]
                 for f in futs:
                     f.result()

@@ -469,12 +469,22 @@ def test_full_width_properties(ops):
 
 def test_full_width_matches_oracle(ops):
     """BASELINE config-2 design (9,400 TRs x 3,072 features, 20 alphas, 5 inner chunked folds) on 384 voxels,
-    train/test mode, against the CPU oracle (six fp32 SVDs of 7,520 x 3,072: ~30 s of host time)."""
+    train/test mode, against the CPU oracle (six fp32 SVDs of 7,520 x 3,072: ~30 s of host time); the design is the
+    output of the repo's own Lanczos -> FIR -> z-score kernels."""
     import litcoder_core_b200 as L
 
-    rng = np.random.default_rng(21)
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import synth8d
+
+    # the design comes out of the product's OWN Lanczos -> FIR -> per-story z-score kernels (SURVEY 8d pipeline: AR(1)
+    # word embeddings, 25 stories), downloaded as fp32 so that the oracle sees the very same matrix
     N, p, V = 9400, 3072, 384
-    X, Y = _synthetic(rng, N, p, V, frac=0.5, noise=4.0)
+    X = synth8d.design_device(synth8d.make_stories("config2_gpt2_9400x3072x95000", 0), ops).cpu().numpy()
+    assert X.shape == (N, p)
+    Y = synth8d.responses_host(X, V, seed=3, true_r=0.3)
     Y[:, 7] = 1.0
     ntr = 7520
     kw = dict(n_inner_folds=5, chunk_length=20, alphas=np.logspace(-1, 8, 20))
