@@ -372,9 +372,25 @@ extern "C" int lit_spd_solve_batched(int nb, int n, int mp, const void* const* G
       long act = (long)n_pad + mp + o + CHOL_NB;  // rows that can be non-zero in this panel
       if (act > rows) act = rows;
       const long off_trail = (long)(o + CHOL_NB) * ldw + (o + CHOL_NB);
-      rc = gemm_nt_batched(S_hi + off_panel, S_lo + off_panel, ldw, sys_stride, S_hi + off_panel, S_lo + off_panel, ldw,
-                           sys_stride, (int)(act - (o + CHOL_NB)), r, CHOL_NB, -1.f, F + off_trail, ldw, sys_stride, 1.f,
-                           F + off_trail, nullptr, ldw, sys_stride, nb, 0, s);
+      const int m_upd = (int)(act - (o + CHOL_NB));
+      if (j % 2 == 0 && r > CHOL_NB) {
+        // first panel of a pair: only the NEXT 128 columns need it now (they are the second panel); the rest of the
+        // trailing matrix gets both panels at once below -- half as many K = 128 passes over the big matrix
+        rc = gemm_nt_batched(S_hi + off_panel, S_lo + off_panel, ldw, sys_stride, S_hi + off_panel, S_lo + off_panel, ldw,
+                             sys_stride, m_upd, CHOL_NB, CHOL_NB, -1.f, F + off_trail, ldw, sys_stride, 1.f,
+                             F + off_trail, nullptr, ldw, sys_stride, nb, 0, s);
+      } else if (j % 2 == 1) {
+        // second panel of a pair: rank-256 update with both panels (adjacent columns o-128 .. o+128 of S)
+        const long off_pair = off_panel - CHOL_NB;
+        rc = gemm_nt_batched(S_hi + off_pair, S_lo + off_pair, ldw, sys_stride, S_hi + off_pair, S_lo + off_pair, ldw,
+                             sys_stride, m_upd, r, 2 * CHOL_NB, -1.f, F + off_trail, ldw, sys_stride, 1.f, F + off_trail,
+                             nullptr, ldw, sys_stride, nb, 0, s);
+      } else {
+        // an unpaired first panel whose trailing matrix is a single 128-column block
+        rc = gemm_nt_batched(S_hi + off_panel, S_lo + off_panel, ldw, sys_stride, S_hi + off_panel, S_lo + off_panel, ldw,
+                             sys_stride, m_upd, r, CHOL_NB, -1.f, F + off_trail, ldw, sys_stride, 1.f, F + off_trail,
+                             nullptr, ldw, sys_stride, nb, 0, s);
+      }
       if (rc) return rc;
     }
   }
