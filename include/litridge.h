@@ -131,8 +131,9 @@ int lit_transpose_f32(const float* src, long rows, long cols, long ld_src, float
 int lit_gather_rows_f32(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, float* dst,
                         float* dst_lo, long ld_dst, long n_rows_out, void* stream);
 /* dst[c][i] = src[idx[i]][c] for i < n_idx (zero for n_idx <= i < ld_dst): gather + transpose,
- * written as a split pair; this is how the K-major (time-contiguous) operands X^T and Y^T of
- * a fold's training rows are produced. */
+ * written as a split pair (or, with dst_lo == NULL, as one fp32 plane: operands that are re-split into fp16
+ * pairs anyway); this is how the K-major (time-contiguous) operands X^T and Y^T of a fold's training rows
+ * are produced. */
 int lit_gather_rows_transpose_split(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
                                     float* dst_hi, float* dst_lo, long ld_dst, void* stream);
 /* y[i] += a * (x_hi[i] (+ x_lo[i])) over a [rows][cols] matrix (x_lo may be NULL). */

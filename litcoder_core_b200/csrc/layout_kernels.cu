@@ -387,7 +387,7 @@ extern "C" int lit_gather_rows_f32(const float* src, long ld_src, const int32_t*
 extern "C" int lit_gather_rows_transpose_split(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
                                                float* dst_hi, float* dst_lo, long ld_dst, void* stream) {
   LIT_REQUIRE(ld_src >= cols && ld_dst >= n_idx, "gather_rows_transpose: bad extents");
-  LIT_REQUIRE(dst_hi && dst_lo, "gather_rows_transpose: both planes required");
+  LIT_REQUIRE(dst_hi, "gather_rows_transpose: destination missing");  // dst_lo == NULL: plain fp32 plane
   return launch_transpose(src, ld_src, idx, n_idx, ld_dst, cols, dst_hi, dst_lo, ld_dst, (cudaStream_t)stream);
 }
 

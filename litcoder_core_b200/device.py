@@ -488,11 +488,13 @@ class DeviceOps:
         return out
 
     # ------------------------------------------------------------------ layout kernels
-    def gather_rows_T_split(self, src: Mat, idx, n: int) -> Mat:
-        out = self.empty(src.cols, n, split=True)
+    def gather_rows_T_split(self, src: Mat, idx, n: int, split: bool = True) -> Mat:
+        """(cols x n) transpose of the gathered rows; split=False: one fp32 plane (enough for an operand that is
+        re-split into fp16 pairs by its GEMM: 4 instead of 8 bytes written, 4 instead of 8 read twice)."""
+        out = self.empty(src.cols, n, split=split)
         check(self.lib.lit_gather_rows_transpose_split(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr()), n, src.cols,
-                                                       _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld,
-                                                       _vp(self.stream)), "gather_rows_transpose_split")
+                                                       _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr() if split else 0),
+                                                       out.ld, _vp(self.stream)), "gather_rows_transpose_split")
         self.launches += 1
         return out
 
@@ -580,7 +582,7 @@ class DeviceOps:
         product accuracy at twice the tensor-core rate; pays for the large voxel-side products."""
         if precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"gemm: unknown precision {precision!r}")
-        if not (A.is_split and B.is_split):
+        if precision == "tf32x3" and not (A.is_split and B.is_split):
             raise ValueError("GEMM operands must be 3xTF32 split pairs")
         if A.cols != B.cols:
             raise ValueError(f"GEMM K mismatch: {A} x {B}")

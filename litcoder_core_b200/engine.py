@@ -467,7 +467,18 @@ class RidgeCVEngine:
                 if comm.world > 1:  # the Cholesky systems are dealt out; their inverses travel by broadcast
                     systems = ops.outer_inverse_systems(lms, a2s)
                     owned = {k for k in range(len(systems)) if k % comm.world == comm.rank}
-                invs = ops.outer_inverses_many([o["G_keep"] for o in direct_outers], lms, a2s, owned=owned)
+                # (outer folds of different sizes -- ragged chunk counts in the dual form -- go in separate batches)
+                invs = [None] * len(direct_outers)
+                for idx in self._same_shape_groups([(i, o["G_keep"]) for i, o in enumerate(direct_outers)]):
+                    sub_owned = None
+                    if owned is not None:
+                        sub_sys = ops.outer_inverse_systems([lms[i] for i in idx], [a2s[i] for i in idx])
+                        glob = {s: k for k, s in enumerate(systems)}
+                        sub_owned = {k for k, (ii, j) in enumerate(sub_sys) if glob[(idx[ii], j)] in owned}
+                    got = ops.outer_inverses_many([direct_outers[i]["G_keep"] for i in idx], [lms[i] for i in idx],
+                                                  [a2s[i] for i in idx], owned=sub_owned)
+                    for i, inv in zip(idx, got):
+                        invs[i] = inv
                 if comm.world > 1:
                     for k, (i, j) in enumerate(systems):
                         comm.broadcast_inplace(ops.inverse_slot(invs[i], j), src=k % comm.world)
@@ -547,16 +558,20 @@ class RidgeCVEngine:
         Also returns C_o^T (V_r x p fp32) for a primal outer fit (None when the outer fold is dual)."""
         ops = self.ops
         vp = cfg.voxel_gemm_precision
+        # operands of the fp16-pair GEMMs are re-split by lit_split_f16 anyway: produce them as ONE fp32 plane instead
+        # of a TF32 pair (half the bytes written by the producer, half read -- twice -- by the re-split)
+        pair_y = vp != "f16x3"
+        pair_ct = cfg.corr_precision != "f16x3"
         Ct_o = None
         if not outer["dual"] and all_rows is not None and sp.get("Ro") is not None:
             # C_o^T = C_all^T - Y_Ro^T X_Ro: the all-rows cross product is formed once per fit (fit_shard)
             n_ro = len(sp["Ro_rows"])
-            YRoT = ops.gather_rows_T_split(Y, sp["Ro"], n_ro)  # (V_r x |Ro|)
+            YRoT = ops.gather_rows_T_split(Y, sp["Ro"], n_ro, split=pair_y)  # (V_r x |Ro|)
             XRoT = ops.gather_rows_T_split(X, sp["Ro"], n_ro)  # (p x |Ro|)
             Ct_o = ops.gemm(YRoT, XRoT, alpha=-1.0, Cin=all_rows["Ct"], beta=1.0, precision=vp)
             del YRoT, XRoT
         elif not outer["dual"]:
-            YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]))  # (V_r x n_o)
+            YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]), split=pair_y)  # (V_r x n_o)
             Ct_o = ops.gemm(YoT, outer["XtT"], precision=vp)  # (V_r x p), K = n_o
             del YoT
         with ops.timed("phase_lbo_prepare"):
@@ -568,11 +583,12 @@ class RidgeCVEngine:
             if n_va < 2 or n_tr < 1:
                 raise ValueError("inner fold needs >= 1 training and >= 2 validation samples")
             rows_pad = -(-n_va // ops.TILE_N) * ops.TILE_N
-            Pv = ops.gather_rows(X, d["val"], n_va, split=True)  # (n_v x p)
+            # (n_v x p) validation design: only the decomposition routes rotate it into an eigenbasis
+            Pv = None if d["cheb"] else ops.gather_rows(X, d["val"], n_va, split=True)
             if d["dual"] and d["cheb"]:
                 # dual GEMM-only fold: pred_a = [J K_vt (K_tt + a^2 I)^-1] Y_tr -- the stack lives in R^n and the
                 # "coefficients" are the training responses themselves (no cross product, no decomposition)
-                Zt = ops.gather_rows_T_split(Y, d["train"], n_tr)  # (V_r x n)
+                Zt = ops.gather_rows_T_split(Y, d["train"], n_tr, split=pair_ct)  # (V_r x n)
                 Lst = self._stack_from_blocks(X, d, n_alphas, rows_pad, cfg.alphas, cfg)
                 L = None
             elif d["dual"]:
@@ -589,12 +605,13 @@ class RidgeCVEngine:
             else:
                 # cross product of the inner training rows (downdated from the outer fold's when possible)
                 if d["R"] is not None:
-                    YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]))  # (V_r x |R|)
-                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, split_out=True, precision=vp)
+                    YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]), split=pair_y)  # (V_r x |R|)
+                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0,
+                                  split_out=pair_ct or not d["cheb"], precision=vp)
                     del YRt
                 else:
-                    YtT = ops.gather_rows_T_split(Y, d["train"], n_tr)
-                    Ct = ops.gemm(YtT, d["XtT"], split_out=True, precision=vp)
+                    YtT = ops.gather_rows_T_split(Y, d["train"], n_tr, split=pair_y)
+                    Ct = ops.gemm(YtT, d["XtT"], split_out=pair_ct or not d["cheb"], precision=vp)
                     del YtT
                 if d["cheb"]:
                     # GEMM-only fold: pred_a^T = C^T [P_c (G + a^2 I)^-1]^T, no rotation into an eigenbasis
@@ -827,7 +844,7 @@ class RidgeCVEngine:
             # (Y is then streamed once + 1/5 per outer fold instead of 4/5 per outer fold)
             with ops.timed("phase_cross_all"):
                 idx_all = ops.stage_indices([np.arange(X.rows, dtype=np.int64)])[0]
-                YaT = ops.gather_rows_T_split(Y, idx_all, X.rows)
+                YaT = ops.gather_rows_T_split(Y, idx_all, X.rows, split=cfg.voxel_gemm_precision != "f16x3")
                 XaT = ops.gather_rows_T_split(X, idx_all, X.rows)
                 all_rows = {"Ct": ops.gemm(YaT, XaT, precision=cfg.voxel_gemm_precision)}
                 del YaT, XaT

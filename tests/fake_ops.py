@@ -129,8 +129,8 @@ class FakeOps:
         return m.a.copy()
 
     # ------------------------------------------------------------------ layout
-    def gather_rows_T_split(self, src, idx, n):
-        return FMat(src.a[np.asarray(idx[:n], dtype=np.int64)].T, split=True)
+    def gather_rows_T_split(self, src, idx, n, split=True):
+        return FMat(src.a[np.asarray(idx[:n], dtype=np.int64)].T, split=split)
 
     def gather_rows(self, src, idx, n, rows_out=None, split=False):
         rows_out = n if rows_out is None else rows_out
@@ -229,7 +229,7 @@ class FakeOps:
 
     # ------------------------------------------------------------------ GEMMs
     def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None, precision="tf32x3"):
-        assert A.is_split and B.is_split, "GEMM operands must be split pairs"
+        assert precision == "f16x3" or (A.is_split and B.is_split), "3xTF32 GEMM operands must be split pairs"
         assert A.cols == B.cols and precision in ("tf32x3", "f16x3")
         if precision == "f16x3":  # lit_gemm_f16x3_nt: what the scaled fp16 pairs keep of the operands
             d = alpha * (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, 1).T)
@@ -269,7 +269,8 @@ class FakeOps:
         if stack is not None:
             assert stack.rows_pad == rows_per_group and stack.n_cheb + len(stack.slot_series) == n_groups
             B, n_plain, n_st = stack.mat, stack.n_cheb, stack.n_tiles
-        assert A.is_split and B.is_split
+        assert precision in ("tf32x3", "f16x3")
+        assert B.is_split and (A.is_split or precision == "f16x3")  # fp16 pairs are re-split from either form
         assert rows_per_group % self.TILE_N == 0 and B.rows == n_plain * rows_per_group + n_st * self.TILE_N
         assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
         assert precision in ("tf32x3", "f16x3")
