@@ -589,7 +589,9 @@ class DeviceOps:
         M, N, K = A.rows, B.rows, A.cols
         if out is None:
             out = self.empty(M, N, split=split_out, ld=ld_out)
-        if precision == "f16x3" and M and N:
+        if M == 0 or N == 0:
+            return out  # an empty voxel shard: nothing to launch
+        if precision == "f16x3":
             A, B = self.split_f16(A, 1), self.split_f16(B, 1)
         self._apply_sm_limit()
         with self.timed("gemm_f16" if isinstance(A, MatF16) else "gemm"):
