@@ -320,7 +320,8 @@ class DeviceOps:
         t = self.torch
         arr = host if isinstance(host, np.ndarray) else None
         big = (arr is not None and arr.ndim == 2 and arr.dtype == np.float32 and arr.flags.c_contiguous
-               and arr.nbytes >= self.BG_UPLOAD_MIN_BYTES and self.lib.lit_host_pointer_kind(_vp(arr.ctypes.data)) == 0)
+               and arr.shape[0] * ((arr.shape[1] if col_stop is None else col_stop) - col_start) * 4 >= self.BG_UPLOAD_MIN_BYTES
+               and self.lib.lit_host_pointer_kind(_vp(arr.ctypes.data)) == 0)
         if not big:
             with self.copy_stream() as ticket:
                 out = self.upload_matrix(np.asarray(host), col_start, col_stop)

@@ -845,9 +845,15 @@ def test_pageable_responses_are_staged_in_the_background(ops):
     np.testing.assert_array_equal(a1, a2)
     np.testing.assert_array_equal(np.asarray(m1["correlations"]), np.asarray(m2["correlations"]))
     np.testing.assert_array_equal(w1, w2)
-    block, ticket = ops.upload_matrix_bg(Y, 4096, 4096 + 70_000)
-    ops.wait_copy(ticket)
-    np.testing.assert_array_equal(ops.download_matrix(block), Y[:, 4096:4096 + 70_000])
+    # a voxel shard (column block) of the pageable array, through the helper thread as well (strided source rows)
+    saved = ops.BG_UPLOAD_MIN_BYTES
+    ops.BG_UPLOAD_MIN_BYTES = 64 << 20
+    try:
+        block, ticket = ops.upload_matrix_bg(Y, 4096, 4096 + 70_003)
+        ops.wait_copy(ticket)
+    finally:
+        ops.BG_UPLOAD_MIN_BYTES = saved
+    np.testing.assert_array_equal(ops.download_matrix(block), Y[:, 4096:4096 + 70_003])
 
 
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
