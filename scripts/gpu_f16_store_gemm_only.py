@@ -1,0 +1,42 @@
+"""Launch only the fp16-pair store GEMM at the shape of an inner fold's cross-product downdate
+(C_i^T = C_o^T - Y_R^T X_R: 95,000 x 3,072, K = 1,500, Cin) for `ncu --set full` captures; prints CUDA-event times."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+
+    from litcoder_core_b200.device import DeviceOps, Mat
+
+    ops = DeviceOps()
+    M, N, K = 95000, 3072, 1500
+    A = ops.split_f16(Mat(torch.randn((M, K), device="cuda"), None, M, K), 1)
+    B = ops.split_f16(Mat(torch.randn((N, K), device="cuda"), None, N, K), 1)
+    Cin = ops.empty(M, N)
+    Cin.hi.normal_()
+    out = ops.empty(M, N)
+    import ctypes as C
+
+    from litcoder_core_b200.device import _vp, check
+
+    times = []
+    for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(ops.lib.lit_gemm_f16x3_nt(_vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()),
+                                        _vp(B.lo.data_ptr()), B.ld, M, N, K, -1.0, _vp(Cin.hi.data_ptr()), Cin.ld, 1.0,
+                                        _vp(out.hi.data_ptr()), _vp(0), out.ld, _vp(A.inv_scale.data_ptr()),
+                                        _vp(B.inv_scale.data_ptr()), 0, _vp(ops.stream)), "gemm_f16x3_nt")
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    fl = 2.0 * M * N * K
+    print(json.dumps({"M": M, "N": N, "K": K, "ms": times, "algorithmic_tflops": [fl / t / 1e9 for t in times]}))
+
+
+if __name__ == "__main__":
+    main()
