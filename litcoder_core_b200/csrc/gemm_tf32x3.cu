@@ -565,7 +565,8 @@ static int group_m_default(int cg) {
     const char* e = getenv("LIT_GEMM_GROUP_M");
     return e ? atoi(e) : 0;
   }();
-  return v > 0 ? v : 32 / cg;  // 16 CTA pairs: ~3 % faster than 8 on the config-2 fused GEMM (gpurun_out/group_m_sweep.log)
+  return v > 0 ? v : 24 / cg;  // 12 CTA pairs: least DRAM traffic (19.6 GB vs 27.4 at 8, 22.5 at 16) and 1-3 % faster on the
+                               // config-2 fused GEMM (profiles/r2_group_m_sweep.md)
 }
 
 static int g_sm_limit = [] {  // 0 = use every SM; LIT_GEMM_SM_LIMIT presets it (development knob)
