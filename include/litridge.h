@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LITRIDGE_ABI_VERSION 5
+#define LITRIDGE_ABI_VERSION 6
 
 const char* lit_last_error(void);
 int lit_abi_version(void);
@@ -111,6 +111,31 @@ int lit_gemm_corr_series(int precision, const void* A_hi, const void* A_lo, long
  * counterpart; the reference multiplies fp32 tensors, ridge_regression.py:32,104,120.) */
 int lit_split_f16(const float* src_hi, const float* src_lo, long ld_src, long rows, long cols, long rows_per_group,
                   void* out_hi, void* out_lo, long ld_out, float* inv_scale, void* scratch, void* stream);
+
+/* fp16 pairs written by the PRODUCER (no lit_split_f16 pass): the scale of a row comes from a bound known beforehand.
+ *   lit_gather_col_reduce: out_sumsq[c] = sum_r src[idx[r]][c]^2, out_absmax[c] = max_r |src[idx[r]][c]| (either
+ *     may be NULL; idx == NULL: rows 0..n_idx-1; negative index = zero row).
+ *   lit_row_absmax: out[r] = max_c |src[r][c]|.
+ *   lit_f16_bound_scales: bound[r] = absmax[r] + sqrt(row_sumsq[r] * max_j col_sumsq[j]) (absmax or the norm pair may
+ *     be NULL); scale[r] = 2^k with bound * (1 + 2^-10) * scale in [2^14, 2^15), inv_scale[r] = 1 / scale[r]
+ *     (both 1 for a zero or non-finite bound).  For the downdated cross product C_i^T = C_o^T - Y_R^T X_R the bound
+ *     is max_j |C_o^T[v][j]| + |y_(v,R)|_2 max_j |x_(j,R)|_2 (Cauchy-Schwarz on the removed rows).
+ *   lit_gather_rows_transpose_f16: dst[c][r] = fp16 pair of scale[c] * src[idx[r]][c], columns r in [n_idx, ld_dst)
+ *     zero-filled (the gathered response rows of a fold as GEMM operand, scale[c] from the column maximum of |Y|).
+ *   lit_gemm_f16x3_nt_pairout: lit_gemm_f16x3_nt whose epilogue writes H = fp16 pair of out_scale[row] * D (pitch ldh
+ *     in fp16 elements, multiple of 4) and, when D != NULL, D itself.
+ * (Operand format only, as lit_split_f16: the reference multiplies fp32 tensors, ridge_regression.py:32,104,120.) */
+int lit_gather_col_reduce(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols, float* out_sumsq,
+                          float* out_absmax, void* stream);
+int lit_row_absmax(const float* src, long ld_src, long rows, long cols, float* out, void* stream);
+int lit_f16_bound_scales(const float* absmax, const float* row_sumsq, const float* col_sumsq, long n_cs, long rows,
+                         float* scale, float* inv_scale, void* stream);
+int lit_gather_rows_transpose_f16(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                                  const float* scale, void* dst_hi, void* dst_lo, long ld_dst, void* stream);
+int lit_gemm_f16x3_nt_pairout(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+                              int M, int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D,
+                              long ldd, const float* inv_a, const float* inv_b, const float* out_scale, void* H_hi,
+                              void* H_lo, long ldh, int variant, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / conversion (bandwidth-bound streaming kernels)

@@ -11,7 +11,7 @@ from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblitridge.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _vp, _l, _i, _f, _d, _sz = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_double, C.c_size_t
 _psz, _pi, _pl = C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_long)
@@ -28,6 +28,12 @@ PROTOTYPES = {
     "lit_gemm_f16x3_nt": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _f, _vp, _l, _f, _vp, _vp, _l, _vp, _vp, _i, _vp],
     "lit_gemm_corr_series": [_i, _vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _i, _i, _vp, _l, _vp, _vp, _vp, _l, _i, _vp],
     "lit_split_f16": [_vp, _vp, _l, _l, _l, _l, _vp, _vp, _l, _vp, _vp, _vp],
+    "lit_gather_col_reduce": [_vp, _l, _vp, _l, _l, _vp, _vp, _vp],
+    "lit_row_absmax": [_vp, _l, _l, _l, _vp, _vp],
+    "lit_f16_bound_scales": [_vp, _vp, _vp, _l, _l, _vp, _vp, _vp],
+    "lit_gather_rows_transpose_f16": [_vp, _l, _vp, _l, _l, _vp, _vp, _vp, _l, _vp],
+    "lit_gemm_f16x3_nt_pairout": [_vp, _vp, _l, _vp, _vp, _l, _i, _i, _i, _f, _vp, _l, _f, _vp, _l, _vp, _vp, _vp, _vp,
+                                  _vp, _l, _i, _vp],
     "lit_convert_f64_to_f32": [_vp, _vp, _sz, _vp],
     "lit_convert_f32_to_f64": [_vp, _vp, _sz, _vp],
     "lit_split_tf32": [_vp, _l, _l, _l, _vp, _vp, _l, _vp],

@@ -122,6 +122,151 @@ split_f16_kernel(const float* __restrict__ hi, const float* __restrict__ lo, lon
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scales chosen from a BOUND instead of the data, so that a producer can write fp16 pairs directly.
+//
+// The cross product of an inner fold is the outer fold's minus the removed rows' contribution,
+// C_i^T = C_o^T - Y_R^T X_R, so |C_i^T[v][j]| <= max_j |C_o^T[v][j]| + |y_{v,R}|_2 max_j |x_{j,R}|_2 (Cauchy-Schwarz on
+// the removed rows only: typically within 2^3 of the true row maximum).  A gathered response row never exceeds the
+// column maximum of |Y| over all rows.  Both bounds are known BEFORE the producing kernel runs; scaling the bound (plus
+// a 2^-10 rounding margin) into [2^14, 2^15) can therefore never overflow fp16, and the pair keeps the accuracy
+// stated at the top of this file as long as the true maximum is within 2^19 of the bound.
+
+// out_sumsq[c] += sum_r src[row(r)][c]^2, out_absmax[c] = max_r |src[row(r)][c]| over a slab of rows per blockIdx.y
+// (outputs zeroed by the caller; absmax as the bit pattern of a non-negative float).
+__global__ void __launch_bounds__(256)
+gather_col_reduce_kernel(const float* __restrict__ src, long ld, const int32_t* __restrict__ idx, long n_idx, long cols,
+                         float* __restrict__ out_sumsq, unsigned* __restrict__ out_absmax) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const long per = (n_idx + gridDim.y - 1) / gridDim.y;
+  const long r0 = blockIdx.y * per, r1 = min(n_idx, r0 + per);
+  float ss = 0.f, m = 0.f;
+  bool nan = false;  // fmaxf drops NaN; keep it so that the column falls back to scale 1 like lit_split_f16
+#pragma unroll 8
+  for (long r = r0; r < r1; ++r) {
+    const long sr = idx ? (long)idx[r] : r;
+    const float x = sr >= 0 ? src[sr * ld + c] : 0.f;
+    ss = fmaf(x, x, ss);
+    m = fmaxf(m, fabsf(x));
+    nan |= x != x;
+  }
+  if (r1 > r0) {
+    if (out_sumsq) atomicAdd(out_sumsq + c, ss);
+    if (out_absmax) atomicMax(out_absmax + c, nan ? 0x7fc00000u : __float_as_uint(m));
+  }
+}
+
+// bound[r] = absmax[r] + sqrt(row_sumsq[r] * max_j col_sumsq[j]); scale[r] = 2^k with bound * (1 + 2^-10) * scale in
+// [2^14, 2^15) (1 for a zero or non-finite bound).
+__global__ void __launch_bounds__(256)
+bound_scales_kernel(const unsigned* __restrict__ absmax, const float* __restrict__ row_sumsq,
+                    const float* __restrict__ col_sumsq, long n_cs, long rows, float* __restrict__ scale,
+                    float* __restrict__ inv_scale) {
+  __shared__ float red[8];
+  float cmax = 0.f;
+  if (row_sumsq && col_sumsq) {
+    for (long j = threadIdx.x; j < n_cs; j += blockDim.x) {
+      const float x = col_sumsq[j];
+      cmax = x != x ? x : fmaxf(cmax, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float y = __shfl_xor_sync(0xffffffffu, cmax, o);
+      cmax = (y != y || cmax != cmax) ? nanf("") : fmaxf(cmax, y);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cmax;
+    __syncthreads();
+    cmax = red[0];
+    for (int w = 1; w < 8; ++w) cmax = (red[w] != red[w] || cmax != cmax) ? nanf("") : fmaxf(cmax, red[w]);
+  }
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float bound = absmax ? __uint_as_float(absmax[r]) : 0.f;
+  if (row_sumsq && col_sumsq) bound += sqrtf(row_sumsq[r] * cmax);
+  bound *= 1.f + 0x1p-10f;
+  float s = 1.f, inv = 1.f;
+  if (bound > 0.f && isfinite(bound)) {
+    int e;
+    frexpf(bound, &e);
+    const int se = min(max(15 - e, -100), 100);
+    s = ldexpf(1.f, se);
+    inv = ldexpf(1.f, -se);
+  }
+  scale[r] = s;
+  inv_scale[r] = inv;
+}
+
+// dst[c][r] = fp16 pair of scale[c] * src[row(r)][c]: the gathered, transposed response rows of a fold as the A
+// operand of an fp16-pair GEMM (one scale per voxel = per output row).  64 x 64 tile through shared memory; columns
+// r in [n_rows, n_rows_pad) are zero-filled.
+__global__ void __launch_bounds__(256)
+transpose64_f16_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx, long n_rows,
+                       long n_rows_pad, long cols, const float* __restrict__ scale, __half* __restrict__ dst_hi,
+                       __half* __restrict__ dst_lo, long ld_dst, int vec) {
+  __shared__ float tile[64][65];
+  const long tiles_r = (n_rows_pad + 63) / 64;
+  const long tiles_c = (cols + 63) / 64;
+  const long total = tiles_r * tiles_c;
+  for (long t = blockIdx.x; t < total; t += gridDim.x) {
+    const long tr = t % tiles_r;  // consecutive blocks walk along the gathered rows
+    const long tc = t / tiles_r;
+    const long r0 = tr * 64, c0 = tc * 64;
+    {
+      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+      for (int k = 0; k < 64; k += 16) {
+        const long r = r0 + ty + k;
+        const long c = c0 + tx * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r < n_rows && c < cols) {
+          const long sr = idx ? (long)idx[r] : r;
+          if (sr >= 0) {
+            const float* sp = src + sr * ld_src + c;
+            if (vec && c + 3 < cols) {
+              const float4 x = *reinterpret_cast<const float4*>(sp);
+              v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+            } else {
+              for (int q = 0; q < 4 && c + q < cols; ++q) v[q] = sp[q];
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tile[ty + k][tx * 4 + q] = v[q];
+      }
+    }
+    __syncthreads();
+    {
+      const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 values (16 bytes per plane) per thread
+#pragma unroll
+      for (int k = 0; k < 64; k += 32) {
+        const long c = c0 + ty + k;  // destination row
+        const long r = r0 + tx * 8;  // destination column group
+        if (c < cols && r < n_rows_pad) {
+          const float s = scale[c];
+          __align__(16) __half vh[8];
+          __align__(16) __half vl[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) split_h(tile[tx * 8 + q][ty + k] * s, vh[q], vl[q]);
+          __half* oh = dst_hi + c * ld_dst + r;
+          __half* ol = dst_lo + c * ld_dst + r;
+          if (vec && r + 7 < n_rows_pad) {
+            *reinterpret_cast<uint4*>(oh) = *reinterpret_cast<const uint4*>(vh);
+            *reinterpret_cast<uint4*>(ol) = *reinterpret_cast<const uint4*>(vl);
+          } else {
+            for (int q = 0; q < 8 && r + q < n_rows_pad; ++q) {
+              oh[q] = vh[q];
+              ol[q] = vl[q];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace lit
 
 using namespace lit;
@@ -151,6 +296,66 @@ extern "C" int lit_split_f16(const float* src_hi, const float* src_lo, long ld_s
   split_f16_kernel<<<(unsigned)(blocks < cap * 4 ? blocks : cap * 4), 256, 0, s>>>(
       src_hi, src_lo, ld_src, rows, cols, rows_per_group, scale, static_cast<__half*>(out_hi),
       static_cast<__half*>(out_lo), ld_out, vec_out);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_gather_col_reduce(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                                     float* out_sumsq, float* out_absmax, void* stream) {
+  LIT_REQUIRE(n_idx >= 0 && cols >= 0 && ld_src >= cols, "gather_col_reduce: bad extents");
+  LIT_REQUIRE(out_sumsq || out_absmax, "gather_col_reduce: no output");
+  if (cols == 0) return LIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_sumsq) LIT_CUDA_CHECK(cudaMemsetAsync(out_sumsq, 0, (size_t)cols * sizeof(float), s));
+  if (out_absmax) LIT_CUDA_CHECK(cudaMemsetAsync(out_absmax, 0, (size_t)cols * sizeof(float), s));
+  if (n_idx == 0) return LIT_OK;
+  const long bx = (cols + 255) / 256;
+  long by = (long)sm_count() * 8 / bx;  // enough row slabs to fill the machine when there are few columns
+  by = by < 1 ? 1 : (by > 64 ? 64 : by);
+  if (by > (n_idx + 31) / 32) by = (n_idx + 31) / 32;
+  gather_col_reduce_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, s>>>(src, ld_src, idx, n_idx, cols, out_sumsq,
+                                                                            reinterpret_cast<unsigned*>(out_absmax));
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_row_absmax(const float* src, long ld_src, long rows, long cols, float* out, void* stream) {
+  LIT_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && out, "row_absmax: bad arguments");
+  if (rows == 0) return LIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  LIT_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)rows * sizeof(float), s));
+  if (cols == 0) return LIT_OK;
+  const long cap = (long)sm_count() * 8;
+  const long blocks = (rows + 7) / 8;
+  group_absmax_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, s>>>(
+      src, nullptr, ld_src, rows, cols, 1, reinterpret_cast<unsigned*>(out), aligned16(src) && ld_src % 4 == 0);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_f16_bound_scales(const float* absmax, const float* row_sumsq, const float* col_sumsq, long n_cs,
+                                    long rows, float* scale, float* inv_scale, void* stream) {
+  LIT_REQUIRE(rows >= 0 && n_cs >= 0 && scale && inv_scale, "f16_bound_scales: bad arguments");
+  LIT_REQUIRE((row_sumsq == nullptr) == (col_sumsq == nullptr), "f16_bound_scales: the two norm vectors go together");
+  LIT_REQUIRE(absmax || row_sumsq, "f16_bound_scales: no bound given");
+  if (rows == 0) return LIT_OK;
+  bound_scales_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned*>(absmax), row_sumsq, col_sumsq, n_cs, rows, scale, inv_scale);
+  LIT_LAUNCH_CHECK();
+  return LIT_OK;
+}
+
+extern "C" int lit_gather_rows_transpose_f16(const float* src, long ld_src, const int32_t* idx, long n_idx, long cols,
+                                             const float* scale, void* dst_hi, void* dst_lo, long ld_dst, void* stream) {
+  LIT_REQUIRE(ld_src >= cols && ld_dst >= n_idx && n_idx >= 0 && cols >= 0, "gather_rows_transpose_f16: bad extents");
+  LIT_REQUIRE(scale && dst_hi && dst_lo, "gather_rows_transpose_f16: null pointer");
+  if (cols == 0 || ld_dst == 0) return LIT_OK;
+  const int vec = aligned16(src) && ld_src % 4 == 0 && aligned16(dst_hi) && aligned16(dst_lo) && ld_dst % 8 == 0;
+  const long tiles = ((ld_dst + 63) / 64) * ((cols + 63) / 64);
+  const long cap = (long)sm_count() * 16;
+  transpose64_f16_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, idx, n_idx, ld_dst, cols, scale, static_cast<__half*>(dst_hi), static_cast<__half*>(dst_lo), ld_dst,
+      vec);
   LIT_LAUNCH_CHECK();
   return LIT_OK;
 }

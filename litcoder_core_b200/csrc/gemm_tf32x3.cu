@@ -40,6 +40,7 @@
 #include "../../include/litridge.h"
 
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <mutex>
 
@@ -65,6 +66,13 @@ struct GemmParams {
   // (either may be NULL = ones; lit_split_f16 writes them as inv_scale)
   const float* scale_m;
   const float* scale_n;
+  // EPI_STORE, fp16-pair output (optional, H_hi != NULL): the result is ALSO (or, with D == NULL, only) written as
+  // the scaled fp16 split pair the next fp16-pair GEMM consumes: hi = fp16(s d), lo = fp16(s d - hi) with
+  // s = out_scale[row] (a power of two chosen by the caller from a bound on |d|; see lit_f16_bound_scales).
+  __half* H_hi;
+  __half* H_lo;
+  long ldh;
+  const float* out_scale;
   // EPI_CORR
   const float* Yz;  // [parts_per_group*BN/2 rows][>= M cols], row pitch ldy
   long ldy;
@@ -349,9 +357,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const long row0 = (long)(mt * CG + (int)cta_rank) * S::BM + quad * 32;
         const int rsub = lane >> 3, chunk = lane & 7;
         const float sm_own = (p.scale_m && row_ok) ? __ldg(p.scale_m + row) : 1.f;
-        const bool has_c = p.Cin != nullptr, has_lo = p.D_lo != nullptr;
+        const bool has_c = p.Cin != nullptr, has_lo = p.D_lo != nullptr, has_d = p.D != nullptr, has_h = p.H_hi != nullptr;
+        const float os_own = (has_h && row_ok) ? __ldg(p.out_scale + row) : 1.f;
         const float* cb = has_c ? p.Cin + b * p.bs_c : nullptr;
-        float* db = p.D + b * p.bs_d;
+        float* db = has_d ? p.D + b * p.bs_d : nullptr;
         float* lb = has_lo ? p.D_lo + b * p.bs_d : nullptr;
         const uint32_t my_sts = ptx::smem_u32(stg + lane * 32);
 #pragma unroll 1
@@ -401,10 +410,36 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
               const int r = 4 * (i0 + ii) + rsub;
               const long rw = row0 + r;
               const float am = p.alpha * __shfl_sync(0xffffffffu, sm_own, r);
+              const float os = __shfl_sync(0xffffffffu, os_own, r);
               const float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((chunk ^ (r & 7)) << 2));
               if (rw >= p.M || !col_ok) continue;
               float h[4] = {am * sn[0] * v.x + p.beta * cv[ii].x, am * sn[1] * v.y + p.beta * cv[ii].y,
                             am * sn[2] * v.z + p.beta * cv[ii].z, am * sn[3] * v.w + p.beta * cv[ii].w};
+              if (has_h) {
+                __align__(8) __half ph[4];
+                __align__(8) __half pl[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float y = h[q] * os;
+                  ph[q] = __float2half_rn(y);
+                  pl[q] = __float2half_rn(y - __half2float(ph[q]));
+                }
+                __half* hp = p.H_hi + rw * p.ldh + col;
+                __half* lp = p.H_lo + rw * p.ldh + col;
+                if (vec_ok) {
+                  *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<const uint2*>(ph);
+                  *reinterpret_cast<uint2*>(lp) = *reinterpret_cast<const uint2*>(pl);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    if (col + q < p.N) {
+                      hp[q] = ph[q];
+                      lp[q] = pl[q];
+                    }
+                  }
+                }
+                if (!has_d) continue;
+              }
               float l[4] = {0.f, 0.f, 0.f, 0.f};
               if (has_lo) {
 #pragma unroll
@@ -741,16 +776,20 @@ extern "C" int lit_gemm_tf32x3_nt_batched(const float* A_hi, const float* A_lo, 
 // D = alpha * A B^T + beta * Cin on fp16 split pairs (lit_split_f16; one scale per row of A and per row of B, whose
 // inverses inv_a / inv_b the epilogue multiplies back in): three kind::f16 MMAs per k-step, twice the rate of the
 // 3xTF32 form at the same product accuracy.
-extern "C" int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
-                                 int M, int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D,
-                                 float* D_lo, long ldd, const float* inv_a, const float* inv_b, int variant,
-                                 void* stream) {
+static int gemm_f16x3(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb, int M,
+                      int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D, float* D_lo, long ldd,
+                      const float* inv_a, const float* inv_b, const float* out_scale, void* H_hi, void* H_lo, long ldh,
+                      int variant, void* stream) {
   LIT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "negative GEMM extent");
-  LIT_REQUIRE(ldd % 4 == 0 && ldd >= N, "output pitch must be a multiple of 4 floats and >= N");
+  LIT_REQUIRE(D || H_hi, "GEMM without an output");
+  LIT_REQUIRE(!D || (ldd % 4 == 0 && ldd >= N), "output pitch must be a multiple of 4 floats and >= N");
   LIT_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0, "output must be 16-byte aligned");
   LIT_REQUIRE(!Cin || (ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(Cin) & 15) == 0), "Cin alignment");
-  LIT_REQUIRE(!D_lo || (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0, "D_lo alignment");
+  LIT_REQUIRE(!D_lo || (D && (reinterpret_cast<uintptr_t>(D_lo) & 15) == 0), "D_lo alignment");
   LIT_REQUIRE(!inv_b || (reinterpret_cast<uintptr_t>(inv_b) & 15) == 0, "inv_b must be 16-byte aligned");
+  LIT_REQUIRE(!H_hi || (H_lo && out_scale && ldh % 4 == 0 && ldh >= N && (reinterpret_cast<uintptr_t>(H_hi) & 7) == 0 &&
+                        (reinterpret_cast<uintptr_t>(H_lo) & 7) == 0),
+              "fp16-pair output: both planes, the row scales, 8-byte alignment and a pitch that is a multiple of 4");
   if (M == 0 || N == 0) return LIT_OK;
   GemmParams p = {};
   p.M = M;
@@ -765,6 +804,10 @@ extern "C" int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, c
   p.beta = beta;
   p.scale_m = inv_a;
   p.scale_n = inv_b;
+  p.H_hi = static_cast<__half*>(H_hi);
+  p.H_lo = static_cast<__half*>(H_lo);
+  p.ldh = ldh;
+  p.out_scale = out_scale;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
   switch (variant) {
@@ -776,6 +819,28 @@ extern "C" int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, c
       set_error("unknown f16x3 GEMM variant %d", variant);
       return LIT_ERR_INVALID;
   }
+}
+
+extern "C" int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+                                 int M, int N, int K, float alpha, const float* Cin, long ldc, float beta, float* D,
+                                 float* D_lo, long ldd, const float* inv_a, const float* inv_b, int variant,
+                                 void* stream) {
+  LIT_REQUIRE(D, "output missing");
+  return gemm_f16x3(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, Cin, ldc, beta, D, D_lo, ldd, inv_a, inv_b, nullptr,
+                    nullptr, nullptr, 0, variant, stream);
+}
+
+// The same product with the result written as the scaled fp16 split pair (H_hi, H_lo; row scales out_scale) that the
+// next fp16-pair GEMM consumes, and optionally (D != NULL) as fp32 too: the downdated cross product of an inner fold
+// goes straight from this epilogue into the fused prediction + correlation GEMM without a lit_split_f16 pass.
+extern "C" int lit_gemm_f16x3_nt_pairout(const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
+                                         long ldb, int M, int N, int K, float alpha, const float* Cin, long ldc,
+                                         float beta, float* D, long ldd, const float* inv_a, const float* inv_b,
+                                         const float* out_scale, void* H_hi, void* H_lo, long ldh, int variant,
+                                         void* stream) {
+  LIT_REQUIRE(H_hi && H_lo && out_scale, "fp16-pair output missing");
+  return gemm_f16x3(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, alpha, Cin, ldc, beta, D, nullptr, ldd, inv_a, inv_b,
+                    out_scale, H_hi, H_lo, ldh, variant, stream);
 }
 
 // Shared body of the fused prediction + correlation entry points.  f16 = 0: 3xTF32 split pairs; 1: fp16 split pairs.

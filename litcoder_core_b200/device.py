@@ -499,6 +499,49 @@ class DeviceOps:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ fp16 pairs written by the producer
+    def col_reduce(self, src: Mat, idx, n: int, sumsq: bool = True, absmax: bool = False):
+        """(sum of squares, |max|) per column over the gathered rows (idx None: rows 0..n-1); device f32 vectors
+        (None for the one not asked for).  lit_gather_col_reduce."""
+        ss = self.vec(src.cols) if sumsq else None
+        am = self.vec(src.cols) if absmax else None
+        check(self.lib.lit_gather_col_reduce(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr() if idx is not None else 0),
+                                             n, src.cols, _vp(ss.data_ptr() if sumsq else 0),
+                                             _vp(am.data_ptr() if absmax else 0), _vp(self.stream)), "gather_col_reduce")
+        self.launches += 1
+        return ss, am
+
+    def row_absmax(self, src: Mat):
+        out = self.vec(src.rows)
+        check(self.lib.lit_row_absmax(_vp(src.hi.data_ptr()), src.ld, src.rows, src.cols, _vp(out.data_ptr()),
+                                      _vp(self.stream)), "row_absmax")
+        self.launches += 1
+        return out
+
+    def f16_bound_scales(self, n: int, absmax=None, row_sumsq=None, col_sumsq=None):
+        """(scale, inv_scale) device vectors of n power-of-two scales that put the bound
+        absmax + sqrt(row_sumsq * max(col_sumsq)) into [2^14, 2^15) (lit_f16_bound_scales)."""
+        scale, inv = self.vec(n), self.vec(n)
+        check(self.lib.lit_f16_bound_scales(
+            _vp(absmax.data_ptr() if absmax is not None else 0), _vp(row_sumsq.data_ptr() if row_sumsq is not None else 0),
+            _vp(col_sumsq.data_ptr() if col_sumsq is not None else 0), col_sumsq.numel() if col_sumsq is not None else 0,
+            n, _vp(scale.data_ptr()), _vp(inv.data_ptr()), _vp(self.stream)), "f16_bound_scales")
+        self.launches += 1
+        return scale, inv
+
+    def gather_rows_T_f16(self, src: Mat, idx, n: int, scales) -> MatF16:
+        """(cols x n) transpose of the gathered rows, written directly as the fp16 pair of scales[0][c] * value
+        (scales = f16_bound_scales of the column maxima of |src|): no fp32 intermediate, no lit_split_f16 pass."""
+        t = self.torch
+        ld = round_up(max(n, 1), 64)
+        hi = t.empty((max(src.cols, 1), ld), dtype=t.float16, device=self.device)
+        lo = t.empty((max(src.cols, 1), ld), dtype=t.float16, device=self.device)
+        check(self.lib.lit_gather_rows_transpose_f16(_vp(src.hi.data_ptr()), src.ld, _vp(idx.data_ptr()), n, src.cols,
+                                                     _vp(scales[0].data_ptr()), _vp(hi.data_ptr()), _vp(lo.data_ptr()),
+                                                     ld, _vp(self.stream)), "gather_rows_transpose_f16")
+        self.launches += 1
+        return MatF16(hi, lo, src.cols, n, ld, 1, scales[1])
+
     def gather_rows(self, src: Mat, idx, n: int, rows_out: Optional[int] = None, split: bool = False) -> Mat:
         rows_out = n if rows_out is None else rows_out
         out = self.empty(rows_out, src.cols, split=split)
@@ -576,27 +619,49 @@ class DeviceOps:
 
     def gemm(self, A: Mat, B: Mat, alpha: float = 1.0, Cin: Optional[Mat] = None, beta: float = 0.0,
              split_out: bool = False, out: Optional[Mat] = None, ld_out: Optional[int] = None,
-             precision: str = "tf32x3") -> Mat:
+             precision: str = "tf32x3", pair_out=None):
         """out[M,N] = alpha * A[M,K] @ B[N,K]^T + beta * Cin (A, B split pairs).
         precision "f16x3": the operands are re-split into scaled fp16 pairs (one power-of-two scale per row of A
-        and of B, lit_split_f16) and multiplied by lit_gemm_f16x3_nt, whose epilogue undoes the scales: the same
-        product accuracy at twice the tensor-core rate; pays for the large voxel-side products."""
+        and of B, lit_split_f16; an operand that already is a MatF16 is taken as it is) and multiplied by
+        lit_gemm_f16x3_nt, whose epilogue undoes the scales: the same product accuracy at twice the tensor-core
+        rate; pays for the large voxel-side products.
+        pair_out = (scale, inv_scale) of f16_bound_scales (f16x3 only): the result is written ONLY as the fp16 pair
+        of scale[row] * value, the A operand of the next fp16-pair GEMM (returns a MatF16)."""
         if precision not in ("tf32x3", "f16x3"):
             raise ValueError(f"gemm: unknown precision {precision!r}")
-        if precision == "tf32x3" and not (A.is_split and B.is_split):
+        if precision == "tf32x3" and not (isinstance(A, Mat) and isinstance(B, Mat) and A.is_split and B.is_split):
             raise ValueError("GEMM operands must be 3xTF32 split pairs")
+        if pair_out is not None and (precision != "f16x3" or split_out or out is not None):
+            raise ValueError("gemm: pair_out needs precision='f16x3' and no other output option")
         if A.cols != B.cols:
             raise ValueError(f"GEMM K mismatch: {A} x {B}")
         M, N, K = A.rows, B.rows, A.cols
-        if out is None:
+        t = self.torch
+        if pair_out is not None:
+            ldh = round_up(max(N, 1), 64)
+            out = MatF16(t.empty((max(M, 1), ldh), dtype=t.float16, device=self.device),
+                         t.empty((max(M, 1), ldh), dtype=t.float16, device=self.device), M, N, ldh, 1, pair_out[1])
+        elif out is None:
             out = self.empty(M, N, split=split_out, ld=ld_out)
         if M == 0 or N == 0:
             return out  # an empty voxel shard: nothing to launch
         if precision == "f16x3":
-            A, B = self.split_f16(A, 1), self.split_f16(B, 1)
+            A = A if isinstance(A, MatF16) else self.split_f16(A, 1)
+            B = B if isinstance(B, MatF16) else self.split_f16(B, 1)
+            if A.rows_per_group != 1 or B.rows_per_group != 1:
+                raise ValueError("gemm: fp16-pair operands need one scale per row")
         self._apply_sm_limit()
         with self.timed("gemm_f16" if isinstance(A, MatF16) else "gemm"):
-            if isinstance(A, MatF16):
+            if pair_out is not None:
+                variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256,
+                                                                     _lib.GEMM_2CTA_N256) else _lib.GEMM_AUTO
+                check(self.lib.lit_gemm_f16x3_nt_pairout(
+                    _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()), _vp(B.lo.data_ptr()), B.ld,
+                    M, N, K, alpha, _vp(Cin.hi.data_ptr() if Cin is not None else 0), Cin.ld if Cin is not None else 0,
+                    beta, _vp(0), 0, _vp(A.inv_scale.data_ptr()), _vp(B.inv_scale.data_ptr()),
+                    _vp(pair_out[0].data_ptr()), _vp(out.hi.data_ptr()), _vp(out.lo.data_ptr()), out.ld, variant,
+                    _vp(self.stream)), "gemm_f16x3_nt_pairout")
+            elif isinstance(A, MatF16):
                 variant = self.gemm_variant if self.gemm_variant in (_lib.GEMM_AUTO, _lib.GEMM_1CTA_N256,
                                                                      _lib.GEMM_2CTA_N256) else _lib.GEMM_AUTO
                 check(self.lib.lit_gemm_f16x3_nt(
@@ -672,8 +737,11 @@ class DeviceOps:
             else _lib.GEMM_AUTO
         flops = 2.0 * M * B.rows * K
         inv_row = inv_tile = None
+        if isinstance(A, MatF16) and (precision != "f16x3" or A.rows_per_group != 1):
+            raise ValueError("gemm_corr: an fp16-pair A operand needs precision='f16x3' and one scale per row")
         if precision == "f16x3":
-            A, B = self.split_f16(A, 1), self.split_f16(B, self.TILE_N)
+            A = A if isinstance(A, MatF16) else self.split_f16(A, 1)
+            B = self.split_f16(B, self.TILE_N)
             inv_row, inv_tile = A.inv_scale, B.inv_scale
         e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         self._timed.setdefault("gemm_corr", []).append((e0, e1))

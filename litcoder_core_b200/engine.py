@@ -95,6 +95,10 @@ class RidgeConfig:
     # alpha (batched Cholesky / Neumann polynomials, DeviceOps.outer_inverses) and ONE grouped GEMM over the voxels
     # sorted by their selected alpha (DeviceOps.gemm_grouped); no syevd is left on the default path
     direct_outer: bool = True
+    # fp16-pair GEMMs: operands that a kernel of ours produces (gathered response rows, downdated cross products) are
+    # written as scaled fp16 pairs by that kernel, with scales from a-priori bounds (DeviceOps.f16_bound_scales),
+    # instead of an fp32 plane that lit_split_f16 then reads twice
+    producer_pairs: bool = True
     # keep the fold-mean inner score curves (n_alphas x V_r per outer fold) for the caller (tests: near-tie proofs)
     record_scores: bool = False
 
@@ -553,6 +557,23 @@ class RidgeCVEngine:
     # ------------------------------------------------------------------------------------------
     # inner CV
     # ------------------------------------------------------------------------------------------
+    def _response_scales(self, Y):
+        """fp16-pair scales of the response COLUMNS from their |max| over all rows: a bound for every gathered subset
+        of rows, so that gather_rows_T_f16 needs no pass over its own output.  One reduction per response matrix."""
+        c = getattr(self, "_y_scales", None)
+        if c is None or c[0] is not Y:
+            _, am = self.ops.col_reduce(Y, None, Y.rows, sumsq=False, absmax=True)
+            c = self._y_scales = (Y, self.ops.f16_bound_scales(Y.cols, absmax=am))
+        return c[1]
+
+    def _response_rows_T(self, Y, idx, n: int, cfg: RidgeConfig, consumer: Optional[str] = None):
+        """(V_r x n) transposed gather of response rows in the form its consumer multiplies: an fp16 pair, one fp32
+        plane (re-split by the GEMM), or a TF32 pair.  consumer: precision of the GEMM (default: voxel GEMMs)."""
+        prec = cfg.voxel_gemm_precision if consumer is None else consumer
+        if prec == "f16x3" and cfg.producer_pairs:
+            return self.ops.gather_rows_T_f16(Y, idx, n, self._response_scales(Y))
+        return self.ops.gather_rows_T_split(Y, idx, n, split=prec != "f16x3")
+
     def _inner_scores(self, X, Y, sp, outer, inners, alphas_dev, n_alphas: int, cfg: RidgeConfig, all_rows=None):
         """Sum over inner folds of the (n_alphas x V_r) validation scores (ridge_corr_torch per fold).
         Also returns C_o^T (V_r x p fp32) for a primal outer fit (None when the outer fold is dual)."""
@@ -560,18 +581,19 @@ class RidgeCVEngine:
         vp = cfg.voxel_gemm_precision
         # operands of the fp16-pair GEMMs are re-split by lit_split_f16 anyway: produce them as ONE fp32 plane instead
         # of a TF32 pair (half the bytes written by the producer, half read -- twice -- by the re-split)
-        pair_y = vp != "f16x3"
         pair_ct = cfg.corr_precision != "f16x3"
+        fuse_ct = cfg.producer_pairs and vp == "f16x3" and cfg.corr_precision == "f16x3"
+        ct_absmax = None  # max_j |C_o^T[v][j]|, formed on the first downdated inner fold
         Ct_o = None
         if not outer["dual"] and all_rows is not None and sp.get("Ro") is not None:
             # C_o^T = C_all^T - Y_Ro^T X_Ro: the all-rows cross product is formed once per fit (fit_shard)
             n_ro = len(sp["Ro_rows"])
-            YRoT = ops.gather_rows_T_split(Y, sp["Ro"], n_ro, split=pair_y)  # (V_r x |Ro|)
+            YRoT = self._response_rows_T(Y, sp["Ro"], n_ro, cfg)  # (V_r x |Ro|)
             XRoT = ops.gather_rows_T_split(X, sp["Ro"], n_ro)  # (p x |Ro|)
             Ct_o = ops.gemm(YRoT, XRoT, alpha=-1.0, Cin=all_rows["Ct"], beta=1.0, precision=vp)
             del YRoT, XRoT
         elif not outer["dual"]:
-            YoT = ops.gather_rows_T_split(Y, sp["train"], len(sp["train_rows"]), split=pair_y)  # (V_r x n_o)
+            YoT = self._response_rows_T(Y, sp["train"], len(sp["train_rows"]), cfg)  # (V_r x n_o)
             Ct_o = ops.gemm(YoT, outer["XtT"], precision=vp)  # (V_r x p), K = n_o
             del YoT
         with ops.timed("phase_lbo_prepare"):
@@ -588,7 +610,7 @@ class RidgeCVEngine:
             if d["dual"] and d["cheb"]:
                 # dual GEMM-only fold: pred_a = [J K_vt (K_tt + a^2 I)^-1] Y_tr -- the stack lives in R^n and the
                 # "coefficients" are the training responses themselves (no cross product, no decomposition)
-                Zt = ops.gather_rows_T_split(Y, d["train"], n_tr, split=pair_ct)  # (V_r x n)
+                Zt = self._response_rows_T(Y, d["train"], n_tr, cfg, consumer=cfg.corr_precision)  # (V_r x n)
                 Lst = self._stack_from_blocks(X, d, n_alphas, rows_pad, cfg.alphas, cfg)
                 L = None
             elif d["dual"]:
@@ -605,12 +627,23 @@ class RidgeCVEngine:
             else:
                 # cross product of the inner training rows (downdated from the outer fold's when possible)
                 if d["R"] is not None:
-                    YRt = ops.gather_rows_T_split(Y, d["R"], len(d["R_rows"]), split=pair_y)  # (V_r x |R|)
-                    Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0,
-                                  split_out=pair_ct or not d["cheb"], precision=vp)
+                    n_r = len(d["R_rows"])
+                    YRt = self._response_rows_T(Y, d["R"], n_r, cfg)  # (V_r x |R|)
+                    if fuse_ct and d["cheb"]:
+                        # the downdate GEMM writes the fp16 pair the prediction GEMM reads; its row scales come
+                        # from |C_i^T[v][j]| <= max_j |C_o^T[v][j]| + |y_(v,R)|_2 max_j |x_(j,R)|_2
+                        if ct_absmax is None:
+                            ct_absmax = ops.row_absmax(Ct_o)
+                        scales = ops.f16_bound_scales(Y.cols, absmax=ct_absmax,
+                                                      row_sumsq=ops.col_reduce(Y, d["R"], n_r)[0],
+                                                      col_sumsq=ops.col_reduce(X, d["R"], n_r)[0])
+                        Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0, precision=vp, pair_out=scales)
+                    else:
+                        Ct = ops.gemm(YRt, d["XRt"], alpha=-1.0, Cin=Ct_o, beta=1.0,
+                                      split_out=pair_ct or not d["cheb"], precision=vp)
                     del YRt
                 else:
-                    YtT = ops.gather_rows_T_split(Y, d["train"], n_tr, split=pair_y)
+                    YtT = self._response_rows_T(Y, d["train"], n_tr, cfg)
                     Ct = ops.gemm(YtT, d["XtT"], split_out=pair_ct or not d["cheb"], precision=vp)
                     del YtT
                 if d["cheb"]:
@@ -747,6 +780,7 @@ class RidgeCVEngine:
         alphas = ops.upload_vector(np.asarray(cfg.alphas, dtype=np.float64), "f64")
         corr, _ = self._inner_scores(XX, YY, sp, outer, inners, alphas, len(cfg.alphas), cfg)
         self._eig_ready(outer)  # consume the (unused) outer ticket
+        self._y_scales = None
         return corr
 
     def ridge_weights(self, X, Y, alpha_v, cfg: RidgeConfig):
@@ -816,7 +850,7 @@ class RidgeCVEngine:
         X (N x p) and Y (N x V_r) are device matrices.  In train/test mode there is one plan whose
         test_rows index X_test / Y_test; in nested mode test rows index X / Y themselves."""
         ops = self.ops
-        self._best_idx = None
+        self._best_idx = self._y_scales = None
         alphas = np.asarray(cfg.alphas, dtype=np.float64)
         alphas_f32 = ops.upload_vector(alphas.astype(np.float32), "f32")
         alphas_f64 = ops.upload_vector(alphas, "f64")
@@ -844,7 +878,7 @@ class RidgeCVEngine:
             # (Y is then streamed once + 1/5 per outer fold instead of 4/5 per outer fold)
             with ops.timed("phase_cross_all"):
                 idx_all = ops.stage_indices([np.arange(X.rows, dtype=np.int64)])[0]
-                YaT = ops.gather_rows_T_split(Y, idx_all, X.rows, split=cfg.voxel_gemm_precision != "f16x3")
+                YaT = self._response_rows_T(Y, idx_all, X.rows, cfg)
                 XaT = ops.gather_rows_T_split(X, idx_all, X.rows)
                 all_rows = {"Ct": ops.gemm(YaT, XaT, precision=cfg.voxel_gemm_precision)}
                 del YaT, XaT
@@ -872,6 +906,7 @@ class RidgeCVEngine:
             res.p.append(p)
             res.alpha.append(alpha_v)
             res.n_test.append(len(plan.test_rows))
+        self._y_scales = None  # holds a reference to the response matrix
         return res
 
     def weights_matrix(self, res: ShardResult):

@@ -343,6 +343,7 @@ class NestedCVModel:
 
         cfg.direct_solver = os.environ.get("LIT_DIRECT_SOLVER", "1") != "0"  # development override
         cfg.direct_outer = os.environ.get("LIT_DIRECT_OUTER", "1") != "0"  # development override
+        cfg.producer_pairs = os.environ.get("LIT_PRODUCER_PAIRS", "1") != "0"  # development override
         engine = RidgeCVEngine(ops, comm)
         with ops.timed("fit"):
             res = engine.fit_shard(X, Y, plans, cfg, X_test=Xt, Y_test=Yt, n_vox_total=n_vox, y_ready=y_ready)

@@ -34,6 +34,14 @@ class FMat:
         return self.a.shape[1]
 
 
+class FPair(FMat):
+    """Mirror of device.MatF16 with one scale per row: `a` holds what the pair keeps, (hi + lo) / s."""
+
+    def __init__(self, a, scales):
+        super().__init__(a, split=False)
+        self.rows_per_group, self.scales = 1, scales
+
+
 class FakeSeriesStack:
     """Mirror of device.SeriesStack."""
 
@@ -132,6 +140,43 @@ class FakeOps:
     def gather_rows_T_split(self, src, idx, n, split=True):
         return FMat(src.a[np.asarray(idx[:n], dtype=np.int64)].T, split=split)
 
+    # ---- fp16 pairs written by the producer (lit_gather_col_reduce / lit_row_absmax / lit_f16_bound_scales / ...)
+    def col_reduce(self, src, idx, n, sumsq=True, absmax=False):
+        rows = src.a[:n] if idx is None else src.a[np.asarray(idx[:n], dtype=np.int64)]
+        self.launches += 1
+        ss = (rows.astype(np.float64) ** 2).sum(0).astype(F32) if sumsq else None
+        am = (np.abs(rows).max(0) if n else np.zeros(src.cols, dtype=F32)) if absmax else None
+        return ss, am
+
+    def row_absmax(self, src):
+        self.launches += 1
+        return np.abs(src.a).max(1) if src.cols else np.zeros(src.rows, dtype=F32)
+
+    def f16_bound_scales(self, n, absmax=None, row_sumsq=None, col_sumsq=None):
+        assert (row_sumsq is None) == (col_sumsq is None) and (absmax is not None or row_sumsq is not None)
+        bound = np.zeros(n, dtype=F32) if absmax is None else np.asarray(absmax[:n], dtype=F32).copy()
+        if row_sumsq is not None:
+            bound = bound + np.sqrt(np.asarray(row_sumsq[:n], dtype=F32) * F32(np.max(col_sumsq) if len(col_sumsq) else 0))
+        bound = (bound * F32(1 + 2.0 ** -10)).astype(F32)
+        scale = np.ones(n, dtype=F32)
+        ok = np.isfinite(bound) & (bound > 0)
+        scale[ok] = np.ldexp(F32(1.0), np.clip(15 - np.frexp(bound[ok])[1], -100, 100)).astype(F32)
+        self.launches += 1
+        return scale, (F32(1.0) / scale).astype(F32)
+
+    @staticmethod
+    def _pair_with_scales(a, scale):
+        """(hi + lo) / s of the fp16 pair of s * a with the given row scales; overflow would show up as inf."""
+        y = (np.asarray(a, dtype=F32) * scale[:, None]).astype(F32)
+        assert not y.size or np.nanmax(np.abs(y[np.isfinite(y)]), initial=0.0) < 65504.0, "fp16 overflow: the scale bound failed"
+        hi = y.astype(np.float16)
+        lo = (y - hi.astype(F32)).astype(np.float16)
+        return ((hi.astype(np.float64) + lo.astype(np.float64)) / scale[:, None].astype(np.float64)).astype(F32)
+
+    def gather_rows_T_f16(self, src, idx, n, scales):
+        self.launches += 1
+        return FPair(self._pair_with_scales(src.a[np.asarray(idx[:n], dtype=np.int64)].T, scales[0]), scales)
+
     def gather_rows(self, src, idx, n, rows_out=None, split=False):
         rows_out = n if rows_out is None else rows_out
         out = np.zeros((rows_out, src.cols), dtype=F32)
@@ -228,11 +273,16 @@ class FakeOps:
         return FMat(out, split)
 
     # ------------------------------------------------------------------ GEMMs
-    def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None, precision="tf32x3"):
+    def gemm(self, A, B, alpha=1.0, Cin=None, beta=0.0, split_out=False, out=None, ld_out=None, precision="tf32x3",
+             pair_out=None):
         assert precision == "f16x3" or (A.is_split and B.is_split), "3xTF32 GEMM operands must be split pairs"
         assert A.cols == B.cols and precision in ("tf32x3", "f16x3")
+        assert precision == "f16x3" or not (isinstance(A, FPair) or isinstance(B, FPair))
+        assert pair_out is None or (precision == "f16x3" and not split_out and out is None)
         if precision == "f16x3":  # lit_gemm_f16x3_nt: what the scaled fp16 pairs keep of the operands
-            d = alpha * (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, 1).T)
+            va = A.a.astype(np.float64) if isinstance(A, FPair) else self._f16_pair_value(A.a, 1)
+            vb = B.a.astype(np.float64) if isinstance(B, FPair) else self._f16_pair_value(B.a, 1)
+            d = alpha * (va @ vb.T)
             self.f16_gemms = getattr(self, "f16_gemms", 0) + 1
         else:
             d = alpha * (A.a.astype(np.float64) @ B.a.astype(np.float64).T)
@@ -240,6 +290,9 @@ class FakeOps:
             d = d + beta * Cin.a.astype(np.float64)
         self.launches += 1
         self.gemm_flops += 2.0 * A.rows * B.rows * A.cols
+        if pair_out is not None:  # lit_gemm_f16x3_nt_pairout
+            self.pair_out_gemms = getattr(self, "pair_out_gemms", 0) + 1
+            return FPair(self._pair_with_scales(d.astype(F32), pair_out[0]), pair_out)
         return FMat(d.astype(F32), split_out)
 
     @staticmethod
@@ -274,8 +327,10 @@ class FakeOps:
         assert rows_per_group % self.TILE_N == 0 and B.rows == n_plain * rows_per_group + n_st * self.TILE_N
         assert Yz.rows == rows_per_group and Yz.cols == A.rows and A.cols == B.cols
         assert precision in ("tf32x3", "f16x3")
+        assert not isinstance(A, FPair) or precision == "f16x3"
         if precision == "f16x3":
-            acc = (self._f16_pair_value(A.a, 1) @ self._f16_pair_value(B.a, self.TILE_N).T).astype(F32)
+            va = A.a.astype(np.float64) if isinstance(A, FPair) else self._f16_pair_value(A.a, 1)
+            acc = (va @ self._f16_pair_value(B.a, self.TILE_N).T).astype(F32)
         else:
             acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][stacked row]
         tpg = rows_per_group // self.PART_N

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in litridge.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototype table and header disagree"
     loaded = _lib.load()
-    assert loaded.lit_abi_version() == _lib.ABI_VERSION == 5
+    assert loaded.lit_abi_version() == _lib.ABI_VERSION == 6
     assert loaded.lit_last_error() is not None
 
 

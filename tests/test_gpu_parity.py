@@ -965,6 +965,103 @@ def test_split_f16_is_bit_exact(ops):
             assert np.all(np.abs(got - x) <= tol)
 
 
+def test_producer_written_f16_pairs(ops):
+    """The kernels that let a producer write fp16 pairs directly (no lit_split_f16 pass): column reductions, row
+    maxima and bound scales bit for bit against their NumPy restatement (tests/fake_ops.py); the fp16 gather-transpose
+    and the pair-output GEMM epilogue against the same restatement applied to what the fp32 kernels produce."""
+    from fake_ops import FakeOps, FMat
+    fake = FakeOps()
+    rng = np.random.default_rng(17)
+    for N, V, p, n_r in [(700, 333, 70, 150), (1200, 1030, 256, 301), (300, 64, 8, 1)]:
+        Y = (rng.standard_normal((N, V)) * np.exp(rng.uniform(-6, 6, (1, V)))).astype(np.float32)
+        Y[:, 3] = 0.0
+        Y[:, 5] = 7.25  # a constant column
+        X = rng.standard_normal((N, p)).astype(np.float32)
+        idx = np.sort(rng.choice(N, n_r, replace=False))
+        Yd, Xd, idx_d = ops.upload_matrix(Y), ops.upload_matrix(X), ops.upload_index(idx)
+        # column reductions
+        ss, am = ops.col_reduce(Yd, idx_d, n_r, sumsq=True, absmax=True)
+        ss_w, am_w = fake.col_reduce(FMat(Y), idx, n_r, sumsq=True, absmax=True)
+        np.testing.assert_array_equal(ops.download(am)[:V], am_w)
+        np.testing.assert_allclose(ops.download(ss)[:V], ss_w, rtol=2e-6)
+        _, am_all = ops.col_reduce(Yd, None, N, sumsq=False, absmax=True)
+        np.testing.assert_array_equal(ops.download(am_all)[:V], np.abs(Y).max(0))
+        # response scales: a bound for every subset of rows, at most one binade above the subset's own scale
+        ys = ops.f16_bound_scales(V, absmax=am_all)
+        ys_w = fake.f16_bound_scales(V, absmax=np.abs(Y).max(0))
+        np.testing.assert_array_equal(ops.download(ys[0])[:V], ys_w[0])
+        np.testing.assert_array_equal(ops.download(ys[1])[:V], ys_w[1])
+        assert ys_w[0][3] == 1.0 and np.all(np.abs(Y).max(0) * ys_w[0] < 2.0 ** 15)
+        # gathered + transposed response rows as fp16 pairs
+        T = ops.gather_rows_T_f16(Yd, idx_d, n_r, ys)
+        assert T.rows == V and T.cols == n_r and T.ld % 64 == 0
+        hi, lo = T.hi.cpu().numpy().astype(np.float64), T.lo.cpu().numpy().astype(np.float64)
+        assert not hi[:V, n_r:].any() and not lo[:V, n_r:].any()  # zero-filled pad columns
+        got = (hi + lo)[:V, :n_r] * ys_w[1][:, None].astype(np.float64)
+        np.testing.assert_array_equal(got.astype(np.float32), fake._pair_with_scales(Y[idx].T, ys_w[0]))
+        # the downdate with a pair-output epilogue: C_i^T = C_o^T - Y_R^T X_R
+        Ct_o = (Y.T.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
+        Cd = ops.upload_matrix(Ct_o)
+        np.testing.assert_array_equal(ops.download(ops.row_absmax(Cd))[:V], np.abs(Ct_o).max(1))
+        sc = ops.f16_bound_scales(V, absmax=ops.row_absmax(Cd), row_sumsq=ss, col_sumsq=ops.col_reduce(Xd, idx_d, n_r)[0])
+        sc_w = fake.f16_bound_scales(V, absmax=np.abs(Ct_o).max(1), row_sumsq=ops.download(ss)[:V],
+                                     col_sumsq=ops.download(ops.col_reduce(Xd, idx_d, n_r)[0])[:p])
+        np.testing.assert_array_equal(ops.download(sc[0])[:V], sc_w[0])
+        XRt = ops.gather_rows_T_split(Xd, idx_d, n_r)
+        D = ops.gemm(T, XRt, alpha=-1.0, Cin=Cd, beta=1.0, precision="f16x3")  # fp32 result of the same product
+        H = ops.gemm(T, XRt, alpha=-1.0, Cin=Cd, beta=1.0, precision="f16x3", pair_out=sc)
+        d = ops.download_matrix(D)
+        hi, lo = H.hi.cpu().numpy().astype(np.float64), H.lo.cpu().numpy().astype(np.float64)
+        assert np.isfinite(hi).all() and np.isfinite(lo).all() and np.abs(hi).max() < 2.0 ** 15
+        got = ((hi + lo)[:V, :p] * sc_w[1][:, None].astype(np.float64)).astype(np.float32)
+        np.testing.assert_array_equal(got, fake._pair_with_scales(d, sc_w[0]))
+        exact = Ct_o.astype(np.float64) - Y[idx].T.astype(np.float64) @ X[idx].astype(np.float64)
+        bound = 1.0 / sc_w[0].astype(np.float64) * 2.0 ** 15  # the scaled bound sits below 2^15
+        assert np.all(np.abs(exact).max(1) <= bound)
+        assert np.all(np.abs(got - d) <= np.maximum(np.abs(d) * 2.0 ** -21, bound[:, None] * 2.0 ** -39))
+        # ... and the fused prediction GEMM takes that pair as it is
+        R = 256
+        B = rng.standard_normal((R, p)).astype(np.float32)
+        Yz = rng.standard_normal((R, V)).astype(np.float32)
+        parts = ops.gemm_corr(H, _split(ops, B), 1, R, ops.upload_matrix(Yz), precision="f16x3")
+        ref = ops.gemm_corr(D, _split(ops, B), 1, R, ops.upload_matrix(Yz), precision="f16x3")
+        for name, pw in (("dot", 1), ("ssq", 2)):
+            va = getattr(parts, name).cpu().numpy()[:, :V] * parts.inv_row.cpu().numpy()[:V].astype(np.float64) ** pw
+            vb = getattr(ref, name).cpu().numpy()[:, :V] * ref.inv_row.cpu().numpy()[:V].astype(np.float64) ** pw
+            assert np.all(np.abs(va - vb).max(0) <= 2e-5 * np.abs(vb).max(0) + 1e-30), name
+    # NaN / inf responses keep scale 1 (and propagate, as in lit_split_f16)
+    Y = rng.standard_normal((40, 9)).astype(np.float32)
+    Y[3, 2], Y[7, 4] = np.nan, np.inf
+    _, am = ops.col_reduce(ops.upload_matrix(Y), None, 40, sumsq=False, absmax=True)
+    s = ops.download(ops.f16_bound_scales(9, absmax=am)[0])[:9]
+    assert s[2] == 1.0 and s[4] == 1.0 and np.all(s[[0, 1, 3]] > 1.0)
+
+
+def test_producer_pairs_agree_on_fit(ops, monkeypatch):
+    """Whole fit with and without the producer-written fp16 pairs: same alphas up to near-ties, same r and weights."""
+    from litcoder_core_b200 import NestedCVModel
+
+    rng = np.random.default_rng(23)
+    X, Y = _synthetic(rng, 900, 128, 1100)
+    Y[:, 7] = 3.0  # constant voxel
+    Y[:, 11] *= 1e4
+    kw = dict(n_outer_folds=3, n_inner_folds=3, chunk_length=10, alphas=np.logspace(-1, 8, 20))
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("LIT_PRODUCER_PAIRS", flag)
+        random.seed(3)
+        model = NestedCVModel("ridge_regression", ops=ops)
+        n0 = ops.launches
+        m, w, a = model.fit_predict(X, Y, **kw)
+        out[flag] = (np.asarray(m["correlations"]), w, np.asarray(a), ops.launches - n0)
+    same = out["1"][2] == out["0"][2]
+    assert same.mean() > 0.97, same.mean()
+    assert np.abs(out["1"][0][same] - out["0"][0][same]).max() < 2e-5
+    w1, w0 = out["1"][1][:, same], out["0"][1][:, same]
+    assert np.abs(w1 - w0).max() < 2e-5 * np.abs(w0).max()
+    assert out["1"][3] != out["0"][3]  # the two routes really differ
+
+
 def test_gemm_corr_f16x3_matches_fp64(ops):
     """The fp16-split form of the fused GEMM: partial sums (after undoing the scales) against fp64, at the
     accuracy of the 3xTF32 form, for badly scaled rows and long K."""

@@ -512,6 +512,9 @@ def test_engine_on_the_baseline_alpha_grid_matches_reference_golden(name, solver
     # the 4 small alphas of every inner fold go through the batched direct (Cholesky) solver, all folds at once
     assert getattr(ops, "direct_solved", 0) == (4 * (3 if tt else 12) if solver == "auto" else 0)
     assert getattr(ops, "lbo_solved", 0) == 0
+    # ... and every downdated cross product leaves its GEMM as the fp16 pair the prediction GEMM reads
+    # (a fold whose removed rows outnumber its training rows forms the product directly instead)
+    assert (getattr(ops, "pair_out_gemms", 0) >= (2 if tt else 8)) == (solver == "auto")
     info = check_against_reference_golden(name, model.last_fold_results, m, w, va)
     assert info["disagreeing_alphas"] <= 0.05 * info["voxel_folds"]
 
