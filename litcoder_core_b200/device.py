@@ -314,15 +314,19 @@ class DeviceOps:
     def upload_matrix_bg(self, host, col_start: int = 0, col_stop: Optional[int] = None):
         """upload_matrix for the responses: returns (Mat, ticket) at once; the copy runs on the copy stream behind
         the work already queued on the current stream and must be awaited with wait_copy(ticket).
-        A large PAGEABLE float32 array (what a drop-in caller passes) would make cudaMemcpy2DAsync block the calling
-        thread at ~10 GB/s, so a helper thread stages it through three page-locked 64 MB buffers -- filled by 4 threads
-        in parallel -- and issues truly asynchronous copies: the upload then overlaps the design side of the fit."""
+        A helper thread feeds the copy engine 64 MB at a time, never more than two chunks ahead:
+        * a large PAGEABLE float32 array (what a drop-in caller passes) would make cudaMemcpy2DAsync block the
+          calling thread at ~10 GB/s, so it is staged through three page-locked buffers filled by 4 threads;
+        * a PAGE-LOCKED array is copied in place, but still chunk by chunk: one 3.6 GB cudaMemcpy2DAsync occupies
+          the host-to-device copy engine for 65 ms, and the first small upload of the design side (fold indices,
+          alphas) queued behind it -- the whole design phase then ran after the responses instead of beside them.
+        Either way the upload overlaps the design side of the fit."""
         t = self.torch
         arr = host if isinstance(host, np.ndarray) else None
         big = (arr is not None and arr.ndim == 2 and arr.dtype == np.float32 and arr.flags.c_contiguous
-               and arr.shape[0] * ((arr.shape[1] if col_stop is None else col_stop) - col_start) * 4 >= self.BG_UPLOAD_MIN_BYTES
-               and self.lib.lit_host_pointer_kind(_vp(arr.ctypes.data)) == 0)
-        if not big:
+               and arr.shape[0] * ((arr.shape[1] if col_stop is None else col_stop) - col_start) * 4 >= self.BG_UPLOAD_MIN_BYTES)
+        kind = self.lib.lit_host_pointer_kind(_vp(arr.ctypes.data)) if big else 2
+        if kind not in (0, 1):
             with self.copy_stream() as ticket:
                 out = self.upload_matrix(np.asarray(host), col_start, col_stop)
             return out, ticket
@@ -341,36 +345,40 @@ class DeviceOps:
             ticket.issued.set()
             return out, ticket
         threading.Thread(target=self._bg_upload, name="litridge-h2d", daemon=True,
-                         args=(arr, col_start, cols, out, ticket)).start()
+                         args=(arr, col_start, cols, out, ticket, kind == 1)).start()
         return out, ticket
 
-    def _bg_upload(self, arr, col_start: int, cols: int, out: Mat, ticket) -> None:
+    def _bg_upload(self, arr, col_start: int, cols: int, out: Mat, ticket, page_locked: bool = False) -> None:
         from concurrent.futures import ThreadPoolExecutor
 
         t = self.torch
         try:
             t.cuda.set_device(self.device)
-            if getattr(self, "_bg_bufs", None) is None:
+            if not page_locked and getattr(self, "_bg_bufs", None) is None:
                 self._bg_bufs = [t.empty((self.BG_CHUNK_BYTES // 4,), dtype=t.float32, pin_memory=True) for _ in range(3)]
                 self._bg_pool = ThreadPoolExecutor(self.BG_COPY_THREADS, thread_name_prefix="litridge-stage")
             stream = self._copy_stream
             n = arr.shape[0]
             rows_per = max(1, (self.BG_CHUNK_BYTES // 4) // cols)
-            free = [None] * len(self._bg_bufs)
+            free = [None] * 3
             for k, r0 in enumerate(range(0, n, rows_per)):
-                b = k % len(self._bg_bufs)
+                b = k % len(free)
                 if free[b] is not None:
-                    free[b].synchronize()  # the DMA that last read this staging buffer has finished
+                    free[b].synchronize()  # chunk k - 3 is through: its staging buffer is free, the queue stays short
                 nr = min(rows_per, n - r0)
-                view = self._bg_bufs[b].numpy()[: nr * cols].reshape(nr, cols)
-                step = -(-nr // self.BG_COPY_THREADS)
-                futs = [self._bg_pool.submit(np.copyto, view[s0:min(s0 + step, nr)],
-                                             arr[r0 + s0:r0 + min(s0 + step, nr), col_start:col_start + cols])
-                        for s0 in range(0, nr, step)]
-                for f in futs:
-                    f.result()
-                check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr() + r0 * out.ld * 4), out.ld * 4, _vp(view.ctypes.data),
-                                             cols * 4, cols * 4, nr, 1, _vp(stream.cuda_stream)), "memcpy_2d(H2D)")
+                if page_locked:
+                    src, pitch = arr.ctypes.data + (r0 * arr.shape[1] + col_start) * 4, arr.shape[1] * 4
+                else:
+                    view = self._bg_bufs[b].numpy()[: nr * cols].reshape(nr, cols)
+                    step = -(-nr // self.BG_COPY_THREADS)
+                    futs = [self._bg_pool.submit(np.copyto, view[s0:min(s0 + step, nr)],
+                                                 arr[r0 + s0:r0 + min(s0 + step, nr), col_start:col_start + cols])
+                            for s0 in range(0, nr, step)]
+                    for f in futs:
+                        f.result()
+                    src, pitch = view.ctypes.data, cols * 4
+                check(self.lib.lit_memcpy_2d(_vp(out.hi.data_ptr() + r0 * out.ld * 4), out.ld * 4, _vp(src), pitch,
+                                             cols * 4, nr, 1, _vp(stream.cuda_stream)), "memcpy_2d(H2D)")
                 free[b] = t.cuda.Event()
                 free[b].record(stream)
             ticket.done = t.cuda.Event()
@@ -472,6 +480,25 @@ class DeviceOps:
     def download(self, t) -> np.ndarray:
         self.d2h_bytes += t.numel() * t.element_size()
         return t.detach().cpu().numpy()
+
+    def download_matrix_start(self, m: Mat):
+        """download_matrix in two halves: the copy into page-locked memory is queued now (current stream); the
+        returned callable waits for it and hands out the ndarray.  The caller keeps `m` alive until then and does
+        host-only work in between (the metrics dictionary of a fit is ~10 ms of list building)."""
+        out = self.torch.empty((m.rows, m.cols), dtype=self.torch.float32, pin_memory=True).numpy()
+        done = None
+        if m.rows and m.cols:
+            check(self.lib.lit_memcpy_2d(_vp(out.ctypes.data), m.cols * 4, _vp(m.hi.data_ptr()), m.ld * 4, m.cols * 4,
+                                         m.rows, 2, _vp(self.stream)), "memcpy_2d(D2H)")
+            done = self.torch.cuda.Event()
+            done.record()
+            self.d2h_bytes += out.nbytes
+
+        def finish(keep=m):
+            if done is not None:
+                done.synchronize()
+            return out
+        return finish
 
     def download_matrix(self, m: Mat) -> np.ndarray:
         """D2H of the logical [rows][cols] block (hi + lo for split pairs is NOT applied here)."""

@@ -385,16 +385,24 @@ class NestedCVModel:
                 ld = -(-n_vox // 32) * 32
                 full = comm.all_gather_cols_device(Wd.hi[:, : Wd.cols], counts, ld)
                 W = ops.download_matrix(type(Wd)(full, None, Wd.rows, n_vox))
+            elif comm.world > 1 and gather_weights:
+                W = comm.all_gather_concat(ops.download_matrix(Wd), counts)
+            elif hasattr(ops, "download_matrix_start"):
+                W = None  # this rank's block: copied while the host builds the metrics (below)
             else:
                 W = ops.download_matrix(Wd)
-                if comm.world > 1 and gather_weights:
-                    W = comm.all_gather_concat(W, counts)
         del res
         t_w = (time.perf_counter() - t_w0) * 1e3
 
         t_s0 = time.perf_counter()
         with ops.timed("stats"):
             masks, comb_p, sig, padj = engine.significance(p_f, cfg)
+        w_finish = None
+        if W is None:
+            # after the device statistics (their small copies must not queue behind 1.2 GB of weights), before the
+            # host-only part: the D2H of the weights runs while the metrics dictionary is built
+            with ops.timed("d2h"):
+                w_finish = ops.download_matrix_start(Wd)
 
         if train_test_mode:
             best = self._single_alpha_values(a_f, alphas, single_dtype)[0] if single_alpha else a_f[0]
@@ -414,6 +422,11 @@ class NestedCVModel:
         if scores is not None:
             self.last_fold_results["inner_scores"] = scores
         t_stats_end = time.perf_counter()
+        if w_finish is not None:
+            t_w0 = time.perf_counter()
+            W = w_finish()
+            t_w += (time.perf_counter() - t_w0) * 1e3
+        del Wd
         self.last_timings = ops.timings()
         self.last_timings["wall_ms"] = (time.perf_counter() - t_start) * 1e3
         self.last_timings["host_weights_ms"] = t_w

@@ -854,6 +854,26 @@ def test_pageable_responses_are_staged_in_the_background(ops):
     finally:
         ops.BG_UPLOAD_MIN_BYTES = saved
     np.testing.assert_array_equal(ops.download_matrix(block), Y[:, 4096:4096 + 70_003])
+    # a page-locked source goes through the same helper thread, copied in place chunk by chunk (so that the small
+    # uploads of the design side are not queued behind one multi-GB copy)
+    Yp = torch.empty((N, V), dtype=torch.float32, pin_memory=True)
+    Yp.copy_(torch.from_numpy(Y))
+    Ypn = Yp.numpy()
+    assert ops.lib.lit_host_pointer_kind(Ypn.ctypes.data) == 1
+    full, ticket = ops.upload_matrix_bg(Ypn)
+    ops.wait_copy(ticket)
+    np.testing.assert_array_equal(ops.download_matrix(full), Y)
+    ops.BG_UPLOAD_MIN_BYTES = 64 << 20
+    try:
+        block, ticket = ops.upload_matrix_bg(Ypn, 4096, 4096 + 70_003)
+        ops.wait_copy(ticket)
+    finally:
+        ops.BG_UPLOAD_MIN_BYTES = saved
+    np.testing.assert_array_equal(ops.download_matrix(block), Y[:, 4096:4096 + 70_003])
+    random.seed(1)
+    m3, w3, a3 = L.fit_nested_cv(features=X, targets=Ypn, **kw)
+    np.testing.assert_array_equal(a3, a2)
+    np.testing.assert_array_equal(w3, w2)
 
 
 def test_fit_predict_eig_solver_matches_reference_golden(ops):
