@@ -309,14 +309,14 @@ class DeviceOps:
 
     BG_UPLOAD_MIN_BYTES = 256 << 20  # pageable float32 blocks at least this large are uploaded by a helper thread
     BG_CHUNK_BYTES = 64 << 20
-    BG_COPY_THREADS = 4
+    BG_COPY_THREADS = max(2, min(8, (os.cpu_count() or 4) // 2))  # 4 threads staged 25 GB/s on the 16-core bench host
 
     def upload_matrix_bg(self, host, col_start: int = 0, col_stop: Optional[int] = None):
         """upload_matrix for the responses: returns (Mat, ticket) at once; the copy runs on the copy stream behind
         the work already queued on the current stream and must be awaited with wait_copy(ticket).
         A helper thread feeds the copy engine 64 MB at a time, never more than two chunks ahead:
         * a large PAGEABLE float32 array (what a drop-in caller passes) would make cudaMemcpy2DAsync block the
-          calling thread at ~10 GB/s, so it is staged through three page-locked buffers filled by 4 threads;
+          calling thread at ~10 GB/s, so it is staged through three page-locked buffers filled by BG_COPY_THREADS threads;
         * a PAGE-LOCKED array is copied in place, but still chunk by chunk: one 3.6 GB cudaMemcpy2DAsync occupies
           the host-to-device copy engine for 65 ms, and the first small upload of the design side (fold indices,
           alphas) queued behind it -- the whole design phase then ran after the responses instead of beside them.
