@@ -98,10 +98,7 @@ int lit_gemm_f16x3_nt(const void* A_hi, const void* A_lo, long lda, const void* 
  * T_q = Q_q A[v]^T.  Every alpha of the series is then a 4-term combination (lit_corr_finalize_series) instead of
  * its own block of stacked rows: 16 of the 20 BASELINE alphas cost 4 row blocks.  The first n_groups *
  * rows_per_group rows are ordinary alpha groups (dot_part / ssq_part as in lit_gemm_tf32x3_nt_corr).
- * precision: 0 = 3xTF32 split pairs (float planes), 1 = fp16 split pairs (lit_split_f16); + 2 (2-CTA variants): the
- * terms q = 2, 3 of the series tiles are multiplied with ONE MMA per k-step (hi x hi, 2^-11 relative) instead of
- * three -- their weight in a prediction is at most 60^-q of the leading term (the series serves a^2 >= 60 lambda_max),
- * so a score moves by < 1e-7, below the series' own truncation error; a series tile then costs 2/3 of the MMAs.
+ * precision: 0 = 3xTF32 split pairs (float planes), 1 = fp16 split pairs (lit_split_f16).
  * Replaces the per-alpha loop of ridge_corr_torch (ridge_regression.py:115-133) for all alphas of a fold at once. */
 int lit_gemm_corr_series(int precision, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo,
                          long ldb, int M, int n_groups, int rows_per_group, int n_series_tiles, int K, const float* Yz,

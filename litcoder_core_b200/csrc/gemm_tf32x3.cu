@@ -85,13 +85,6 @@ struct GemmParams {
   // points and emits the 4 sums T_q y and the 10 sums T_q T_q' (q <= q') into series_part[part*14 + j][ld_part].
   int series_tile0;
   float* series_part;
-  // series_coarse != 0 (2-CTA kernels): the terms q = 2, 3 of a series tile get ONE MMA per k-step (hi x hi) instead
-  // of three.  Their weight in a prediction is at most (lambda_max / a^2)^q <= 60^-q of the leading term, so the
-  // 2^-11 relative product error of a single fp16 / TF32 MMA enters a score below 1e-7 (q = 2) and 3e-9 (q = 3),
-  // under the truncation error (60^-4) the series already carries.  A series tile is then four N = 128 MMAs per
-  // k-step instead of three N = 256 ones: each CTA's B rows 0..63 (q = 0, 1 of its 32 time points) accumulate into
-  // TMEM columns [0, 128), rows 64..127 (q = 2, 3) into columns [128, 256).
-  int series_coarse;
   // Batched launches (EPI_STORE): `batch` equally shaped problems; operand b lives at base + b * stride (the
   // strides of A and B are part of their 3-D tensor maps), D / D_lo at + b * bs_d floats, Cin at + b * bs_c.
   int batch;
@@ -247,15 +240,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       // ======================= MMA issuer =======================
       if (lane == 0 && cta_rank == 0) {
         constexpr uint32_t idesc = F16 ? ptx::umma_idesc_f16(S::BM * CG, BN) : ptx::umma_idesc_tf32(S::BM * CG, BN);
-        constexpr uint32_t idesc_half =
-            F16 ? ptx::umma_idesc_f16(S::BM * CG, BN / 2) : ptx::umma_idesc_tf32(S::BM * CG, BN / 2);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t cc = 0;  // running chunk counter: TMEM buffer = cc & 1
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
           int b, mt, nt, kb_begin;
           if (batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin) < 0) continue;
-          const bool coarse_tile = EPI == EPI_CORR && CG == 2 && p.series_coarse && nt >= p.series_tile0;
           for (int kb0 = kb_begin; kb0 < p.num_k_blocks; kb0 += p.kc_blocks, ++cc) {
             const uint32_t buf = cc & 1u;
             ptx::mbar_wait(&tmem_empty_bar[buf], ((cc >> 1) & 1u) ^ 1u);
@@ -275,19 +265,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
                 const uint64_t dal = ptx::umma_desc_k_sw128(a_lo + koff);
                 const uint64_t dbh = ptx::umma_desc_k_sw128(b_hi + koff);
                 const uint64_t dbl = ptx::umma_desc_k_sw128(b_lo + koff);
-                const uint32_t fresh = (uint32_t)((kb != kb0) | (ks != 0));
-                if constexpr (EPI == EPI_CORR && CG == 2 && BN == 256) {
-                  if (coarse_tile) {
-                    // rows 64..127 of each CTA's B tile (8 swizzle atoms of 1 KB further on): the coarse terms
-                    const uint64_t dbc = ptx::umma_desc_k_sw128(b_hi + 64 * 128 + koff);
-                    ptx::umma_split<CG, F16>(d_tmem, dal, dbh, idesc_half, fresh);
-                    ptx::umma_split<CG, F16>(d_tmem, dah, dbl, idesc_half, 1u);
-                    ptx::umma_split<CG, F16>(d_tmem, dah, dbh, idesc_half, 1u);
-                    ptx::umma_split<CG, F16>(d_tmem + 128, dah, dbc, idesc_half, fresh);
-                    continue;
-                  }
-                }
-                ptx::umma_split<CG, F16>(d_tmem, dal, dbh, idesc, fresh);
+                ptx::umma_split<CG, F16>(d_tmem, dal, dbh, idesc, (uint32_t)((kb != kb0) | (ks != 0)));
                 ptx::umma_split<CG, F16>(d_tmem, dah, dbl, idesc, 1u);
                 ptx::umma_split<CG, F16>(d_tmem, dah, dbh, idesc, 1u);
               }
@@ -321,7 +299,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       int b, mt, nt, kb_begin;
       if (batch_tile_coords<BN, S::BK>(p, tile, b, mt, nt, kb_begin) < 0) continue;
       const int num_chunks = (p.num_k_blocks - kb_begin + p.kc_blocks - 1) / p.kc_blocks;
-      const bool coarse_cols = EPI == EPI_CORR && CG == 2 && BN == 256 && p.series_coarse && nt >= p.series_tile0;
       if constexpr (EPI == EPI_STORE) {
         // Cin of this tile towards L2 now: it is read only after the tile's MMAs, several microseconds from here
         if (p.Cin) {
@@ -341,14 +318,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
         const uint32_t buf = cc & 1u;
         ptx::mbar_wait(&tmem_full_bar[buf], (cc >> 1) & 1u);
         ptx::tc_fence_after();
-        // (coarse series tiles: this half's q = 0, 1 sit in columns 64 half .., its q = 2, 3 in 128 + 64 half ..)
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + (coarse_cols ? half * 64 : half * COLS);
-        const uint32_t jstride = coarse_cols ? 128 : 64;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * BN + half * COLS;
 #pragma unroll
         for (int j = 0; j < COLS / 64; ++j) {
           float v0[32], v1[32];
-          ptx::tmem_ld_32x32(taddr + j * jstride, v0);
-          ptx::tmem_ld_32x32(taddr + j * jstride + 32, v1);
+          ptx::tmem_ld_32x32(taddr + j * 64, v0);
+          ptx::tmem_ld_32x32(taddr + j * 64 + 32, v1);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -869,7 +844,7 @@ extern "C" int lit_gemm_f16x3_nt_pairout(const void* A_hi, const void* A_lo, lon
 }
 
 // Shared body of the fused prediction + correlation entry points.  f16 = 0: 3xTF32 split pairs; 1: fp16 split pairs.
-static int corr_gemm(int mode, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
+static int corr_gemm(int f16, const void* A_hi, const void* A_lo, long lda, const void* B_hi, const void* B_lo, long ldb,
                      int M, int n_groups, int rows_per_group, int n_series_tiles, int K, const float* Yz, long ldy,
                      float* dot_part, float* ssq_part, float* series_part, long ld_part, int variant, void* stream) {
   LIT_REQUIRE(M >= 0 && n_groups >= 0 && rows_per_group >= 0 && K >= 0 && n_series_tiles >= 0, "negative extent");
@@ -891,8 +866,6 @@ static int corr_gemm(int mode, const void* A_hi, const void* A_lo, long lda, con
   p.ld_part = ld_part;
   p.series_tile0 = (int)(n_plain / 256);
   p.series_part = series_part;
-  p.series_coarse = (mode >> 1) & 1;
-  const int f16 = mode & 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (variant == LIT_GEMM_AUTO) variant = M > 128 ? LIT_GEMM_2CTA_N256 : LIT_GEMM_1CTA_N256;
   switch (variant) {
@@ -934,7 +907,7 @@ extern "C" int lit_gemm_corr_series(int precision, const void* A_hi, const void*
                                     const void* B_lo, long ldb, int M, int n_groups, int rows_per_group,
                                     int n_series_tiles, int K, const float* Yz, long ldy, float* dot_part,
                                     float* ssq_part, float* series_part, long ld_part, int variant, void* stream) {
-  LIT_REQUIRE(precision >= 0 && precision <= 3, "corr_series: precision must be 0 (tf32x3) or 1 (f16x3), + 2 = coarse terms");
+  LIT_REQUIRE(precision == 0 || precision == 1, "corr_series: precision must be 0 (tf32x3) or 1 (f16x3)");
   return corr_gemm(precision, A_hi, A_lo, lda, B_hi, B_lo, ldb, M, n_groups, rows_per_group, n_series_tiles, K, Yz, ldy,
                    dot_part, ssq_part, series_part, ld_part, variant, stream);
 }

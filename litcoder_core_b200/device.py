@@ -307,9 +307,6 @@ class DeviceOps:
             self.launches += 1
         return out
 
-    # series tiles of the fused GEMM: single-MMA products for the two highest-order terms (development override)
-    series_coarse = os.environ.get("LIT_SERIES_COARSE", "1") != "0"
-
     BG_UPLOAD_MIN_BYTES = 256 << 20  # pageable float32 blocks at least this large are uploaded by a helper thread
     BG_CHUNK_BYTES = 64 << 20
     BG_COPY_THREADS = max(2, min(8, (os.cpu_count() or 4) // 2))  # 4 threads staged 25 GB/s on the 16-core bench host
@@ -778,10 +775,8 @@ class DeviceOps:
         self._corr_log.append((e0, e1, flops))
         self._apply_sm_limit()
         e0.record()
-        # + 2: the q = 2, 3 terms of the series tiles get one MMA per k-step (see litridge.h); 2-CTA launches only
-        mode = int(precision == "f16x3") | (2 if (n_st and self.series_coarse) else 0)
         check(self.lib.lit_gemm_corr_series(
-            mode, _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()),
+            int(precision == "f16x3"), _vp(A.hi.data_ptr()), _vp(A.lo.data_ptr()), A.ld, _vp(B.hi.data_ptr()),
             _vp(B.lo.data_ptr()), B.ld, M, n_plain, rows_per_group, n_st, K, _vp(Yz.hi.data_ptr()), Yz.ld,
             _vp(dot.data_ptr()), _vp(ssq.data_ptr()), _vp(series.data_ptr() if n_st else 0), ld, variant,
             _vp(self.stream)), "gemm_corr_series")

@@ -296,7 +296,7 @@ class FakeOps:
         return FMat(d.astype(F32), split_out)
 
     @staticmethod
-    def _f16_pair_value(a, rows_per_group, hi_only=False):
+    def _f16_pair_value(a, rows_per_group):
         """What lit_split_f16 keeps of `a`: hi = fp16(s a), lo = fp16(s a - hi), one power-of-two scale per row
         group with the group maximum in [2^14, 2^15); returns (hi + lo) / s as float64."""
         a = np.asarray(a, dtype=F32)
@@ -312,8 +312,6 @@ class FakeOps:
             with np.errstate(over="ignore"):
                 hi = y.astype(np.float16)
                 lo = (y - hi.astype(F32)).astype(np.float16)
-            if hi_only:
-                lo = np.zeros_like(lo)
             out[g * rows_per_group:(g + 1) * rows_per_group] = (hi.astype(np.float64) + lo.astype(np.float64)) / float(s)
         return out
 
@@ -333,13 +331,6 @@ class FakeOps:
         if precision == "f16x3":
             va = A.a.astype(np.float64) if isinstance(A, FPair) else self._f16_pair_value(A.a, 1)
             acc = (va @ self._f16_pair_value(B.a, self.TILE_N).T).astype(F32)
-            if n_st and getattr(self, "series_coarse", True) and A.rows > 128:
-                # 2-CTA launches: rows 64..127 of each half tile (the terms q = 2, 3) see hi x hi only
-                r = np.arange(B.rows)
-                coarse = (r >= n_plain * rows_per_group) & ((r % 128) >= 64)
-                a_hi = self._f16_pair_value(A.a, 1, hi_only=True)
-                b_hi = self._f16_pair_value(B.a, self.TILE_N, hi_only=True)
-                acc[:, coarse] = (a_hi @ b_hi[coarse].T).astype(F32)
         else:
             acc = (A.a.astype(np.float64) @ B.a.astype(np.float64).T).astype(F32)  # [voxel][stacked row]
         tpg = rows_per_group // self.PART_N
