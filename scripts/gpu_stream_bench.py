@@ -73,6 +73,16 @@ def main():
     timeit("group_plan: counting sort of V voxels by alpha index (1 block)", V * 4 * 3, lambda: ops.group_plan(idx, V, A))
     timeit("gather_rows C^T by alpha group (V x 3072 f32 -> hi/lo, padded)", V * p * 4 * 3, lambda: ops.gather_rows(Ct, perm, cap, split=True))
 
+    # round 2, later: fp16 pairs written by their producers (bounds instead of passes over the data)
+    timeit("gather_col_reduce |max| of Y over all 9400 rows (once per fit)", N * V * 4,
+           lambda: ops.col_reduce(Y, None, N, sumsq=False, absmax=True))
+    ysc = ops.f16_bound_scales(V, absmax=ops.col_reduce(Y, None, N, sumsq=False, absmax=True)[1])
+    timeit("gather_col_reduce sum of squares of Y[1500 rows]", n_v * V * 4, lambda: ops.col_reduce(Y, va, n_v))
+    timeit("gather_col_reduce sum of squares of X[1500 rows] (3072 columns)", n_v * p * 4, lambda: ops.col_reduce(X, va, n_v))
+    timeit("row_absmax C^T (V x 3072)", V * p * 4, lambda: ops.row_absmax(Ct))
+    timeit("gather_rows_transpose_f16 Y[1500 rows] -> (V x 1500) fp16 hi/lo", n_v * V * (4 + 4), lambda: ops.gather_rows_T_f16(Y, va, n_v, ysc))
+    timeit("gather_rows_transpose_f16 Y[9400 rows] -> (V x 9400) fp16 hi/lo", N * V * (4 + 4), lambda: ops.gather_rows_T_f16(Y, ops.upload_index(np.arange(N)), N, ysc), reps=3)
+
     # feature construction: device-resident buffers through the C ABI (the API-level calls add H2D/D2H)
     nt, D = 9400, 768
     stim = torch.randn((nt, D), device="cuda")
