@@ -12,6 +12,7 @@
 //   * large alphas (a^2 >> lambda_max) by the truncated Neumann series in the shared powers P_c G^q.
 // The per-step scalars are computed on the host from lambda_max (control flow only).
 #include "common.cuh"
+#include <cstdlib>
 #include "ptx_sm100.cuh"
 #include "../../include/litridge.h"
 
@@ -337,7 +338,8 @@ static int lanczos_batch(const float* const* G, int batch, long ld, int n, int s
                          double* scal_scratch, float* lam_out_f32, double* lam_out_f64, cudaStream_t s,
                          double rel_tol = 0.0) {
   const long scal_stride = 2L * steps + 4;
-  if (!lam_out_f64) rel_tol = 0.0;
+  static const bool fixed = getenv("LIT_LANCZOS_FIXED") != nullptr;  // development knob: always run all the steps
+  if (!lam_out_f64 || fixed) rel_tol = 0.0;
   for (int b0 = 0; b0 < batch; b0 += LANCZOS_MAX_BATCH) {
     const int nb = batch - b0 < LANCZOS_MAX_BATCH ? batch - b0 : LANCZOS_MAX_BATCH;
     MatPtrs ptrs = {};
