@@ -264,9 +264,7 @@ int lit_lanczos_lambda_max(const float* G, long ld, int n, int steps, float* vec
                            float* lam_out_f32, double* lam_out_f64, void* stream);
 /* The same for `batch` matrices of one size at once (one launch per Lanczos step for all of them): G is a HOST
  * array of device pointers (all n x n, pitch ld); vec_scratch: batch * 3*n floats; scal_scratch:
- * batch * (2*steps + 4) doubles; lam_out_f64: batch doubles.  steps <= n is the MAXIMUM: from step 40 on the Ritz
- * values are read back every 8 steps (the call synchronises `stream` there) and the recurrence ends once none of
- * them moved by more than 1e-8 (relative) over 8 steps -- below the accuracy the fp32 products give S[0]^2. */
+ * batch * (2*steps + 4) doubles; lam_out_f64: batch doubles.  steps <= n. */
 int lit_lanczos_lambda_max_batched(const float* const* G, int batch, long ld, int n, int steps, float* vec_scratch,
                                    double* scal_scratch, double* lam_out_f64, void* stream);
 /* `batch` equally shaped products D_b = alpha * A_b B_b^T + beta * Cin_b in ONE launch (3xTF32 split pairs):

@@ -12,7 +12,6 @@
 //   * large alphas (a^2 >> lambda_max) by the truncated Neumann series in the shared powers P_c G^q.
 // The per-step scalars are computed on the host from lambda_max (control flow only).
 #include "common.cuh"
-#include <cstdlib>
 #include "ptx_sm100.cuh"
 #include "../../include/litridge.h"
 
@@ -136,13 +135,12 @@ __global__ void lanczos_step_kernel(float* __restrict__ vec, int o_y, int o_v, i
 
 // Largest eigenvalue of the symmetric tridiagonal (alpha[0..m), beta[1..m)) by Sturm multisection (fp64):
 // one warp evaluates 32 trial points per round (5 bits per round instead of 1).
-// m_layout: the step count the scalar scratch was laid out for (beta follows alpha[m_layout]); m <= m_layout steps done.
-__global__ void tridiag_lmax_kernel(const double* __restrict__ scal, long scal_stride, int m, int m_layout,
+__global__ void tridiag_lmax_kernel(const double* __restrict__ scal, long scal_stride, int m,
                                     float* __restrict__ out_f32, double* __restrict__ out_f64) {
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   const double* __restrict__ alpha = scal + (long)blockIdx.x * scal_stride + 2;
-  const double* __restrict__ beta = alpha + m_layout;
+  const double* __restrict__ beta = alpha + m;
   if (out_f32) out_f32 += blockIdx.x;
   if (out_f64) out_f64 += blockIdx.x;
   // an (almost) invariant subspace ends the recurrence early: keep the leading block
@@ -330,16 +328,9 @@ __global__ void series_stack_kernel(PolySources src, long ld_src, long rows, lon
 
 using namespace lit;
 
-// rel_tol > 0 (needs lam_out_f64): from step 40 on the Ritz value is read back every 8 steps (one small copy + stream
-// synchronisation each) and the recurrence stops once no matrix of the batch moved by more than rel_tol (relative)
-// over the last 8 steps -- on the BASELINE design (top eigenvalues 0.8 % apart) that is step 56 of 96, at the 1e-9
-// floor the fp32 matrix-vector products set anyway.
 static int lanczos_batch(const float* const* G, int batch, long ld, int n, int steps, float* vec_scratch,
-                         double* scal_scratch, float* lam_out_f32, double* lam_out_f64, cudaStream_t s,
-                         double rel_tol = 0.0) {
+                         double* scal_scratch, float* lam_out_f32, double* lam_out_f64, cudaStream_t s) {
   const long scal_stride = 2L * steps + 4;
-  static const bool fixed = getenv("LIT_LANCZOS_FIXED") != nullptr;  // development knob: always run all the steps
-  if (!lam_out_f64 || fixed) rel_tol = 0.0;
   for (int b0 = 0; b0 < batch; b0 += LANCZOS_MAX_BATCH) {
     const int nb = batch - b0 < LANCZOS_MAX_BATCH ? batch - b0 : LANCZOS_MAX_BATCH;
     MatPtrs ptrs = {};
@@ -354,36 +345,17 @@ static int lanczos_batch(const float* const* G, int batch, long ld, int n, int s
     const int rows_per_block = 8;
     const int gblocks = (n + rows_per_block - 1) / rows_per_block;
     int o_v = 0, o_prev = 1;  // roles of the three work vectors (offset 2 holds y)
-    double now[LANCZOS_MAX_BATCH], prev[LANCZOS_MAX_BATCH];
-    bool have_prev = false, converged = false;
-    for (int j = 0; j < steps && !converged; ++j) {
+    for (int j = 0; j < steps; ++j) {
       sym_gemv_dot_kernel<<<dim3(gblocks, nb), rows_per_block * 32, 0, s>>>(ptrs, ld, n, vec, o_v, 2, scal, scal_stride);
       lanczos_step_kernel<<<nb, 1024, 0, s>>>(vec, 2, o_v, o_prev, n, j, steps, scal, scal_stride);
       const int tmp = o_v;  // v_{j+1} was written over v_{j-1}
       o_v = o_prev;
       o_prev = tmp;
-      const int done = j + 1;
-      if (rel_tol > 0.0 && done >= 40 && done % 8 == 0 && done < steps) {
-        tridiag_lmax_kernel<<<nb, 32, 0, s>>>(scal, scal_stride, done, steps, lam_out_f32 ? lam_out_f32 + b0 : nullptr,
-                                              lam_out_f64 + b0);
-        LIT_LAUNCH_CHECK();
-        LIT_CUDA_CHECK(cudaMemcpyAsync(now, lam_out_f64 + b0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, s));
-        LIT_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (have_prev) {
-          converged = true;
-          for (int b = 0; b < nb; ++b)
-            converged = converged && fabs(now[b] - prev[b]) <= rel_tol * fabs(now[b]);  // false for NaN
-        }
-        for (int b = 0; b < nb; ++b) prev[b] = now[b];
-        have_prev = true;
-      }
     }
     LIT_LAUNCH_CHECK();
-    if (!converged) {
-      tridiag_lmax_kernel<<<nb, 32, 0, s>>>(scal, scal_stride, steps, steps, lam_out_f32 ? lam_out_f32 + b0 : nullptr,
-                                            lam_out_f64 ? lam_out_f64 + b0 : nullptr);
-      LIT_LAUNCH_CHECK();
-    }
+    tridiag_lmax_kernel<<<nb, 32, 0, s>>>(scal, scal_stride, steps, lam_out_f32 ? lam_out_f32 + b0 : nullptr,
+                                          lam_out_f64 ? lam_out_f64 + b0 : nullptr);
+    LIT_LAUNCH_CHECK();
   }
   return LIT_OK;
 }
@@ -406,8 +378,7 @@ extern "C" int lit_lanczos_lambda_max_batched(const float* const* G /* host arra
   LIT_REQUIRE(steps <= n, "lanczos_lambda_max_batched: steps must not exceed n (the scratch layout depends on it)");
   LIT_REQUIRE(batch == 0 || (G && vec_scratch && scal_scratch && lam_out_f64), "lanczos_lambda_max_batched: null argument");
   if (batch == 0) return LIT_OK;
-  return lanczos_batch(G, batch, ld, n, steps, vec_scratch, scal_scratch, nullptr, lam_out_f64, (cudaStream_t)stream,
-                       1e-8);
+  return lanczos_batch(G, batch, ld, n, steps, vec_scratch, scal_scratch, nullptr, lam_out_f64, (cudaStream_t)stream);
 }
 
 extern "C" int lit_cheb_update(float* d, const float* r, float* x, float* t, float* d_hi, float* d_lo, long ld, long rows,

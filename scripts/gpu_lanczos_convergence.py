@@ -12,7 +12,6 @@ for p in (ROOT, os.path.join(ROOT, "scripts")):
 
 
 def main():
-    os.environ["LIT_LANCZOS_FIXED"] = "1"  # every call below runs exactly `steps` steps
     import torch
 
     import synth8d

@@ -583,10 +583,8 @@ def test_gemm_only_inner_solver_kernels(ops):
     mats = [ops.upload_matrix((G * (1.0 + 0.01 * i)).astype(np.float32)) for i in range(40)]
     single = np.array([float(ops.lambda_max(m).cpu()[0]) for m in mats[:3] + mats[-2:]])
     batched = ops.lambda_max_batched(mats).cpu().numpy()
-    # (the batched entry stops once no Ritz value moved by more than 1e-8 over 8 steps; the single one runs all 96)
-    np.testing.assert_allclose(batched[[0, 1, 2, 38, 39]], single, rtol=3e-8)
-    # a batch is only as fast as its slowest member: a white-noise Gram (clustered top eigenvalues) keeps the
-    # recurrence going, and the well-separated one next to it is unharmed
+    np.testing.assert_allclose(batched[[0, 1, 2, 38, 39]], single, rtol=1e-9)
+    # a slowly converging member (white-noise Gram: clustered top eigenvalues) next to a well-separated one
     Ws = rng.standard_normal((6000, p)).astype(np.float32)
     Gs = Ws.T.astype(np.float64) @ Ws.astype(np.float64)
     mixed = ops.lambda_max_batched([mats[0], ops.upload_matrix(Gs.astype(np.float32))]).cpu().numpy()
