@@ -13,3 +13,5 @@ print(d['phases_ms'])
 print(d['e2e_phases_ms'])
 print(d['result_check'])
 PY
+# full-scale parity of the final code (config 2 at V = 95,000; 8,192-voxel stripe against the CPU oracle)
+timeout 600 python scripts/gpu_fullscale_parity.py --out gpurun_out/final_fullscale_parity.json 2>&1 | tail -2 | cut -c1-1500
