@@ -309,7 +309,9 @@ class DeviceOps:
 
     BG_UPLOAD_MIN_BYTES = 256 << 20  # pageable float32 blocks at least this large are uploaded by a helper thread
     BG_CHUNK_BYTES = 64 << 20
-    BG_COPY_THREADS = max(2, min(8, (os.cpu_count() or 4) // 2))  # 4 threads staged 25 GB/s on the 16-core bench host
+    # staging threads per process: half the host cores, shared between the ranks of this node (torchrun's
+    # LOCAL_WORLD_SIZE); 4 threads staged 25 GB/s and 8 threads 38 GB/s on the 16-core bench host
+    BG_COPY_THREADS = max(2, min(8, (os.cpu_count() or 4) // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))))
 
     def upload_matrix_bg(self, host, col_start: int = 0, col_stop: Optional[int] = None):
         """upload_matrix for the responses: returns (Mat, ticket) at once; the copy runs on the copy stream behind
