@@ -199,48 +199,60 @@ bound_scales_kernel(const unsigned* __restrict__ absmax, const float* __restrict
 }
 
 // dst[c][r] = fp16 pair of scale[c] * src[row(r)][c]: the gathered, transposed response rows of a fold as the A
-// operand of an fp16-pair GEMM (one scale per voxel = per output row).  64 x 64 tile through shared memory; columns
-// r in [n_rows, n_rows_pad) are zero-filled.
+// operand of an fp16-pair GEMM (one scale per voxel = per output row).  A tile is 64 gathered rows x 128 source
+// columns through shared memory: 512-byte row segments on the way in, 128-byte segments of each fp16 plane on the way
+// out; columns r in [n_rows, n_rows_pad) are zero-filled.
+constexpr int TF16_R = 64, TF16_C = 128;
 __global__ void __launch_bounds__(256)
 transpose64_f16_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx, long n_rows,
                        long n_rows_pad, long cols, const float* __restrict__ scale, __half* __restrict__ dst_hi,
                        __half* __restrict__ dst_lo, long ld_dst, int vec) {
-  __shared__ float tile[64][65];
-  const long tiles_r = (n_rows_pad + 63) / 64;
-  const long tiles_c = (cols + 63) / 64;
+  extern __shared__ float tile_f16[];  // [TF16_R][TF16_C + 1]
+  constexpr int PITCH = TF16_C + 1;
+  const long tiles_r = (n_rows_pad + TF16_R - 1) / TF16_R;
+  const long tiles_c = (cols + TF16_C - 1) / TF16_C;
   const long total = tiles_r * tiles_c;
   for (long t = blockIdx.x; t < total; t += gridDim.x) {
     const long tr = t % tiles_r;  // consecutive blocks walk along the gathered rows
     const long tc = t / tiles_r;
-    const long r0 = tr * 64, c0 = tc * 64;
+    const long r0 = tr * TF16_R, c0 = tc * TF16_C;
     {
-      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 float4 column groups x 8 rows per pass
+      float4 v[TF16_R / 8];
 #pragma unroll
-      for (int k = 0; k < 64; k += 16) {
-        const long r = r0 + ty + k;
+      for (int k = 0; k < TF16_R / 8; ++k) {
+        const long r = r0 + ty + 8 * k;
         const long c = c0 + tx * 4;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n_rows && c < cols) {
           const long sr = idx ? (long)idx[r] : r;
           if (sr >= 0) {
             const float* sp = src + sr * ld_src + c;
             if (vec && c + 3 < cols) {
-              const float4 x = *reinterpret_cast<const float4*>(sp);
-              v[0] = x.x, v[1] = x.y, v[2] = x.z, v[3] = x.w;
+              v[k] = *reinterpret_cast<const float4*>(sp);
             } else {
-              for (int q = 0; q < 4 && c + q < cols; ++q) v[q] = sp[q];
+              v[k].x = sp[0];
+              if (c + 1 < cols) v[k].y = sp[1];
+              if (c + 2 < cols) v[k].z = sp[2];
+              if (c + 3 < cols) v[k].w = sp[3];
             }
           }
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tile[ty + k][tx * 4 + q] = v[q];
+      for (int k = 0; k < TF16_R / 8; ++k) {
+        float* row = tile_f16 + (ty + 8 * k) * PITCH + tx * 4;
+        row[0] = v[k].x;
+        row[1] = v[k].y;
+        row[2] = v[k].z;
+        row[3] = v[k].w;
       }
     }
     __syncthreads();
     {
-      const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 values (16 bytes per plane) per thread
+      const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 values (16 bytes per plane) per thread, 32 rows per pass
 #pragma unroll
-      for (int k = 0; k < 64; k += 32) {
+      for (int k = 0; k < TF16_C; k += 32) {
         const long c = c0 + ty + k;  // destination row
         const long r = r0 + tx * 8;  // destination column group
         if (c < cols && r < n_rows_pad) {
@@ -248,7 +260,7 @@ transpose64_f16_kernel(const float* __restrict__ src, long ld_src, const int32_t
           __align__(16) __half vh[8];
           __align__(16) __half vl[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) split_h(tile[tx * 8 + q][ty + k] * s, vh[q], vl[q]);
+          for (int q = 0; q < 8; ++q) split_h(tile_f16[(tx * 8 + q) * PITCH + ty + k] * s, vh[q], vl[q]);
           __half* oh = dst_hi + c * ld_dst + r;
           __half* ol = dst_lo + c * ld_dst + r;
           if (vec && r + 7 < n_rows_pad) {
@@ -351,9 +363,10 @@ extern "C" int lit_gather_rows_transpose_f16(const float* src, long ld_src, cons
   LIT_REQUIRE(scale && dst_hi && dst_lo, "gather_rows_transpose_f16: null pointer");
   if (cols == 0 || ld_dst == 0) return LIT_OK;
   const int vec = aligned16(src) && ld_src % 4 == 0 && aligned16(dst_hi) && aligned16(dst_lo) && ld_dst % 8 == 0;
-  const long tiles = ((ld_dst + 63) / 64) * ((cols + 63) / 64);
-  const long cap = (long)sm_count() * 16;
-  transpose64_f16_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, (cudaStream_t)stream>>>(
+  const long tiles = ((ld_dst + TF16_R - 1) / TF16_R) * ((cols + TF16_C - 1) / TF16_C);
+  const long cap = (long)sm_count() * 6;  // 33 KB of shared memory per block: 6 resident blocks per SM
+  constexpr int smem = TF16_R * (TF16_C + 1) * (int)sizeof(float);
+  transpose64_f16_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, smem, (cudaStream_t)stream>>>(
       src, ld_src, idx, n_idx, ld_dst, cols, scale, static_cast<__half*>(dst_hi), static_cast<__half*>(dst_lo), ld_dst,
       vec);
   LIT_LAUNCH_CHECK();
