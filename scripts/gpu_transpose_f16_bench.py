@@ -21,7 +21,7 @@ def main():
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6454.6
     rng = np.random.default_rng(0)
     # correctness (ragged widths, unaligned row counts)
-    for N, V, n in [(700, 333, 150), (300, 1030, 301), (90, 64, 1)]:
+    for N, V, n in [(700, 333, 150), (400, 1030, 301), (90, 64, 1)]:
         Y = (rng.standard_normal((N, V)) * np.exp(rng.uniform(-6, 6, (1, V)))).astype(np.float32)
         idx = np.sort(rng.choice(N, n, replace=False))
         sc = FakeOps().f16_bound_scales(V, absmax=np.abs(Y).max(0))
