@@ -199,29 +199,29 @@ bound_scales_kernel(const unsigned* __restrict__ absmax, const float* __restrict
 }
 
 // dst[c][r] = fp16 pair of scale[c] * src[row(r)][c]: the gathered, transposed response rows of a fold as the A
-// operand of an fp16-pair GEMM (one scale per voxel = per output row).  A tile is 64 gathered rows x 128 source
-// columns through shared memory: 512-byte row segments on the way in, 128-byte segments of each fp16 plane on the way
-// out; columns r in [n_rows, n_rows_pad) are zero-filled.
-constexpr int TF16_R = 64, TF16_C = 128;
+// operand of an fp16-pair GEMM (one scale per voxel = per output row).  64 x 64 tile through shared memory; columns
+// r in [n_rows, n_rows_pad) are zero-filled.  The tile has no padding: 16-byte groups are XOR-swizzled with
+// (row >> 3) & 7, which makes the float4 stores of the load phase and the scalar column reads of the store phase
+// (8 lanes x 8 rows apart, 4 adjacent columns) both bank-conflict-free.  (A 64 x 128 tile with a padded pitch and
+// scalar stores was measured slower: 0.305 vs 0.285 ms for the 1,500-row gather.)
 __global__ void __launch_bounds__(256)
 transpose64_f16_kernel(const float* __restrict__ src, long ld_src, const int32_t* __restrict__ idx, long n_rows,
                        long n_rows_pad, long cols, const float* __restrict__ scale, __half* __restrict__ dst_hi,
                        __half* __restrict__ dst_lo, long ld_dst, int vec) {
-  extern __shared__ float tile_f16[];  // [TF16_R][TF16_C + 1]
-  constexpr int PITCH = TF16_C + 1;
-  const long tiles_r = (n_rows_pad + TF16_R - 1) / TF16_R;
-  const long tiles_c = (cols + TF16_C - 1) / TF16_C;
+  __shared__ __align__(16) float tile[64 * 64];
+  const long tiles_r = (n_rows_pad + 63) / 64;
+  const long tiles_c = (cols + 63) / 64;
   const long total = tiles_r * tiles_c;
   for (long t = blockIdx.x; t < total; t += gridDim.x) {
     const long tr = t % tiles_r;  // consecutive blocks walk along the gathered rows
     const long tc = t / tiles_r;
-    const long r0 = tr * TF16_R, c0 = tc * TF16_C;
+    const long r0 = tr * 64, c0 = tc * 64;
     {
-      const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 float4 column groups x 8 rows per pass
-      float4 v[TF16_R / 8];
+      const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 float4 column groups x 16 rows per pass
+      float4 v[4];
 #pragma unroll
-      for (int k = 0; k < TF16_R / 8; ++k) {
-        const long r = r0 + ty + 8 * k;
+      for (int k = 0; k < 4; ++k) {
+        const long r = r0 + ty + 16 * k;
         const long c = c0 + tx * 4;
         v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r < n_rows && c < cols) {
@@ -240,27 +240,27 @@ transpose64_f16_kernel(const float* __restrict__ src, long ld_src, const int32_t
         }
       }
 #pragma unroll
-      for (int k = 0; k < TF16_R / 8; ++k) {
-        float* row = tile_f16 + (ty + 8 * k) * PITCH + tx * 4;
-        row[0] = v[k].x;
-        row[1] = v[k].y;
-        row[2] = v[k].z;
-        row[3] = v[k].w;
+      for (int k = 0; k < 4; ++k) {
+        const int row = ty + 16 * k;
+        *reinterpret_cast<float4*>(tile + row * 64 + ((tx ^ ((row >> 3) & 7)) << 2)) = v[k];
       }
     }
     __syncthreads();
     {
       const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;  // 8 values (16 bytes per plane) per thread, 32 rows per pass
 #pragma unroll
-      for (int k = 0; k < TF16_C; k += 32) {
-        const long c = c0 + ty + k;  // destination row
+      for (int k = 0; k < 64; k += 32) {
+        const int cl = ty + k;       // column inside the tile = destination row
+        const long c = c0 + cl;
         const long r = r0 + tx * 8;  // destination column group
         if (c < cols && r < n_rows_pad) {
           const float s = scale[c];
           __align__(16) __half vh[8];
           __align__(16) __half vl[8];
+          // rows 8 tx + q: (row >> 3) & 7 == tx for every q
+          const float* col = tile + tx * 8 * 64 + ((((cl >> 2) ^ tx) << 2) | (cl & 3));
 #pragma unroll
-          for (int q = 0; q < 8; ++q) split_h(tile_f16[(tx * 8 + q) * PITCH + ty + k] * s, vh[q], vl[q]);
+          for (int q = 0; q < 8; ++q) split_h(col[q * 64] * s, vh[q], vl[q]);
           __half* oh = dst_hi + c * ld_dst + r;
           __half* ol = dst_lo + c * ld_dst + r;
           if (vec && r + 7 < n_rows_pad) {
@@ -363,10 +363,9 @@ extern "C" int lit_gather_rows_transpose_f16(const float* src, long ld_src, cons
   LIT_REQUIRE(scale && dst_hi && dst_lo, "gather_rows_transpose_f16: null pointer");
   if (cols == 0 || ld_dst == 0) return LIT_OK;
   const int vec = aligned16(src) && ld_src % 4 == 0 && aligned16(dst_hi) && aligned16(dst_lo) && ld_dst % 8 == 0;
-  const long tiles = ((ld_dst + TF16_R - 1) / TF16_R) * ((cols + TF16_C - 1) / TF16_C);
-  const long cap = (long)sm_count() * 6;  // 33 KB of shared memory per block: 6 resident blocks per SM
-  constexpr int smem = TF16_R * (TF16_C + 1) * (int)sizeof(float);
-  transpose64_f16_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, smem, (cudaStream_t)stream>>>(
+  const long tiles = ((ld_dst + 63) / 64) * ((cols + 63) / 64);
+  const long cap = (long)sm_count() * 16;
+  transpose64_f16_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, (cudaStream_t)stream>>>(
       src, ld_src, idx, n_idx, ld_dst, cols, scale, static_cast<__half*>(dst_hi), static_cast<__half*>(dst_lo), ld_dst,
       vec);
   LIT_LAUNCH_CHECK();
