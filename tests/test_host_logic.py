@@ -268,6 +268,53 @@ def test_downdate_and_overlap_do_not_change_results(name):
     assert np.abs(w1[:, same] - w2[:, same]).max() <= 2e-5 * np.abs(w2).max()
 
 
+def test_bound_scales_cannot_overflow_fp16():
+    """The a-priori bounds behind the producer-written fp16 pairs (DeviceOps.f16_bound_scales, restated in
+    tests/fake_ops.py): gathered response rows never exceed the column maximum over all rows, and a downdated cross
+    product C_o^T - Y_R^T X_R never exceeds max_j |C_o^T[v][j]| + |y_(v,R)|_2 max_j |x_(j,R)|_2 -- also when the outer
+    cross product cancels to rounding noise, when a voxel is zero outside the removed rows, and with outliers."""
+    from fake_ops import FakeOps, FMat
+
+    ops = FakeOps()
+    rng = np.random.default_rng(12)
+    N, p, V, nR = 600, 40, 64, 130
+    X = rng.standard_normal((N, p)).astype(np.float32)
+    R = np.sort(rng.choice(N, nR, replace=False))
+    Y = rng.standard_normal((N, V)).astype(np.float32)
+    # voxel 0: orthogonal to every feature over all rows (C_o row = rounding noise), large on the removed rows
+    y0 = rng.standard_normal(N)
+    y0[R] *= 50.0
+    y0 -= X.astype(np.float64) @ np.linalg.lstsq(X.astype(np.float64), y0, rcond=None)[0]
+    Y[:, 0] = y0
+    Y[:, 1] = 0.0
+    Y[R, 1] = 1e4          # zero outside the removed rows
+    Y[R[3], 2] = 3e7       # one outlier inside the removed rows
+    Y[5, 3] = -2e6         # one outlier outside them
+    Y[:, 4] = 0.0          # all-zero voxel: scale 1
+    Y[:, 5] *= 1e-20       # tiny voxel
+    Ct_o = (Y.T.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
+    exact = Ct_o.astype(np.float64) - Y[R].T.astype(np.float64) @ X[R].astype(np.float64)
+    ys = ops.f16_bound_scales(V, absmax=ops.col_reduce(FMat(Y), None, N, sumsq=False, absmax=True)[1])
+    assert ys[0][4] == 1.0 and np.all(np.abs(Y).max(0) * ys[0] < 2.0 ** 15)
+    T = ops.gather_rows_T_f16(FMat(Y), R, nR, ys)  # asserts |scaled value| < 65504 inside
+    np.testing.assert_allclose(T.a[[0, 6, 7]], Y[R].T[[0, 6, 7]], rtol=2.0 ** -20)
+    sc = ops.f16_bound_scales(V, absmax=ops.row_absmax(FMat(Ct_o)), row_sumsq=ops.col_reduce(FMat(Y), R, nR)[0],
+                              col_sumsq=ops.col_reduce(FMat(X), R, nR)[0])
+    bound = 2.0 ** 15 / sc[0].astype(np.float64)
+    assert np.all(np.abs(exact).max(1) <= bound)  # the bound holds for every voxel, the adversarial ones included ...
+    ordinary = np.arange(V) >= 6
+    assert np.all(bound[ordinary] <= 2.0 ** 4 * np.abs(exact).max(1)[ordinary])  # ... and is tight for ordinary ones
+    H = ops.gemm(T, FMat(X[R].T.copy(), split=True), alpha=-1.0, Cin=FMat(Ct_o), beta=1.0, precision="f16x3",
+                 pair_out=sc)  # asserts no overflow inside
+    # what the pair keeps: 2^-21 of the element or 2^-39 of the bound, whichever is larger (lit_split_f16's contract
+    # with the bound in place of the row maximum) -- measured against the fp32 result the epilogue converts
+    d32 = (Ct_o.astype(np.float64) - T.a.astype(np.float64) @ ops._f16_pair_value(X[R].T, 1).T).astype(np.float32)
+    tol = np.maximum(np.abs(d32) * 2.0 ** -21, bound[:, None] * 2.0 ** -39)
+    assert np.all(np.abs(H.a.astype(np.float64) - d32) <= tol)
+    err = np.abs(H.a.astype(np.float64) - exact).max(1)
+    assert np.all(err[ordinary] <= 2e-6 * np.abs(exact).max(1)[ordinary])
+
+
 def test_engine_edge_cases_on_fake_ops():
     """Constant voxels (zero variance), duplicated voxels and a rank-deficient design."""
     rng = np.random.default_rng(3)
