@@ -579,8 +579,9 @@ class RidgeCVEngine:
         Also returns C_o^T (V_r x p fp32) for a primal outer fit (None when the outer fold is dual)."""
         ops = self.ops
         vp = cfg.voxel_gemm_precision
-        # operands of the fp16-pair GEMMs are re-split by lit_split_f16 anyway: produce them as ONE fp32 plane instead
-        # of a TF32 pair (half the bytes written by the producer, half read -- twice -- by the re-split)
+        # operands of the fp16-pair GEMMs: written as fp16 pairs by their producers where a bound on their magnitude is
+        # known beforehand (_response_rows_T, the downdate below), else as ONE fp32 plane that the GEMM re-splits (never
+        # as a TF32 pair: half the bytes written, half read -- twice -- by lit_split_f16)
         pair_ct = cfg.corr_precision != "f16x3"
         fuse_ct = cfg.producer_pairs and vp == "f16x3" and cfg.corr_precision == "f16x3"
         ct_absmax = None  # max_j |C_o^T[v][j]|, formed on the first downdated inner fold
